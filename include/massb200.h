@@ -1,0 +1,101 @@
+/*
+ * massb200.h -- C ABI of libmassb200.so: hand-written sm_100a CUDA kernels for the
+ * mapping-and-matching hot path of brandontrabucco/mass (MaSS).
+ *
+ * The reference has no FFI: its boundary for this path is a Python call surface
+ * (SURVEY.md 8b).  Each entry point below names the reference function it
+ * replaces (paths relative to /root/reference); mass_b200/ binds them with ctypes
+ * behind classes/functions that carry the reference's names and arguments.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; mb_last_error()
+ *     returns a thread-local message for the last failure on the calling thread;
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *     all work is enqueued asynchronously on it, nothing synchronises unless stated;
+ *   - the library owns no memory: scratch space is a caller-provided workspace whose
+ *     size comes from the matching *_workspace_bytes() function;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Map layout (reference: mass/nn/base_projection_layer.py:158-160, 339):
+ *   float map[S0 = map_height (y, flipped)][S1 = map_width (x)][S2 = map_depth (z)][F], F contiguous.
+ * Pose layout: 12 floats per frame = rotation R row-major (R[i][0] = (eye x up)[i],
+ *   R[i][1] = up[i], R[i][2] = -eye[i]; mass/utils/projection.py:104-105) followed by
+ *   the camera position (x, y, z).  R is produced on the host with the reference's own
+ *   ATen ops so that it is bit-identical to the reference CPU path.
+ */
+#ifndef MASSB200_H
+#define MASSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_OK 0
+#define MB_ERR_ARG 1
+#define MB_ERR_CUDA 2
+#define MB_ERR_WORKSPACE 3
+
+/* arithmetic mode of the voxel reduce */
+#define MB_MODE_EXACT 0 /* reference operation order, no FMA: map values bitwise equal to the CPU path  */
+#define MB_MODE_FAST 1  /* per-voxel affine form new = a*old + b: <= 1e-5 relative         */
+
+const char *mb_last_error(void);
+int mb_version(void);
+/* number of kernels this library has launched in the calling process (bench.py: gpu_launches) */
+uint64_t mb_launch_count(void);
+
+/* ---- a3: mass/utils/projection.py:77-110 transform_rays ----------------------------------
+ * out[p][i] = (rays[p][0]*R[i][0] + rays[p][1]*R[i][1]) + rays[p][2]*R[i][2], each product and sum
+ * rounded separately.  pose points at 12 floats (only R is read). */
+int mb_transform_rays(void *stream, const float *rays, int64_t npix, const float *pose, float *out);
+
+/* ---- a4: mass/utils/projection.py:113-230 bin_rays -----------------------------------------
+ * rays are ORIENTED rays [npix][3]; origin = 3 floats.  Valid pixels are compacted in row-major
+ * order.  Outputs sized npix; *count (device int64) receives N.  pix receives flat pixel ids
+ * (the reference's `indices`).  Axis 1 is flipped exactly as the reference does. */
+size_t mb_bin_rays_workspace_bytes(int64_t npix);
+int mb_bin_rays(void *stream, const float *bins0, int n0, const float *bins1, int n1,
+                const float *bins2, int n2, const float *origin, const float *rays,
+                const float *depth, int64_t npix, float min_ray_depth, float max_ray_depth,
+                int64_t *ind0, int64_t *ind1, int64_t *ind2, float *ratio0, float *ratio1,
+                float *ratio2, int64_t *pix, int64_t *count, void *workspace, size_t workspace_bytes);
+
+/* ---- a5: mass/utils/projection.py:233-351 update_feature_map -------------------------------
+ * Trilinear 8-neighbour splat + per-voxel weighted-average recurrence, in place on `map`
+ * [S0][S1][S2][F].  features is [npts][F].  Deterministic: contributions are radix-sorted by
+ * voxel key (stable, so the reference's slot-major/point order is kept) and reduced per voxel
+ * segment by one warp; no float atomics. */
+size_t mb_update_feature_map_workspace_bytes(int64_t npts, int S0, int S1, int S2);
+int mb_update_feature_map(void *stream, const int64_t *ind0, const int64_t *ind1, const int64_t *ind2,
+                          const float *ratio0, const float *ratio1, const float *ratio2,
+                          const float *features, int64_t npts, int F, float *map, int S0, int S1,
+                          int S2, float interpolation_weight, int mode, void *workspace,
+                          size_t workspace_bytes);
+
+/* ---- a6..a9: BaseProjectionLayer.update (mass/nn/base_projection_layer.py:282-343) ---------
+ * Fused unproject + voxelise + deterministic voxel reduce for T consecutive frames, applied in
+ * frame order (frames do not commute).
+ *   rays      [H*W][3]  camera-frame ray table (the layer's `rays` buffer)
+ *   depth     [T][H*W]
+ *   features  [T][fh*fw][F], nearest up-sampled to H x W by integer factors H/fh, W/fw
+ *             (repeat_interleave of lines 322-325); or NULL with class_ids != NULL
+ *   class_ids [T][H*W] int64 semantic ids: one-hot features without materialising them
+ *             (mass/nn/applications/semantic_projection_layer.py:203-214); else NULL
+ *   pose      [T][12]
+ *   bins_x/y/z edge tables with nx/ny/nz entries (map is [ny-1][nx-1][nz-1][F]) */
+size_t mb_layer_update_workspace_bytes(int H, int W, int nx, int ny, int nz, int T);
+int mb_layer_update(void *stream, const float *rays, const float *depth, const float *features,
+                    const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw,
+                    int F, const float *bins_x, int nx, const float *bins_y, int ny,
+                    const float *bins_z, int nz, float *map, float interpolation_weight,
+                    float min_ray_depth, float max_ray_depth, int mode, void *workspace,
+                    size_t workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MASSB200_H */

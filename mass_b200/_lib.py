@@ -1,0 +1,118 @@
+"""ctypes binding of libmassb200.so (the C ABI declared in include/massb200.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is
+missing it is built in-tree with nvcc for sm_100a, and if that is impossible the
+import of any hot-path function fails loudly.
+"""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(CSRC, "libmassb200.so")
+
+MODE_EXACT = 0
+MODE_FAST = 1
+
+_lib = None
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int
+_f32 = ctypes.c_float
+_sz = ctypes.c_size_t
+
+
+def build(force=False):
+    """Compile every CUDA source for sm_100a (see csrc/Makefile)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "massb200.h"))
+    stale = (not os.path.exists(SO_PATH) or
+             any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs))
+    if force or stale:
+        cmd = ["make", "-C", CSRC, "-j8"] + (["-B"] if force else [])
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("building libmassb200.so failed:\n" + proc.stdout[-4000:])
+    return SO_PATH
+
+
+_SIGNATURES = {
+    "mb_last_error": (ctypes.c_char_p, []),
+    "mb_version": (_i32, []),
+    "mb_launch_count": (ctypes.c_uint64, []),
+    "mb_transform_rays": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "mb_bin_rays_workspace_bytes": (_sz, [_i64]),
+    "mb_bin_rays": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _f32, _f32,
+                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),
+    "mb_update_feature_map_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
+    "mb_update_feature_map": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _i32,
+                                     _i32, _f32, _i32, _vp, _sz]),
+    "mb_layer_update_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "mb_layer_update": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32,
+                               _vp, _i32, _vp, _i32, _vp, _f32, _f32, _f32, _i32, _vp, _sz]),
+}
+
+
+def lib():
+    """Loads (building first if needed) the shared library; raises if impossible."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            build()
+        L = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError here = header/library mismatch
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().mb_last_error().decode("utf-8", "replace")
+        if rc == 1:
+            raise ValueError("libmassb200: " + msg)
+        raise RuntimeError("libmassb200 (status %d): %s" % (rc, msg))
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor that must already be CUDA + contiguous."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    if not t.is_cuda:
+        raise ValueError("mass_b200 kernels need CUDA tensors (there is no CPU path), got %s" % t.device)
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def require_cuda(device):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("mass_b200 runs on CUDA (sm_100a) only; the layer is on %s. "
+                           "Move it with .cuda() first -- there is no CPU fallback." % device)
+    return device
+
+
+class Workspace:
+    """A grow-only device scratch buffer owned by the caller side (torch allocator)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        return self.buf

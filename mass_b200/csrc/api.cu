@@ -1,0 +1,215 @@
+// extern "C" entry points of libmassb200.so (see include/massb200.h for the contract).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace {
+thread_local char g_error[512] = "";
+std::atomic<uint64_t> g_launches{0};
+}  // namespace
+
+void mb_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+void mb_count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+MB_API const char *mb_last_error(void) { return g_error; }
+MB_API int mb_version(void) { return 100; }
+MB_API uint64_t mb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// ---- a3 -------------------------------------------------------------------------------------
+MB_API int mb_transform_rays(void *stream, const float *rays, int64_t npix, const float *pose, float *out)
+{
+    MB_REQUIRE(rays && pose && out && npix >= 0, "mb_transform_rays: null pointer or negative size");
+    return mbk_transform_rays((cudaStream_t)stream, rays, npix, pose, out);
+}
+
+// ---- a4 -------------------------------------------------------------------------------------
+MB_API size_t mb_bin_rays_workspace_bytes(int64_t npix)
+{
+    if (npix <= 0) return 256;
+    return mb_align_up((size_t)npix * sizeof(uint32_t)) + mb_scan_workspace_bytes((uint32_t)npix) + 512;
+}
+
+MB_API int mb_bin_rays(void *stream_, const float *bins0, int n0, const float *bins1, int n1,
+                       const float *bins2, int n2, const float *origin, const float *rays,
+                       const float *depth, int64_t npix, float min_ray_depth, float max_ray_depth,
+                       int64_t *ind0, int64_t *ind1, int64_t *ind2, float *ratio0, float *ratio1,
+                       float *ratio2, int64_t *pix, int64_t *count, void *workspace, size_t workspace_bytes)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MB_REQUIRE(bins0 && bins1 && bins2 && origin && count, "mb_bin_rays: null pointer");
+    MB_REQUIRE(n0 >= 2 && n1 >= 2 && n2 >= 2, "mb_bin_rays: every edge table needs >= 2 entries");
+    MB_REQUIRE(npix >= 0 && npix < (int64_t)1 << 31, "mb_bin_rays: npix out of range");
+    if (npix == 0) {
+        MB_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(int64_t), stream));
+        return MB_OK;
+    }
+    MB_REQUIRE(rays && depth && ind0 && ind1 && ind2 && ratio0 && ratio1 && ratio2 && pix,
+               "mb_bin_rays: null pointer");
+    MB_REQUIRE(workspace && workspace_bytes >= mb_bin_rays_workspace_bytes(npix),
+               "mb_bin_rays: workspace too small (%zu < %zu)", workspace_bytes,
+               mb_bin_rays_workspace_bytes(npix));
+    MbArena arena(workspace, workspace_bytes);
+    uint32_t *flags = arena.take<uint32_t>((size_t)npix);
+    const size_t scan_bytes = mb_scan_workspace_bytes((uint32_t)npix);
+    char *scan_ws = arena.take<char>(scan_bytes);
+    int rc = mbk_bin_flags(stream, bins0, n0, bins1, n1, bins2, n2, origin, rays, depth, npix,
+                           min_ray_depth, max_ray_depth, flags);
+    if (rc) return rc;
+    rc = mb_exclusive_scan_u32(stream, flags, flags, (uint32_t)npix, scan_ws, scan_bytes);
+    if (rc) return rc;
+    return mbk_bin_write(stream, bins0, n0, bins1, n1, bins2, n2, origin, rays, depth, npix, min_ray_depth,
+                         max_ray_depth, flags, ind0, ind1, ind2, ratio0, ratio1, ratio2, pix, count);
+}
+
+// ---- shared back half: sort contributions by voxel, find segments, reduce -----------------------
+namespace {
+
+struct SplatBuffers {
+    uint32_t *keys_a, *keys_b, *vals_a, *vals_b, *heads, *counters;
+    float4 *pt_ratio;
+    char *sort_ws;
+    size_t sort_bytes;
+};
+
+size_t splat_workspace_bytes(uint32_t npts)
+{
+    MbArena a(nullptr, 0);
+    const size_t n = (size_t)npts * 8;
+    a.take<uint32_t>(n); a.take<uint32_t>(n); a.take<uint32_t>(n); a.take<uint32_t>(n);
+    a.take<uint32_t>(n);
+    a.take<uint32_t>(64);
+    a.take<float4>(npts);
+    a.take<char>(mb_sort_workspace_bytes((uint32_t)n));
+    return a.used + 256;
+}
+
+bool carve(SplatBuffers &b, void *workspace, size_t bytes, uint32_t npts)
+{
+    MbArena a(workspace, bytes);
+    const size_t n = (size_t)npts * 8;
+    b.keys_a = a.take<uint32_t>(n);
+    b.keys_b = a.take<uint32_t>(n);
+    b.vals_a = a.take<uint32_t>(n);
+    b.vals_b = a.take<uint32_t>(n);
+    b.heads = a.take<uint32_t>(n);
+    b.counters = a.take<uint32_t>(64);
+    b.pt_ratio = a.take<float4>(npts);
+    b.sort_bytes = mb_sort_workspace_bytes((uint32_t)n);
+    b.sort_ws = a.take<char>(b.sort_bytes);
+    return a.ok();
+}
+
+// keys_a / pt_ratio / counters have been produced by a K1 variant
+int sort_and_reduce(cudaStream_t stream, SplatBuffers &b, uint32_t npts, const MbGrid &g,
+                    const MbFeatIndex &fi, const float *features, const int64_t *class_ids, int F,
+                    float *map, float alpha, int mode)
+{
+    const uint32_t n = npts * 8;
+    uint32_t *keys, *vals;
+    int rc = mb_sort_pairs(stream, b.keys_a, b.vals_a, b.keys_b, b.vals_b, n, mb_key_bits(g), true,
+                           b.sort_ws, b.sort_bytes, &keys, &vals);
+    if (rc) return rc;
+    rc = mbk_segment_heads(stream, keys, n, g, b.heads, b.counters);
+    if (rc) return rc;
+    return mbk_voxel_reduce(stream, keys, vals, n, b.heads, b.counters, b.pt_ratio, fi, features, class_ids,
+                            F, map, g, alpha, mode);
+}
+
+}  // namespace
+
+// ---- a5 -------------------------------------------------------------------------------------
+MB_API size_t mb_update_feature_map_workspace_bytes(int64_t npts, int S0, int S1, int S2)
+{
+    (void)S0; (void)S1; (void)S2;
+    if (npts <= 0) return 256;
+    return splat_workspace_bytes((uint32_t)npts);
+}
+
+MB_API int mb_update_feature_map(void *stream_, const int64_t *ind0, const int64_t *ind1, const int64_t *ind2,
+                                 const float *ratio0, const float *ratio1, const float *ratio2,
+                                 const float *features, int64_t npts, int F, float *map, int S0, int S1,
+                                 int S2, float interpolation_weight, int mode, void *workspace,
+                                 size_t workspace_bytes)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MB_REQUIRE(npts >= 0 && npts < ((int64_t)1 << 28), "mb_update_feature_map: npts out of range");
+    if (npts == 0) return MB_OK;
+    MB_REQUIRE(ind0 && ind1 && ind2 && ratio0 && ratio1 && ratio2 && features && map,
+               "mb_update_feature_map: null pointer");
+    MB_REQUIRE(S0 > 0 && S1 > 0 && S2 > 0 && F > 0, "mb_update_feature_map: bad map shape");
+    MB_REQUIRE(mode == MB_MODE_EXACT || mode == MB_MODE_FAST, "mb_update_feature_map: bad mode %d", mode);
+    const MbGrid g = mb_make_grid(S0, S1, S2);
+    MB_REQUIRE((uint64_t)g.B0 * g.B1 * g.B2 * MB_BRICK_VOX < 0xffffffffull, "map too large for 32-bit keys");
+    SplatBuffers b;
+    MB_REQUIRE(workspace && carve(b, workspace, workspace_bytes, (uint32_t)npts),
+               "mb_update_feature_map: workspace too small (%zu < %zu)", workspace_bytes,
+               splat_workspace_bytes((uint32_t)npts));
+    int rc = mbk_points_to_keys(stream, ind0, ind1, ind2, ratio0, ratio1, ratio2, (uint32_t)npts, g, b.keys_a,
+                                b.pt_ratio, b.counters);
+    if (rc) return rc;
+    MbFeatIndex fi = { (uint32_t)npts, 1u, 1u, 1u, 1u };
+    return sort_and_reduce(stream, b, (uint32_t)npts, g, fi, features, nullptr, F, map, interpolation_weight,
+                           mode);
+}
+
+// ---- a6..a9 ---------------------------------------------------------------------------------
+MB_API size_t mb_layer_update_workspace_bytes(int H, int W, int nx, int ny, int nz, int T)
+{
+    (void)nx; (void)ny; (void)nz; (void)T;
+    if (H <= 0 || W <= 0) return 256;
+    return splat_workspace_bytes((uint32_t)H * (uint32_t)W);
+}
+
+MB_API int mb_layer_update(void *stream_, const float *rays, const float *depth, const float *features,
+                           const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw,
+                           int F, const float *bins_x, int nx, const float *bins_y, int ny,
+                           const float *bins_z, int nz, float *map, float interpolation_weight,
+                           float min_ray_depth, float max_ray_depth, int mode, void *workspace,
+                           size_t workspace_bytes)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MB_REQUIRE(T >= 0 && H > 0 && W > 0 && F > 0, "mb_layer_update: bad sizes");
+    if (T == 0) return MB_OK;
+    MB_REQUIRE(rays && depth && pose && bins_x && bins_y && bins_z && map, "mb_layer_update: null pointer");
+    MB_REQUIRE((features != nullptr) != (class_ids != nullptr),
+               "mb_layer_update: pass exactly one of features / class_ids");
+    MB_REQUIRE(nx >= 2 && ny >= 2 && nz >= 2, "mb_layer_update: every edge table needs >= 2 entries");
+    MB_REQUIRE(mode == MB_MODE_EXACT || mode == MB_MODE_FAST, "mb_layer_update: bad mode %d", mode);
+    MB_REQUIRE((int64_t)H * W < ((int64_t)1 << 28), "mb_layer_update: frame too large");
+    if (features) {
+        MB_REQUIRE(fh > 0 && fw > 0 && H % fh == 0 && W % fw == 0,
+                   "mb_layer_update: feature image %dx%d does not divide the camera %dx%d", fh, fw, H, W);
+    } else {
+        fh = H; fw = W;
+    }
+    const uint32_t npix = (uint32_t)H * (uint32_t)W;
+    const MbGrid g = mb_make_grid(ny - 1, nx - 1, nz - 1);
+    MB_REQUIRE((uint64_t)g.B0 * g.B1 * g.B2 * MB_BRICK_VOX < 0xffffffffull, "map too large for 32-bit keys");
+    SplatBuffers b;
+    MB_REQUIRE(workspace && carve(b, workspace, workspace_bytes, npix),
+               "mb_layer_update: workspace too small (%zu < %zu)", workspace_bytes,
+               splat_workspace_bytes(npix));
+    MbFeatIndex fi = { npix, (uint32_t)W, (uint32_t)(H / fh), (uint32_t)(W / fw), (uint32_t)fw };
+    const size_t feat_stride = (size_t)fh * fw * F;
+    for (int t = 0; t < T; ++t) {
+        int rc = mbk_unproject_voxelise(stream, rays, depth + (size_t)t * npix, pose + (size_t)t * 12, npix,
+                                        bins_x, nx, bins_y, ny, bins_z, nz, g, min_ray_depth, max_ray_depth,
+                                        b.keys_a, b.pt_ratio, b.counters);
+        if (rc) return rc;
+        rc = sort_and_reduce(stream, b, npix, g, fi, features ? features + (size_t)t * feat_stride : nullptr,
+                             class_ids ? class_ids + (size_t)t * npix : nullptr, F, map,
+                             interpolation_weight, mode);
+        if (rc) return rc;
+    }
+    return MB_OK;
+}

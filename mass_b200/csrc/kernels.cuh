@@ -1,0 +1,43 @@
+// Internal launcher interfaces between the translation units of libmassb200.
+#pragma once
+#include "common.cuh"
+
+// device counters zeroed by K1 at the start of every frame
+constexpr int MB_CNT_HEADS = 0;      // number of voxel segments (= voxels touched by the frame)
+constexpr int MB_NUM_COUNTERS = 8;
+
+// How a contribution's point id maps to its feature row.
+//   dense:   row = point id (upsample == 0), or the nearest-upsampled source pixel
+//   one-hot: class_ids[point id] is the only non-zero channel
+struct MbFeatIndex {
+    uint32_t np;        // points per slot (contribution id = slot * np + point)
+    uint32_t W;         // camera width (for the up-sampling map)
+    uint32_t ky, kx;    // integer up-sampling factors (1 = none)
+    uint32_t fw;        // feature image width
+};
+
+// voxelise.cu
+int mbk_transform_rays(cudaStream_t stream, const float *rays, int64_t npix, const float *pose, float *out);
+int mbk_bin_flags(cudaStream_t stream, const float *bins0, int n0, const float *bins1, int n1,
+                  const float *bins2, int n2, const float *origin, const float *rays, const float *depth,
+                  int64_t npix, float min_d, float max_d, uint32_t *flags);
+int mbk_bin_write(cudaStream_t stream, const float *bins0, int n0, const float *bins1, int n1,
+                  const float *bins2, int n2, const float *origin, const float *rays, const float *depth,
+                  int64_t npix, float min_d, float max_d, const uint32_t *offsets, int64_t *ind0,
+                  int64_t *ind1, int64_t *ind2, float *ratio0, float *ratio1, float *ratio2, int64_t *pix,
+                  int64_t *count);
+int mbk_unproject_voxelise(cudaStream_t stream, const float *rays, const float *depth, const float *pose,
+                           uint32_t npix, const float *bins_x, int nx, const float *bins_y, int ny,
+                           const float *bins_z, int nz, const MbGrid &g, float min_d, float max_d,
+                           uint32_t *keys, float4 *pt_ratio, uint32_t *counters);
+int mbk_points_to_keys(cudaStream_t stream, const int64_t *ind0, const int64_t *ind1, const int64_t *ind2,
+                       const float *ratio0, const float *ratio1, const float *ratio2, uint32_t npts,
+                       const MbGrid &g, uint32_t *keys, float4 *pt_ratio, uint32_t *counters);
+
+// voxel_reduce.cu
+int mbk_segment_heads(cudaStream_t stream, const uint32_t *keys, uint32_t n, const MbGrid &g,
+                      uint32_t *heads, uint32_t *counters);
+int mbk_voxel_reduce(cudaStream_t stream, const uint32_t *keys, const uint32_t *vals, uint32_t n,
+                     const uint32_t *heads, const uint32_t *counters, const float4 *pt_ratio,
+                     const MbFeatIndex &fi, const float *features, const int64_t *class_ids, int F,
+                     float *map, const MbGrid &g, float alpha, int mode);

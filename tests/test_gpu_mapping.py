@@ -1,0 +1,271 @@
+"""Parity of the sm_100a mapping kernels (through the C ABI, via the reference-shaped
+Python surface) against the CPU oracle and the committed golden vectors.
+Bit-exact: validity, voxel indices, ratios, occupancy -- and, in exact mode, map values.
+Affine (fast) mode: map values within 1e-5 relative."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, golden_kwargs
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5   # north_star tolerance for aggregated class scores / features
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+def make_layer(kw, dev, exact=True, cls=None):
+    from mass_b200.nn.base_projection_layer import BaseProjectionLayer
+    kw = dict(kw)
+    kw.pop("class_to_colors", None)
+    return (cls or BaseProjectionLayer)(exact=exact, **kw).to(dev)
+
+
+def assert_close_rel(got, ref, rtol=RTOL):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    err = np.abs(got - ref)
+    bad = err > rtol * np.abs(ref)
+    assert not bad.any(), "max rel err %.3g at %d entries" % (
+        (err[bad] / np.maximum(np.abs(ref[bad]), 1e-300)).max(), bad.sum())
+
+
+def test_library_reports_launches(dev):
+    from mass_b200 import _lib
+    L = _lib.lib()
+    before = L.mb_launch_count()
+    from mass_b200.utils import projection as P
+    rays = torch.randn(10, 3, device=dev)
+    P.transform_rays(rays, torch.tensor([1.0, 0, 0]), torch.tensor([0, 0, 1.0]))
+    assert L.mb_launch_count() > before
+
+
+def test_transform_rays_bitwise(dev, oracle):
+    from mass_b200.utils import projection as P
+    g = golden("pose.npz")
+    rays = torch.from_numpy(g["rays"]).to(dev)
+    out = P.transform_rays(rays, torch.from_numpy(g["eye"][9]), torch.from_numpy(g["up"][9]))
+    assert np.array_equal(out.cpu().numpy(), g["oriented9"])
+    rng = np.random.default_rng(0)
+    big = rng.standard_normal((1000, 37, 3)).astype(np.float32)
+    for k in (0, 5, 77):
+        ref = oracle.transform_rays(big, g["eye"][k], g["up"][k])
+        out = P.transform_rays(torch.from_numpy(big).to(dev), torch.from_numpy(g["eye"][k]),
+                               torch.from_numpy(g["up"][k]))
+        assert np.array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("name,T", [("small_seq.npz", 6), ("border.npz", 2)])
+def test_bin_rays_golden(dev, name, T):
+    from mass_b200.utils import projection as P
+    g = golden(name)
+    L = make_layer(golden_kwargs(g), dev)
+    for t in range(T):
+        eye = P.spherical_to_cartesian(torch.tensor(g["yaw"][t]), torch.tensor(g["elevation"][t]))
+        up = P.spherical_to_cartesian(torch.tensor(g["yaw"][t]), torch.tensor(g["elevation"][t]) + np.pi / 2)
+        oriented = P.transform_rays(L.rays, eye, up)
+        feats = torch.from_numpy(g["features"][t]).to(dev)
+        out = P.bin_rays(L.bins_x, L.bins_y, L.bins_z, torch.from_numpy(g["position"][t]), oriented,
+                         torch.from_numpy(g["depth"][t]).to(dev), feats)
+        for nm, a in zip(("ind_x", "ind_y", "ind_z", "ratio_x", "ratio_y", "ratio_z"), out):
+            ref = g["%s_%d" % (nm, t)]
+            assert a.dtype == (torch.int64 if nm.startswith("ind") else torch.float32)
+            assert np.array_equal(a.cpu().numpy(), ref), (nm, t)
+        assert out[6].shape == (out[0].shape[0], feats.shape[-1])
+
+
+def test_bin_rays_empty_and_all_invalid(dev):
+    from mass_b200.utils import projection as P
+    bins = torch.arange(-1, 1.01, 0.5)
+    rays = torch.zeros(4, 4, 3, device=dev)
+    rays[..., 2] = -1
+    depth = torch.full((4, 4, 1), 50.0, device=dev)            # beyond max_ray_depth
+    out = P.bin_rays(bins, bins, bins, torch.zeros(3), rays, depth)
+    assert all(o.numel() == 0 for o in out)
+    out = P.bin_rays(bins, bins, bins, torch.zeros(3), rays[:0], depth[:0])
+    assert all(o.numel() == 0 for o in out)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_update_feature_map_vs_oracle(dev, oracle, exact):
+    from mass_b200.utils import projection as P
+    rng = np.random.default_rng(3)
+    S0, S1, S2, F = 14, 11, 9, 6
+    n = 5000
+    ind = [rng.integers(0, s, n) for s in (S0, S1, S2)]
+    rat = [rng.random(n).astype(np.float32) for _ in range(3)]
+    rat[0][:50] = 0.5          # weight exactly 0 + 1e-9 on one side
+    rat[1][50:100] = 0.0
+    feats = rng.random((n, F)).astype(np.float32)
+    old = rng.random((S0, S1, S2, F)).astype(np.float32)
+    old[::2] = 0
+    ref = old.copy()
+    oracle.update_feature_map(*ind, *rat, feats, ref, interpolation_weight=0.5)
+    got = torch.from_numpy(old).to(dev)
+    P.update_feature_map(*[torch.from_numpy(i).to(dev) for i in ind], *[torch.from_numpy(r).to(dev) for r in rat],
+                         torch.from_numpy(feats).to(dev), got, interpolation_weight=0.5, exact=exact)
+    got = got.cpu().numpy()
+    assert np.array_equal((got != 0).any(-1), (ref != 0).any(-1))
+    if exact:
+        assert np.array_equal(got, ref)
+    else:
+        assert_close_rel(got, ref)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("name,T", [("small_seq.npz", 6), ("border.npz", 2)])
+def test_layer_sequence_golden(dev, name, T, exact):
+    g = golden(name)
+    L = make_layer(golden_kwargs(g), dev, exact=exact)
+    for t in range(T):
+        obs = {k: g[k][t] for k in ("position", "yaw", "elevation", "depth", "features")}
+        assert L.update(obs) is L
+        got, ref = L.data.cpu().numpy(), g["data_%d" % t]
+        assert np.array_equal((got != 0).any(-1), (ref != 0).any(-1)), t
+        if exact:
+            assert np.array_equal(got, ref), t
+        elif name == "small_seq.npz":
+            # signed random features: cancellation makes a relative bound on the sum meaningless;
+            # bound the error by the magnitude of the terms instead
+            assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+        else:
+            assert_close_rel(got, ref)
+
+
+def test_layer_batch_equals_per_frame(dev):
+    g = golden("small_seq.npz")
+    A = make_layer(golden_kwargs(g), dev)
+    B = make_layer(golden_kwargs(g), dev)
+    for t in range(6):
+        A.update({k: g[k][t] for k in ("position", "yaw", "elevation", "depth", "features")})
+    B.update_batch({k: g[k] for k in ("position", "yaw", "elevation", "depth", "features")})
+    assert torch.equal(A.data, B.data)
+    assert np.array_equal(B.data.cpu().numpy(), g["data_5"])
+
+
+def test_lowres_features_upsampled(dev):
+    g = golden("lowres.npz")
+    L = make_layer(golden_kwargs(g), dev)
+    for t in range(3):
+        L.update({k: g[k][t] for k in ("position", "yaw", "elevation", "depth", "features")})
+    assert np.array_equal(L.data.cpu().numpy(), g["data"])
+
+
+def test_kat_tiny(dev):
+    g = golden("kat_tiny.npz")
+    L = make_layer(dict(camera_height=2, camera_width=2, vertical_fov=90.0, map_height=8, map_width=8,
+                        map_depth=4, feature_size=2, grid_resolution=0.5, interpolation_weight=0.5), dev)
+    assert np.array_equal(L.rays.cpu().numpy(), g["rays"])
+    for b in ("bins_x", "bins_y", "bins_z"):
+        assert np.array_equal(getattr(L, b).cpu().numpy(), g[b])
+    obs = {k[4:]: g[k] for k in g.files if k.startswith("obs_")}
+    assert np.array_equal(L(obs).cpu().numpy(), g["data1"])
+    L.update(obs)
+    assert np.array_equal(L.data.cpu().numpy(), g["data2"])
+    assert L.world_to_map(torch.tensor([0.1, 0.2, 0.3])).cpu().tolist() == g["world_to_map"].tolist()
+    assert np.array_equal(L.map_to_world(torch.tensor([4, 3, 2])).cpu().numpy(), g["map_to_world"])
+    L.reset(origin_x=0.0, origin_y=0.0, origin_z=0.0)
+    assert float(L.data.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_c1_frames_full_size(dev, exact):
+    """BASELINE config 1 (224x224, F=54, 384x384x96 @0.05 m) against the reference's digests."""
+    from mass_b200.utils import synthetic
+    g = golden("c1_frames.npz")
+    L = make_layer(golden_kwargs(g), dev, exact=exact)
+    for n in range(2):
+        obs = dict(position=g["position_%d" % n], yaw=g["yaw_%d" % n], elevation=g["elevation_%d" % n],
+                   depth=g["depth_%d" % n][..., None], features=g["probs_low_%d" % n])   # 28x28 -> x8
+        L.update(obs)
+        data = L.data.reshape(-1, 54)
+        occ = torch.nonzero((data != 0).any(-1)).reshape(-1)
+        assert occ.numel() == int(g["occ_count_%d" % n])
+        assert np.array_equal(sha(occ.cpu().numpy().astype(np.int64)), g["occ_sha_%d" % n])
+        rows = data[torch.from_numpy(g["sample_idx_%d" % n]).to(dev)].cpu().numpy()
+        if exact:
+            assert np.array_equal(rows, g["sample_rows_%d" % n])
+            assert np.array_equal(sha(data[occ].cpu().numpy()), g["rows_sha_%d" % n])
+        else:
+            assert_close_rel(rows, g["sample_rows_%d" % n])
+
+
+def test_c1_bin_rays_digests(dev):
+    from mass_b200.utils import projection as P
+    g = golden("c1_frames.npz")
+    L = make_layer(golden_kwargs(g), dev)
+    for n in range(2):
+        yaw, el = torch.tensor(g["yaw_%d" % n]), torch.tensor(g["elevation_%d" % n])
+        oriented = P.transform_rays(L.rays, P.spherical_to_cartesian(yaw, el),
+                                    P.spherical_to_cartesian(yaw, el + np.pi / 2))
+        out = P.bin_rays(L.bins_x, L.bins_y, L.bins_z, torch.from_numpy(g["position_%d" % n]), oriented,
+                         torch.from_numpy(g["depth_%d" % n][..., None]).to(dev))
+        assert out[0].numel() == int(g["n_valid_%d" % n])
+        for nm, a in zip(("ind_x", "ind_y", "ind_z", "ratio_x", "ratio_y", "ratio_z"), out):
+            a = a.cpu().numpy()
+            a = a.astype(np.int32) if a.dtype == np.int64 else a
+            assert np.array_equal(sha(a), g["%s_sha_%d" % (nm, n)]), (nm, n)
+
+
+def test_one_hot_ids_equal_dense_one_hot(dev):
+    """SemanticProjectionLayer (class ids) == BaseProjectionLayer fed the one-hot image."""
+    from mass_b200.nn.applications.semantic_projection_layer import SemanticProjectionLayer
+    kw = dict(camera_height=32, camera_width=48, map_height=40, map_width=40, map_depth=16, feature_size=54,
+              grid_resolution=0.1, origin_z=0.5)
+    S = make_layer(kw, dev, cls=SemanticProjectionLayer)
+    B = make_layer(kw, dev)
+    rng = np.random.default_rng(9)
+    for t in range(4):
+        ids = rng.integers(0, 54, (32, 48, 1))
+        obs = dict(position=rng.uniform(-.5, .5, 3).astype(np.float32), yaw=np.float32(rng.uniform(-3, 3)),
+                   elevation=np.float32(rng.uniform(-.5, .5)), depth=rng.uniform(0.3, 2.5, (32, 48, 1)).astype(np.float32))
+        S.update(dict(semantic=ids, **obs))
+        B.update(dict(features=np.eye(54, dtype=np.float32)[ids[..., 0]], **obs))
+        assert torch.equal(S.data, B.data)
+    with pytest.raises(RuntimeError):
+        S.update(dict(semantic=np.full((32, 48, 1), 54), **obs))
+
+
+def test_occupancy_and_resnet_layers(dev, oracle):
+    from mass_b200.nn.applications.occupancy_projection_layer import OccupancyProjectionLayer
+    from mass_b200.nn.applications.resnet_projection_layer import ResNetProjectionLayer
+    kw = dict(vertical_fov=90.0, map_height=32, map_width=32, map_depth=12, grid_resolution=0.2, origin_z=0.4)
+    occ = OccupancyProjectionLayer(camera_height=32, camera_width=32, feature_size=1, **kw).to(dev)
+    res = ResNetProjectionLayer(camera_height=32, camera_width=32, feature_size=256, **kw).to(dev)
+    assert res.camera_height == 8 and res.rays.shape == (8, 8, 3)
+    o_occ = oracle.OracleLayer(camera_height=32, camera_width=32, feature_size=1, **kw)
+    o_res = oracle.OracleLayer(camera_height=8, camera_width=8, feature_size=256, **kw)
+    rng = np.random.default_rng(4)
+    for t in range(3):
+        obs = dict(position=rng.uniform(-.5, .5, 3).astype(np.float32), yaw=np.float32(rng.uniform(-3, 3)),
+                   elevation=np.float32(rng.uniform(-.5, .5)),
+                   depth=rng.uniform(0.3, 3, (32, 32, 1)).astype(np.float32))
+        feats = rng.random((8, 8, 256)).astype(np.float32)
+        occ.update(obs)
+        res.update(dict(features=feats, **obs))
+        o_occ.update(dict(features=np.ones((32, 32, 1), np.float32), **obs))
+        o_res.update(dict(features=feats, **dict(obs, depth=obs["depth"][2::4, 2::4])))
+    assert np.array_equal(occ.data.cpu().numpy(), o_occ.data)
+    assert np.array_equal(res.data.cpu().numpy(), o_res.data)
+
+
+def test_errors_are_loud(dev):
+    from mass_b200.nn.base_projection_layer import BaseProjectionLayer
+    L = BaseProjectionLayer(camera_height=4, camera_width=4, map_height=8, map_width=8, map_depth=4)
+    obs = dict(position=np.zeros(3, np.float32), yaw=np.float32(0), elevation=np.float32(0),
+               depth=np.ones((4, 4, 1), np.float32), features=np.ones((4, 4, 1), np.float32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        L.update(obs)                                        # layer still on the CPU
+    L = L.to(dev)
+    with pytest.raises(ValueError):
+        L.update(dict(obs, features=np.ones((3, 3, 1), np.float32)))   # 3 does not divide 4
