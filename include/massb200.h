@@ -40,8 +40,10 @@ extern "C" {
 #define MB_ERR_WORKSPACE 3
 
 /* arithmetic mode of the voxel reduce */
-#define MB_MODE_EXACT 0 /* reference operation order, no FMA: map values bitwise equal to the CPU path  */
-#define MB_MODE_FAST 1  /* per-voxel affine form new = a*old + b: <= 1e-5 relative         */
+#define MB_MODE_EXACT 0 /* reference operation order, no FMA: map values bitwise equal to the CPU path;
+                           frames are processed one at a time (sort by voxel + one warp per voxel segment)  */
+#define MB_MODE_FAST 1  /* per-voxel affine form new = a*old + b: <= 1e-5 relative, occupancy
+                           still bit-exact; all frames of the call go through the batched brick pipeline    */
 
 const char *mb_last_error(void);
 int mb_version(void);
@@ -87,7 +89,7 @@ int mb_update_feature_map(void *stream, const int64_t *ind0, const int64_t *ind1
  *             (mass/nn/applications/semantic_projection_layer.py:203-214); else NULL
  *   pose      [T][12]
  *   bins_x/y/z edge tables with nx/ny/nz entries (map is [ny-1][nx-1][nz-1][F]) */
-size_t mb_layer_update_workspace_bytes(int H, int W, int nx, int ny, int nz, int T);
+size_t mb_layer_update_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int mode);
 int mb_layer_update(void *stream, const float *rays, const float *depth, const float *features,
                     const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw,
                     int F, const float *bins_x, int nx, const float *bins_y, int ny,

@@ -116,7 +116,7 @@ int sort_and_reduce(cudaStream_t stream, SplatBuffers &b, uint32_t npts, const M
 {
     const uint32_t n = npts * 8;
     uint32_t *keys, *vals;
-    int rc = mb_sort_pairs(stream, b.keys_a, b.vals_a, b.keys_b, b.vals_b, n, mb_key_bits(g), true,
+    int rc = mb_sort_pairs(stream, b.keys_a, b.vals_a, b.keys_b, b.vals_b, n, nullptr, mb_key_bits(g), true,
                            b.sort_ws, b.sort_bytes, &keys, &vals);
     if (rc) return rc;
     rc = mbk_segment_heads(stream, keys, n, g, b.heads, b.counters);
@@ -163,11 +163,19 @@ MB_API int mb_update_feature_map(void *stream_, const int64_t *ind0, const int64
 }
 
 // ---- a6..a9 ---------------------------------------------------------------------------------
-MB_API size_t mb_layer_update_workspace_bytes(int H, int W, int nx, int ny, int nz, int T)
+// frames the batched path fuses per internal chunk when the caller sizes the workspace with
+// mb_layer_update_workspace_bytes (a larger workspace is used if given)
+static const int MB_DEFAULT_CHUNK_FRAMES = 64;
+
+MB_API size_t mb_layer_update_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int mode)
 {
-    (void)nx; (void)ny; (void)nz; (void)T;
-    if (H <= 0 || W <= 0) return 256;
-    return splat_workspace_bytes((uint32_t)H * (uint32_t)W);
+    (void)nx; (void)ny; (void)nz;
+    if (H <= 0 || W <= 0 || T <= 0) return 256;
+    const uint32_t npix = (uint32_t)H * (uint32_t)W;
+    if (mode == MB_MODE_EXACT) return splat_workspace_bytes(npix);
+    int chunk = T < MB_DEFAULT_CHUNK_FRAMES ? T : MB_DEFAULT_CHUNK_FRAMES;
+    while (chunk > 1 && (uint64_t)chunk * npix * 8 >= 0xffffffffull) chunk /= 2;
+    return mbk_batch_workspace_bytes(npix, chunk);
 }
 
 MB_API int mb_layer_update(void *stream_, const float *rays, const float *depth, const float *features,
@@ -193,6 +201,23 @@ MB_API int mb_layer_update(void *stream_, const float *rays, const float *depth,
         fh = H; fw = W;
     }
     const uint32_t npix = (uint32_t)H * (uint32_t)W;
+    const size_t feat_stride = (size_t)fh * fw * F;
+    if (mode == MB_MODE_FAST) {
+        // batched brick pipeline, as many frames per chunk as the workspace holds
+        const int chunk = workspace ? mbk_batch_frames_that_fit(npix, workspace_bytes, T) : 0;
+        MB_REQUIRE(chunk >= 1, "mb_layer_update: workspace too small (%zu < %zu)", workspace_bytes,
+                   mbk_batch_workspace_bytes(npix, 1));
+        for (int t = 0; t < T; t += chunk) {
+            const int n = T - t < chunk ? T - t : chunk;
+            int rc = mbk_batch_update(stream, rays, depth + (size_t)t * npix,
+                                      features ? features + (size_t)t * feat_stride : nullptr,
+                                      class_ids ? class_ids + (size_t)t * npix : nullptr, pose + (size_t)t * 12, n,
+                                      H, W, fh, fw, F, bins_x, nx, bins_y, ny, bins_z, nz, map, nullptr,
+                                      interpolation_weight, min_ray_depth, max_ray_depth, workspace, workspace_bytes);
+            if (rc) return rc;
+        }
+        return MB_OK;
+    }
     const MbGrid g = mb_make_grid(ny - 1, nx - 1, nz - 1);
     MB_REQUIRE((uint64_t)g.B0 * g.B1 * g.B2 * MB_BRICK_VOX < 0xffffffffull, "map too large for 32-bit keys");
     SplatBuffers b;
@@ -200,7 +225,6 @@ MB_API int mb_layer_update(void *stream_, const float *rays, const float *depth,
                "mb_layer_update: workspace too small (%zu < %zu)", workspace_bytes,
                splat_workspace_bytes(npix));
     MbFeatIndex fi = { npix, (uint32_t)W, (uint32_t)(H / fh), (uint32_t)(W / fw), (uint32_t)fw };
-    const size_t feat_stride = (size_t)fh * fw * F;
     for (int t = 0; t < T; ++t) {
         int rc = mbk_unproject_voxelise(stream, rays, depth + (size_t)t * npix, pose + (size_t)t * 12, npix,
                                         bins_x, nx, bins_y, ny, bins_z, nz, g, min_ray_depth, max_ray_depth,

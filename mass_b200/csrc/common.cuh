@@ -106,8 +106,10 @@ __device__ __forceinline__ size_t mb_key_to_voxel(const MbGrid &g, uint32_t key)
 // keys_a/vals_a hold the input; the sorted result lands in *keys_out / *vals_out (one of a/b).
 // If vals_a_is_iota the first pass synthesises vals = 0..n-1 instead of reading them.
 size_t mb_sort_workspace_bytes(uint32_t n);
+// n is the host-side element count (or an upper bound of it); if n_dev is not null the device
+// value min(n, *n_dev) is the real count.
 int mb_sort_pairs(cudaStream_t stream, uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b,
-                  uint32_t *vals_b, uint32_t n, int key_bits, bool vals_a_is_iota,
+                  uint32_t *vals_b, uint32_t n, const uint32_t *n_dev, int key_bits, bool vals_a_is_iota,
                   void *workspace, size_t workspace_bytes, uint32_t **keys_out, uint32_t **vals_out);
 
 // exclusive prefix sum of n u32 values (in place allowed)

@@ -1,0 +1,89 @@
+// Device-side geometry shared by the per-frame and the batched kernels: the reference's fp32
+// operation sequence for ray orientation, unprojection and binning, written with
+// explicit round-to-nearest intrinsics so no FMA contraction can change a bit.
+//   transform_rays   /root/reference/mass/utils/projection.py:104-110
+//   bin_rays         /root/reference/mass/utils/projection.py:182-230
+//   neighbour pairs  /root/reference/mass/utils/projection.py:280-291
+#pragma once
+#include "common.cuh"
+
+namespace {
+
+// torch.bucketize(x, bins, right=True) - 1 == (number of edges <= x) - 1, in [-1, n-1].
+// Guess from the (near-uniform) table spacing, then walk to the exact answer on the table
+// itself: the table is ATen's arange output and is the only authority on edge positions.
+__device__ __forceinline__ int bucket_right(const float *__restrict__ bins, int n, float x)
+{
+    if (x != x) return n - 1;                     // NaN: ATen's upper bound runs off the end
+    const float b0 = __ldg(bins), b1 = __ldg(bins + n - 1);
+    if (!(x >= b0)) return -1;
+    int i;
+    if (x >= b1) {
+        i = n - 1;
+    } else {
+        const float g = (x - b0) * ((float)(n - 1) / (b1 - b0));
+        i = g >= (float)(n - 1) ? n - 1 : (int)g;
+        if (i < 0) i = 0;
+    }
+    while (i + 1 < n && __ldg(bins + i + 1) <= x) ++i;
+    while (i >= 0 && __ldg(bins + i) > x) --i;
+    return i;
+}
+
+struct BinResult {
+    int i0, i1, i2;      // bucket per input axis (x, y, z); valid only if ok
+    float q0, q1, q2;    // ratio per input axis (axis 1 already flipped together with i1)
+    bool ok;
+};
+
+// world point + binning of one pixel.  ray = oriented ray, o = origin.
+__device__ __forceinline__ BinResult bin_point(const float *__restrict__ bins0, int n0,
+                                               const float *__restrict__ bins1, int n1,
+                                               const float *__restrict__ bins2, int n2, float o0, float o1,
+                                               float o2, float r0, float r1, float r2, float d,
+                                               float min_d, float max_d)
+{
+    BinResult b;
+    const float x0 = __fadd_rn(o0, __fmul_rn(r0, d));
+    const float x1 = __fadd_rn(o1, __fmul_rn(r1, d));
+    const float x2 = __fadd_rn(o2, __fmul_rn(r2, d));
+    const int i0 = bucket_right(bins0, n0, x0);
+    const int i1 = bucket_right(bins1, n1, x1);
+    const int i2 = bucket_right(bins2, n2, x2);
+    b.ok = (d >= min_d) && (d <= max_d) && i0 >= 0 && i0 < n0 - 1 && i1 >= 0 && i1 < n1 - 1 &&
+           i2 >= 0 && i2 < n2 - 1;
+    b.i0 = i0; b.i1 = i1; b.i2 = i2;
+    b.q0 = b.q1 = b.q2 = 0.f;
+    if (b.ok) {
+        const float l0 = __ldg(bins0 + i0), h0 = __ldg(bins0 + i0 + 1);
+        const float l1 = __ldg(bins1 + i1), h1 = __ldg(bins1 + i1 + 1);
+        const float l2 = __ldg(bins2 + i2), h2 = __ldg(bins2 + i2 + 1);
+        b.q0 = __fdiv_rn(__fsub_rn(x0, l0), __fsub_rn(h0, l0));
+        b.q1 = __fsub_rn(1.0f, __fdiv_rn(__fsub_rn(x1, l1), __fsub_rn(h1, l1)));
+        b.q2 = __fdiv_rn(__fsub_rn(x2, l2), __fsub_rn(h2, l2));
+        b.i1 = n1 - 2 - i1;
+    }
+    return b;
+}
+
+__device__ __forceinline__ void orient(const float *__restrict__ R, float a, float b, float c, float &o0,
+                                       float &o1, float &o2)
+{
+    o0 = __fadd_rn(__fadd_rn(__fmul_rn(a, R[0]), __fmul_rn(b, R[1])), __fmul_rn(c, R[2]));
+    o1 = __fadd_rn(__fadd_rn(__fmul_rn(a, R[3]), __fmul_rn(b, R[4])), __fmul_rn(c, R[5]));
+    o2 = __fadd_rn(__fadd_rn(__fmul_rn(a, R[6]), __fmul_rn(b, R[7])), __fmul_rn(c, R[8]));
+}
+
+// per-axis neighbour pair of update_feature_map (projection.py:280-291)
+__device__ __forceinline__ void axis_pair(int ind, float ratio, int size, int &lo, int &hi)
+{
+    if (ratio < 0.5f) {
+        lo = ind - 1 < 0 ? 0 : ind - 1;
+        hi = ind;
+    } else {
+        lo = ind;
+        hi = ind + 1 > size - 1 ? size - 1 : ind + 1;
+    }
+}
+
+}  // namespace

@@ -4,6 +4,9 @@
 
 // device counters zeroed by K1 at the start of every frame
 constexpr int MB_CNT_HEADS = 0;      // number of voxel segments (= voxels touched by the frame)
+constexpr int MB_CNT_ENTRIES = 1;    // batched path: (brick, pixel) entries emitted
+constexpr int MB_CNT_BRICKS = 2;     // batched path: bricks touched
+constexpr int MB_CNT_TICKET = 3;     // batched path: next brick to hand to a CTA
 constexpr int MB_NUM_COUNTERS = 8;
 
 // How a contribution's point id maps to its feature row.
@@ -41,3 +44,12 @@ int mbk_voxel_reduce(cudaStream_t stream, const uint32_t *keys, const uint32_t *
                      const uint32_t *heads, const uint32_t *counters, const float4 *pt_ratio,
                      const MbFeatIndex &fi, const float *features, const int64_t *class_ids, int F,
                      float *map, const MbGrid &g, float alpha, int mode);
+
+// batch.cu: batched brick pipeline (affine form of the update; see the file header)
+int mbk_batch_frames_that_fit(uint32_t npix, size_t workspace_bytes, int T);
+size_t mbk_batch_workspace_bytes(uint32_t npix, int T);
+int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth, const float *features,
+                     const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw, int F,
+                     const float *bins_x, int nx, const float *bins_y, int ny, const float *bins_z, int nz,
+                     float *map, float *affine_a, float alpha, float min_d, float max_d, void *workspace,
+                     size_t workspace_bytes);

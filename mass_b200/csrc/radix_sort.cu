@@ -5,18 +5,14 @@
 // /root/reference/mass/utils/projection.py:294-298, 319-323, 349-351) without float atomics.
 //
 // One pass = per-tile digit histogram -> exclusive scan over (digit, tile) -> stable scatter.
-// A tile is 2048 elements; inside a tile each warp owns 256 consecutive elements and ranks them
-// in 8 rounds of 32 with match.any, so the order (tile, warp, round, lane) is the input order.
+// A tile is 2048 (8-bit digits) or 4096 (9-bit digits) elements; inside a tile each warp owns 256
+// consecutive elements and ranks them in 8 rounds of 32 with match.any, so the order
+// (tile, warp, round, lane) is the input order.
 #include "common.cuh"
 
 namespace {
 
-constexpr int RADIX_BITS = 8;
-constexpr int RADIX = 1 << RADIX_BITS;
-constexpr int SORT_THREADS = 256;
-constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 8;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+constexpr int SORT_ITEMS = 8;      // keys per thread and pass
 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
@@ -108,35 +104,47 @@ k_scan_apply(const uint32_t *in, uint32_t *out, uint32_t n, const uint32_t *__re
 }
 
 // ---------------------------------------------------------------------------------------------
-// radix pass
-__global__ void __launch_bounds__(SORT_THREADS)
-k_radix_hist(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint32_t *__restrict__ tile_hist,
-             uint32_t ntiles)
+// radix pass, BITS bits per digit with one thread per digit (256 or 512 threads per CTA).
+// n_dev (optional) overrides n with a count produced on the device; the grid is sized for the
+// host-side upper bound n and tiles past the device count write empty histograms.
+template <int BITS>
+__global__ void __launch_bounds__(1 << BITS)
+k_radix_hist(const uint32_t *__restrict__ keys, uint32_t n, const uint32_t *__restrict__ n_dev, int shift,
+             uint32_t *__restrict__ tile_hist, uint32_t ntiles)
 {
-    __shared__ uint32_t h[RADIX];
+    constexpr int R = 1 << BITS, TILE = R * SORT_ITEMS;
+    __shared__ uint32_t h[R];
+    if (n_dev) n = min(n, *n_dev);
     h[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t base = blockIdx.x * SORT_TILE;
+    const uint32_t base = blockIdx.x * TILE;
+    if (base < n) {
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        uint32_t idx = base + i * SORT_THREADS + threadIdx.x;
-        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & (RADIX - 1)], 1u);
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            uint32_t idx = base + i * R + threadIdx.x;
+            if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & (R - 1)], 1u);
+        }
     }
     __syncthreads();
     tile_hist[threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];   // digit-major
 }
 
-__global__ void __launch_bounds__(SORT_THREADS)
+template <int BITS>
+__global__ void __launch_bounds__(1 << BITS)
 k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, int shift,
-                const uint32_t *__restrict__ tile_offs, uint32_t ntiles, int vals_iota)
+                uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n,
+                const uint32_t *__restrict__ n_dev, int shift, const uint32_t *__restrict__ tile_offs,
+                uint32_t ntiles, int vals_iota)
 {
-    __shared__ uint32_t wcnt[SORT_WARPS][RADIX];
+    constexpr int R = 1 << BITS, WARPS = R / 32, TILE = R * SORT_ITEMS;
+    __shared__ uint32_t wcnt[WARPS][R];
+    if (n_dev) n = min(n, *n_dev);
+    if (blockIdx.x * TILE >= n) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < WARPS * R; i += R) (&wcnt[0][0])[i] = 0;
     __syncthreads();
 
-    const uint32_t wbase = blockIdx.x * SORT_TILE + warp * (32 * SORT_ITEMS);
+    const uint32_t wbase = blockIdx.x * TILE + warp * (32 * SORT_ITEMS);
     uint32_t k[SORT_ITEMS], v[SORT_ITEMS], rk[SORT_ITEMS];
 #pragma unroll
     for (int r = 0; r < SORT_ITEMS; ++r) {
@@ -144,9 +152,9 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
         const bool valid = idx < n;
         k[r] = valid ? keys_in[idx] : 0xffffffffu;
         v[r] = valid ? (vals_iota ? idx : vals_in[idx]) : 0u;
-        const uint32_t d = (k[r] >> shift) & (RADIX - 1);
+        const uint32_t d = (k[r] >> shift) & (R - 1);
         // out-of-range lanes get a private pseudo-digit so they never join a real group
-        const uint32_t m = __match_any_sync(0xffffffffu, valid ? d : (RADIX + lane));
+        const uint32_t m = __match_any_sync(0xffffffffu, valid ? d : (R + lane));
         const uint32_t rank = __popc(m & ((1u << lane) - 1u));
         const uint32_t prev = valid ? wcnt[warp][d] : 0u;
         __syncwarp();
@@ -158,7 +166,7 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     {   // thread d: exclusive scan of digit d over the warps, seeded with this tile's global offset
         uint32_t run = tile_offs[threadIdx.x * ntiles + blockIdx.x];
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; ++w) {
+        for (int w = 0; w < WARPS; ++w) {
             uint32_t c = wcnt[w][threadIdx.x];
             wcnt[w][threadIdx.x] = run;
             run += c;
@@ -169,12 +177,29 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     for (int r = 0; r < SORT_ITEMS; ++r) {
         const uint32_t idx = wbase + r * 32 + lane;
         if (idx < n) {
-            const uint32_t d = (k[r] >> shift) & (RADIX - 1);
+            const uint32_t d = (k[r] >> shift) & (R - 1);
             const uint32_t pos = wcnt[warp][d] + rk[r];
             keys_out[pos] = k[r];
             vals_out[pos] = v[r];
         }
     }
+}
+
+template <int BITS>
+int radix_pass(cudaStream_t stream, const uint32_t *kin, const uint32_t *vin, uint32_t *kout, uint32_t *vout,
+               uint32_t n, const uint32_t *n_dev, int shift, bool iota, uint32_t *hist, void *scan_ws,
+               size_t scan_bytes)
+{
+    constexpr int R = 1 << BITS, TILE = R * SORT_ITEMS;
+    const uint32_t ntiles = (n + TILE - 1) / TILE;
+    k_radix_hist<BITS><<<ntiles, R, 0, stream>>>(kin, n, n_dev, shift, hist, ntiles);
+    MB_LAUNCHED();
+    int rc = mb_exclusive_scan_u32(stream, hist, hist, ntiles * R, scan_ws, scan_bytes);
+    if (rc) return rc;
+    k_radix_scatter<BITS><<<ntiles, R, 0, stream>>>(kin, vin, kout, vout, n, n_dev, shift, hist, ntiles,
+                                                    iota ? 1 : 0);
+    MB_LAUNCHED();
+    return MB_OK;
 }
 
 }  // namespace
@@ -200,39 +225,39 @@ int mb_exclusive_scan_u32(cudaStream_t stream, const uint32_t *in, uint32_t *out
     return MB_OK;
 }
 
+// 9-bit digits only where they save a pass: 18-bit brick keys sort in two passes, 24-bit voxel keys
+// in three 8-bit ones
+static int digit_bits(int key_bits) { return (key_bits + 8) / 9 < (key_bits + 7) / 8 ? 9 : 8; }
+
 size_t mb_sort_workspace_bytes(uint32_t n)
 {
-    const size_t ntiles = ((size_t)n + SORT_TILE - 1) / SORT_TILE;
-    const size_t hist = mb_align_up(ntiles * RADIX * sizeof(uint32_t));
-    return hist + mb_scan_workspace_bytes((uint32_t)(ntiles * RADIX)) + 256;
+    const size_t ntiles = ((size_t)n + 256 * SORT_ITEMS - 1) / (256 * SORT_ITEMS);   // the smaller tile
+    const size_t hist = mb_align_up(ntiles * 512 * sizeof(uint32_t));
+    return hist + mb_scan_workspace_bytes((uint32_t)(ntiles * 512)) + 256;
 }
 
 int mb_sort_pairs(cudaStream_t stream, uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b,
-                  uint32_t *vals_b, uint32_t n, int key_bits, bool vals_a_is_iota,
+                  uint32_t *vals_b, uint32_t n, const uint32_t *n_dev, int key_bits, bool vals_a_is_iota,
                   void *workspace, size_t workspace_bytes, uint32_t **keys_out, uint32_t **vals_out)
 {
     *keys_out = keys_a;
     *vals_out = vals_a;
     if (n == 0) return MB_OK;
     MB_REQUIRE(workspace_bytes >= mb_sort_workspace_bytes(n), "sort workspace too small");
-    const uint32_t ntiles = (n + SORT_TILE - 1) / SORT_TILE;
     MbArena arena(workspace, workspace_bytes);
-    uint32_t *hist = arena.take<uint32_t>((size_t)ntiles * RADIX);
-    const size_t scan_bytes = mb_scan_workspace_bytes(ntiles * RADIX);
+    const size_t ntiles = ((size_t)n + 256 * SORT_ITEMS - 1) / (256 * SORT_ITEMS);
+    uint32_t *hist = arena.take<uint32_t>(ntiles * 512);
+    const size_t scan_bytes = mb_scan_workspace_bytes((uint32_t)(ntiles * 512));
     char *scan_ws = arena.take<char>(scan_bytes);
 
     uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
     bool iota = vals_a_is_iota;
-    const int passes = (key_bits + RADIX_BITS - 1) / RADIX_BITS;
+    const int bits = digit_bits(key_bits);
+    const int passes = (key_bits + bits - 1) / bits;
     for (int p = 0; p < passes; ++p) {
-        const int shift = p * RADIX_BITS;
-        k_radix_hist<<<ntiles, SORT_THREADS, 0, stream>>>(kin, n, shift, hist, ntiles);
-        MB_LAUNCHED();
-        int rc = mb_exclusive_scan_u32(stream, hist, hist, ntiles * RADIX, scan_ws, scan_bytes);
+        int rc = bits == 9 ? radix_pass<9>(stream, kin, vin, kout, vout, n, n_dev, p * 9, iota, hist, scan_ws, scan_bytes)
+                           : radix_pass<8>(stream, kin, vin, kout, vout, n, n_dev, p * 8, iota, hist, scan_ws, scan_bytes);
         if (rc) return rc;
-        k_radix_scatter<<<ntiles, SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, n, shift, hist,
-                                                             ntiles, iota ? 1 : 0);
-        MB_LAUNCHED();
         iota = false;
         uint32_t *t;
         t = kin; kin = kout; kout = t;

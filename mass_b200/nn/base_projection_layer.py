@@ -106,13 +106,14 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
             features = features.contiguous()
         L = _lib.lib()
         nx, ny, nz = self.bins_x.numel(), self.bins_y.numel(), self.bins_z.numel()
-        ws = self._ws.get(L.mb_layer_update_workspace_bytes(H, W, nx, ny, nz, T), device)
+        mode = _lib.MODE_EXACT if self.exact else _lib.MODE_FAST
+        ws = self._ws.get(L.mb_layer_update_workspace_bytes(H, W, nx, ny, nz, T, mode), device)
         _lib.check(L.mb_layer_update(
             _lib.stream_ptr(device), _lib.ptr(self.rays), _lib.ptr(depth), _lib.ptr(features),
             _lib.ptr(class_ids), _lib.ptr(pose), T, H, W, fh, fw, F, _lib.ptr(self.bins_x), nx,
             _lib.ptr(self.bins_y), ny, _lib.ptr(self.bins_z), nz, _lib.ptr(self.data),
             float(self.interpolation_weight), float(self.min_ray_depth), float(self.max_ray_depth),
-            _lib.MODE_EXACT if self.exact else _lib.MODE_FAST, _lib.ptr(ws), ws.numel()))
+            mode, _lib.ptr(ws), ws.numel()))
         return self
 
     def update(self, observation: Dict[str, Any]):

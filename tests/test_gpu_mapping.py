@@ -269,3 +269,99 @@ def test_errors_are_loud(dev):
     L = L.to(dev)
     with pytest.raises(ValueError):
         L.update(dict(obs, features=np.ones((3, 3, 1), np.float32)))   # 3 does not divide 4
+
+
+# ---- batched brick pipeline (affine form) -----------------------------------------------------------
+def _random_frames(rng, T, H, W, fh, fw, F, depth_lo=0.3, depth_hi=3.0, signed=False):
+    feats = rng.standard_normal((T, fh, fw, F)) if signed else rng.random((T, fh, fw, F))
+    return dict(position=rng.uniform(-.5, .5, (T, 3)).astype(np.float32),
+                yaw=rng.uniform(-3, 3, T).astype(np.float32),
+                elevation=rng.uniform(-.6, .6, T).astype(np.float32),
+                depth=rng.uniform(depth_lo, depth_hi, (T, H, W, 1)).astype(np.float32),
+                features=feats.astype(np.float32))
+
+
+def _oracle_run(oracle, kw, frames, T):
+    ref = oracle.OracleLayer(**kw)
+    for t in range(T):
+        ref.update({k: v[t] for k, v in frames.items()})
+    return ref.data
+
+
+@pytest.mark.parametrize("F,fdiv", [(1, 1), (2, 1), (5, 1), (7, 4), (54, 1), (54, 8), (64, 1), (100, 2), (256, 1), (130, 1)])
+def test_batched_fast_path_vs_oracle(dev, oracle, F, fdiv):
+    H, W, T = 32, 48, 5
+    kw = dict(camera_height=H, camera_width=W, vertical_fov=90.0, map_height=44, map_width=50, map_depth=18,
+              feature_size=F, grid_resolution=0.12, interpolation_weight=0.5, origin_z=0.3)
+    rng = np.random.default_rng(100 + F)
+    frames = _random_frames(rng, T, H, W, H // fdiv, W // fdiv, F)
+    ref = _oracle_run(oracle, kw, frames, T)
+    batch = make_layer(kw, dev, exact=False)
+    batch.update_batch(frames)
+    got = batch.data.cpu().numpy()
+    assert np.array_equal((got != 0).any(-1), (ref != 0).any(-1))
+    assert_close_rel(got, ref)
+    # frame by frame through the same pipeline: identical bits (same per-voxel summation order)
+    single = make_layer(kw, dev, exact=False)
+    for t in range(T):
+        single.update({k: v[t] for k, v in frames.items()})
+    assert torch.equal(single.data, batch.data)
+    # and reproducible run to run (no float atomics)
+    again = make_layer(kw, dev, exact=False)
+    again.update_batch(frames)
+    assert torch.equal(again.data, batch.data)
+
+
+def test_batched_many_entries_per_brick(dev, oracle):
+    """Camera almost touching a surface: thousands of pixels land in a handful of voxels, so one
+    (brick, frame) group spans many 256-entry chunks (the multi-chunk partial-sum path)."""
+    H, W, T, F = 64, 64, 3, 6
+    kw = dict(camera_height=H, camera_width=W, vertical_fov=60.0, map_height=24, map_width=24, map_depth=12,
+              feature_size=F, grid_resolution=0.1, interpolation_weight=0.5)
+    rng = np.random.default_rng(5)
+    frames = _random_frames(rng, T, H, W, H, W, F, depth_lo=0.05, depth_hi=0.12)
+    frames["position"][:] = rng.uniform(-.2, .2, (T, 3)).astype(np.float32)
+    ref = _oracle_run(oracle, kw, frames, T)
+    L = make_layer(kw, dev, exact=False)
+    L.update_batch(frames)
+    got = L.data.cpu().numpy()
+    assert np.array_equal((got != 0).any(-1), (ref != 0).any(-1))
+    assert_close_rel(got, ref)
+    # exactly 256 / 512 entries in one group is the edge of the chunk logic: sweep a few sizes
+    for n in (255, 256, 257, 511, 512, 513):
+        kw1 = dict(kw, camera_height=1, camera_width=n)
+        fr = _random_frames(rng, 2, 1, n, 1, n, F, depth_lo=0.05, depth_hi=0.06)
+        fr["position"][:] = 0.01
+        ref = _oracle_run(oracle, kw1, fr, 2)
+        L = make_layer(kw1, dev, exact=False)
+        L.update_batch(fr)
+        got = L.data.cpu().numpy()
+        assert np.array_equal((got != 0).any(-1), (ref != 0).any(-1)), n
+        assert_close_rel(got, ref)
+
+
+def test_batched_border_and_special_depths(dev):
+    g = golden("border.npz")
+    L = make_layer(golden_kwargs(g), dev, exact=False)
+    L.update_batch({k: g[k] for k in ("position", "yaw", "elevation", "depth", "features")})
+    got, ref = L.data.cpu().numpy(), g["data_1"]
+    assert np.array_equal((got != 0).any(-1), (ref != 0).any(-1))
+    assert_close_rel(got, ref)
+
+
+def test_batched_c2_prefix_vs_oracle(dev, oracle):
+    """First frames of the BASELINE config-2 walkthrough at full size, batched, against the oracle."""
+    from mass_b200.utils import synthetic
+    kw = dict(camera_height=224, camera_width=224, vertical_fov=90.0, map_height=384, map_width=384,
+              map_depth=96, feature_size=54, grid_resolution=0.05, interpolation_weight=0.5, **synthetic.MAP_ORIGIN)
+    rays = synthetic.camera_rays(224, 224)
+    frames = [synthetic.boxroom_frame(t, 500, rays=rays) for t in (0, 1, 2, 250)]
+    ref = oracle.OracleLayer(nthreads=8, **kw)
+    for f in frames:
+        ref.update(f)
+    L = make_layer(kw, dev, exact=False)
+    L.update_batch(frames)
+    got = L.data.cpu().numpy()
+    assert np.array_equal((got != 0).any(-1), (ref.data != 0).any(-1))
+    idx = np.flatnonzero((ref.data != 0).any(-1).reshape(-1))
+    assert_close_rel(got.reshape(-1, 54)[idx], ref.data.reshape(-1, 54)[idx])
