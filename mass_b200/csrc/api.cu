@@ -87,7 +87,7 @@ size_t splat_workspace_bytes(uint32_t npts)
     const size_t n = (size_t)npts * 8;
     a.take<uint32_t>(n); a.take<uint32_t>(n); a.take<uint32_t>(n); a.take<uint32_t>(n);
     a.take<uint32_t>(n);
-    a.take<uint32_t>(64);
+    a.take<uint32_t>(MB_NUM_COUNTERS);
     a.take<float4>(npts);
     a.take<char>(mb_sort_workspace_bytes((uint32_t)n));
     return a.used + 256;
@@ -102,7 +102,7 @@ bool carve(SplatBuffers &b, void *workspace, size_t bytes, uint32_t npts)
     b.vals_a = a.take<uint32_t>(n);
     b.vals_b = a.take<uint32_t>(n);
     b.heads = a.take<uint32_t>(n);
-    b.counters = a.take<uint32_t>(64);
+    b.counters = a.take<uint32_t>(MB_NUM_COUNTERS);
     b.pt_ratio = a.take<float4>(npts);
     b.sort_bytes = mb_sort_workspace_bytes((uint32_t)n);
     b.sort_ws = a.take<char>(b.sort_bytes);
@@ -169,13 +169,12 @@ static const int MB_DEFAULT_CHUNK_FRAMES = 64;
 
 MB_API size_t mb_layer_update_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int mode)
 {
-    (void)nx; (void)ny; (void)nz;
-    if (H <= 0 || W <= 0 || T <= 0) return 256;
+    if (H <= 0 || W <= 0 || T <= 0 || nx < 2 || ny < 2 || nz < 2) return 256;
     const uint32_t npix = (uint32_t)H * (uint32_t)W;
     if (mode == MB_MODE_EXACT) return splat_workspace_bytes(npix);
     int chunk = T < MB_DEFAULT_CHUNK_FRAMES ? T : MB_DEFAULT_CHUNK_FRAMES;
     while (chunk > 1 && (uint64_t)chunk * npix * 8 >= 0xffffffffull) chunk /= 2;
-    return mbk_batch_workspace_bytes(npix, chunk);
+    return mbk_batch_workspace_bytes(npix, nx, ny, nz, chunk);
 }
 
 MB_API int mb_layer_update(void *stream_, const float *rays, const float *depth, const float *features,
@@ -204,9 +203,9 @@ MB_API int mb_layer_update(void *stream_, const float *rays, const float *depth,
     const size_t feat_stride = (size_t)fh * fw * F;
     if (mode == MB_MODE_FAST) {
         // batched brick pipeline, as many frames per chunk as the workspace holds
-        const int chunk = workspace ? mbk_batch_frames_that_fit(npix, workspace_bytes, T) : 0;
+        const int chunk = workspace ? mbk_batch_frames_that_fit(npix, nx, ny, nz, workspace_bytes, T) : 0;
         MB_REQUIRE(chunk >= 1, "mb_layer_update: workspace too small (%zu < %zu)", workspace_bytes,
-                   mbk_batch_workspace_bytes(npix, 1));
+                   mbk_batch_workspace_bytes(npix, nx, ny, nz, 1));
         for (int t = 0; t < T; t += chunk) {
             const int n = T - t < chunk ? T - t : chunk;
             int rc = mbk_batch_update(stream, rays, depth + (size_t)t * npix,

@@ -128,9 +128,11 @@ k_emit_entries(const uint4 *__restrict__ rec, const uint32_t *__restrict__ cnt, 
             }
 }
 
-// brick segment starts of the sorted entry list (order of the list is irrelevant: bricks are independent)
+// One (start, entries) pair per touched brick of the sorted entry list, bucketed by log2(entries) so
+// that the reduce kernel can hand out the heaviest bricks first.  The order inside a bucket is
+// arbitrary: bricks are independent, the result does not depend on it.
 __global__ void __launch_bounds__(256)
-k_brick_heads(const uint32_t *__restrict__ keys, uint32_t nmax, uint32_t *__restrict__ starts,
+k_brick_heads(const uint32_t *__restrict__ keys, uint32_t nmax, uint2 *__restrict__ bricks,
               uint32_t *__restrict__ counters)
 {
     const uint32_t n = min(nmax, counters[MB_CNT_ENTRIES]);
@@ -138,19 +140,40 @@ k_brick_heads(const uint32_t *__restrict__ keys, uint32_t nmax, uint32_t *__rest
     const int lane = threadIdx.x & 31;
     const bool head = i < n && (i == 0 || keys[i - 1] != keys[i]);
     const uint32_t m = __ballot_sync(FULL, head);
-    if (m) {
-        const int leader = __ffs(m) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(&counters[MB_CNT_BRICKS], (uint32_t)__popc(m));
-        base = __shfl_sync(FULL, base, leader);
-        if (head) starts[base + __popc(m & ((1u << lane) - 1u))] = i;
+    if (m == 0) return;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&counters[MB_CNT_BRICKS], (uint32_t)__popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (!head) return;
+    const uint32_t key = keys[i];
+    uint32_t lo = i + 1, hi = n;                       // first index past the brick's segment
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (keys[mid] == key) lo = mid + 1; else hi = mid;
     }
+    const uint32_t count = lo - i;
+    bricks[base + __popc(m & ((1u << lane) - 1u))] = make_uint2(i, count);
+    atomicAdd(&counters[MB_CNT_BUCKET + (31 - __clz(count))], 1u);
+}
+
+__global__ void __launch_bounds__(256)
+k_brick_order(const uint2 *__restrict__ bricks, uint32_t *__restrict__ order, uint32_t *__restrict__ counters)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counters[MB_CNT_BRICKS]) return;
+    const int bucket = 31 - __clz(bricks[i].y);
+    uint32_t base = 0;
+    for (int b = 31; b > bucket; --b) base += counters[MB_CNT_BUCKET + b];
+    order[base + atomicAdd(&counters[MB_CNT_FILL + bucket], 1u)] = i;
 }
 
 // ---------------------------------------------------------------------------------------------
 // K2
 struct ReduceArgs {
-    const uint32_t *keys, *pids, *starts;
+    const uint32_t *keys, *pids;
+    const uint2 *bricks;        // (start, entries) per touched brick
+    const uint32_t *order;      // brick list indices, heaviest bricks first
     uint32_t *counters;
     uint32_t nmax;
     const uint4 *rec;
@@ -160,30 +183,25 @@ struct ReduceArgs {
     const int64_t *class_ids;   // [T][np] or null
     int F;
     float *map;                 // [S0][S1][S2][F], updated in place
-    float *affine_a;            // optional [S0*S1*S2]: multiplied by the frame's a (affine output mode)
+    float *affine_a;            // optional [S0*S1*S2]: multiplied by every frame's a (affine output mode)
     MbBricks g;
     float alpha;
 };
 
-template <int VEC> struct VecT;
-template <> struct VecT<1> { typedef float type; };
-template <> struct VecT<2> { typedef float2 type; };
-template <> struct VecT<4> { typedef float4 type; };
-
 template <int VEC>
 __device__ __forceinline__ void vec_load(float (&dst)[VEC], const float *p)
-{
-    if (VEC == 1) dst[0] = __ldg(p);
-    if (VEC == 2) { const float2 v = __ldg((const float2 *)p); dst[0] = v.x; dst[1] = v.y; }
-    if (VEC == 4) { const float4 v = __ldg((const float4 *)p); dst[0] = v.x; dst[1] = v.y; dst[VEC > 2 ? 2 : 0] = v.z; dst[VEC > 2 ? 3 : 0] = v.w; }
-}
-
-template <int VEC>
-__device__ __forceinline__ void vec_load_rw(float (&dst)[VEC], const float *p)
 {
     if (VEC == 1) dst[0] = *p;
     if (VEC == 2) { const float2 v = *(const float2 *)p; dst[0] = v.x; dst[1] = v.y; }
     if (VEC == 4) { const float4 v = *(const float4 *)p; dst[0] = v.x; dst[1] = v.y; dst[VEC > 2 ? 2 : 0] = v.z; dst[VEC > 2 ? 3 : 0] = v.w; }
+}
+
+template <int VEC>
+__device__ __forceinline__ void vec_load_nc(float (&dst)[VEC], const float *p)
+{
+    if (VEC == 1) dst[0] = __ldg(p);
+    if (VEC == 2) { const float2 v = __ldg((const float2 *)p); dst[0] = v.x; dst[1] = v.y; }
+    if (VEC == 4) { const float4 v = __ldg((const float4 *)p); dst[0] = v.x; dst[1] = v.y; dst[VEC > 2 ? 2 : 0] = v.z; dst[VEC > 2 ? 3 : 0] = v.w; }
 }
 
 template <int VEC>
@@ -194,49 +212,61 @@ __device__ __forceinline__ void vec_store(float *p, const float (&src)[VEC])
     if (VEC == 4) *(float4 *)p = make_float4(src[0], src[1], src[VEC > 2 ? 2 : 0], src[VEC > 2 ? 3 : 0]);
 }
 
-// Applies one frame's affine update to the map row of voxel `vox`.
-template <int VEC, int IT>
-__device__ __forceinline__ void apply_row(const ReduceArgs &A, size_t vox, int lane, float W, float S2,
-                                          const float (&acc)[IT][VEC])
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem_dst, const void *gmem_src)
 {
-    const float a = 1.0f - A.alpha * S2 / W;
-    const float sc = A.alpha / W;
-    float *row = A.map + vox * (size_t)A.F;
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// One frame's affine update of a voxel row held in registers: row = a*row + (alpha/W)*B, a = 1 - alpha*S2/W.
+template <int VEC, int IT>
+__device__ __forceinline__ void apply_frame(float alpha, float W, float S2, float (&row)[IT][VEC],
+                                            float (&acc)[IT][VEC], float &aprod)
+{
+    const float a = 1.0f - alpha * S2 / W;
+    const float sc = alpha / W;
 #pragma unroll
-    for (int it = 0; it < IT; ++it) {
-        const int c = (it * 32 + lane) * VEC;
-        if (c < A.F) {
-            float old[VEC], out[VEC];
-            vec_load_rw<VEC>(old, row + c);
+    for (int it = 0; it < IT; ++it)
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) out[j] = fmaf(a, old[j], sc * acc[it][j]);
-            vec_store<VEC>(row + c, out);
+        for (int j = 0; j < VEC; ++j) {
+            row[it][j] = fmaf(a, row[it][j], sc * acc[it][j]);
+            acc[it][j] = 0.f;
         }
-    }
-    if (A.affine_a != nullptr && lane == 0) A.affine_a[vox] = A.affine_a[vox] * a;
+    aprod *= a;
 }
 
-template <int VEC, int IT, bool ONEHOT>
+// Shared memory plan of k_brick_reduce (dynamic):
+//   s_con   [2048] float4  sorted contributions {w, w^2, tag = entry | frame offset << 8, -}
+//   s_part  [64][RS]       partial sums of a frame that continues into the next chunk
+//   s_feat  [256][F]       staged feature rows of the chunk's entries (STAGE only)
+//   s_cnt   [8][64], s_start[64], s_total[64], s_W[64], s_S2[64], s_esrc[256], s_eframe[256]
+template <int VEC, int IT, bool ONEHOT, bool STAGE>
 __global__ void __launch_bounds__(RED_THREADS)
 k_brick_reduce(const ReduceArgs A)
 {
-    constexpr int RS = 32 * VEC * IT;                       // floats per partial row
+    constexpr int RS = 32 * VEC * IT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *s_part = (float *)smem_raw;                      // [64][RS] partial sums of a multi-chunk frame
-    float2 *s_con = (float2 *)(s_part + 64 * RS);           // [RED_CONTRIB] sorted (w, source row)
-    uint32_t *s_cnt = (uint32_t *)(s_con + RED_CONTRIB);    // [RED_WARPS][64]
-    uint32_t *s_start = s_cnt + RED_WARPS * 64;             // [64]
-    uint32_t *s_total = s_start + 64;                       // [64]
-    float *s_W = (float *)(s_total + 64);                   // [64]
-    float *s_S2 = s_W + 64;                                 // [64]
-    __shared__ uint32_t s_ticket, s_frame0;
+    float4 *s_con = (float4 *)smem_raw;
+    float *s_part = (float *)(s_con + RED_CONTRIB);
+    uint32_t *s_cnt = (uint32_t *)(s_part + 64 * RS);
+    uint32_t *s_start = s_cnt + RED_WARPS * 64;
+    uint32_t *s_total = s_start + 64;
+    float *s_W = (float *)(s_total + 64);
+    float *s_S2 = s_W + 64;
+    uint32_t *s_esrc = (uint32_t *)(s_S2 + 64);
+    uint32_t *s_eframe = s_esrc + RED_THREADS;
+    float *s_feat = (float *)(s_eframe + RED_THREADS);
+    __shared__ uint32_t s_ticket, s_next, s_cont;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t ltmask = (1u << lane) - 1u;
     const uint32_t n = min(A.nmax, A.counters[MB_CNT_ENTRIES]);
     const uint32_t nbricks = A.counters[MB_CNT_BRICKS];
     const uint32_t np = A.fi.np;
+    const int F = A.F;
 
-    for (int i = tid; i < 64 * RS; i += RED_THREADS) s_part[i] = 0.f;
     if (tid < 64) { s_W[tid] = 0.f; s_S2[tid] = 0.f; }
 
     for (;;) {
@@ -245,54 +275,58 @@ k_brick_reduce(const ReduceArgs A)
         __syncthreads();
         const uint32_t ticket = s_ticket;
         if (ticket >= nbricks) break;
-        uint32_t pos = A.starts[ticket];
-        const uint32_t bkey = A.keys[pos];
+        const uint2 brick = A.bricks[A.order[ticket]];
+        const uint32_t bend = brick.x + brick.y;
+        const uint32_t bkey = A.keys[brick.x];
         const int bz = bkey % A.g.N2, by = (bkey / A.g.N2) % A.g.N1, bx = bkey / (A.g.N2 * A.g.N1);
+        const int org0 = bx * 4, org1 = by * 4, org2 = bz * 4;
         uint32_t pending = NO_FRAME;          // frame whose partial sums sit in s_part / s_W / s_S2
 
-        for (;;) {
-            // ---- next chunk: the leading entries of [pos, pos + 256) that share one frame ----------
+        for (uint32_t pos = brick.x; pos < bend; pos += RED_THREADS) {
+            // ---- entries of this chunk ---------------------------------------------------------------
             const uint32_t idx = pos + tid;
-            const bool mine = idx < n && A.keys[idx] == bkey;
-            const uint32_t pid = mine ? A.pids[idx] : 0u;
+            const bool active = idx < bend;
+            const int nact = min((uint32_t)RED_THREADS, bend - pos);
+            const uint32_t pid = active ? A.pids[idx] : 0u;
             const uint32_t frame = pid / np;
-            if (tid == 0) s_frame0 = mine ? frame : NO_FRAME;
-            __syncthreads();
-            const uint32_t f0 = s_frame0;
-            const bool active = mine && frame == f0;
-            const int nact = f0 == NO_FRAME ? 0 : __syncthreads_count(active);
-            const bool last = nact < RED_THREADS;           // the frame's entries end inside this chunk
-
-            // ---- a finished multi-chunk frame whose sums are still pending ------------------------
-            if (pending != NO_FRAME && pending != f0) {
-                for (int v = warp; v < 64; v += RED_WARPS) {
-                    const float W = s_W[v];
-                    if (W > 0.f) {
-                        float acc[IT][VEC];
-#pragma unroll
-                        for (int it = 0; it < IT; ++it)
-#pragma unroll
-                            for (int j = 0; j < VEC; ++j) {
-                                acc[it][j] = s_part[v * RS + (it * 32 + lane) * VEC + j];
-                                s_part[v * RS + (it * 32 + lane) * VEC + j] = 0.f;
-                            }
-                        const size_t vox = ((size_t)(bx * 4 + (v >> 4)) * A.g.S1 + (by * 4 + ((v >> 2) & 3))) * A.g.S2 +
-                                           (bz * 4 + (v & 3));
-                        apply_row<VEC, IT>(A, vox, lane, W, s_S2[v], acc);
-                        __syncwarp();
-                        if (lane == 0) { s_W[v] = 0.f; s_S2[v] = 0.f; }
-                    }
-                }
-                pending = NO_FRAME;
-            }
-            if (f0 == NO_FRAME) break;                       // brick finished
-
-            // ---- lanes = entries: the 8 contributions of this thread's entry -----------------------
-            uint32_t cv[8];      // local voxel (0..63) or 0xff
-            float cw[8];
             uint32_t src = 0;
+            if (active) {
+                const uint32_t p = pid - frame * np;
+                if (ONEHOT) {
+                    src = (uint32_t)A.class_ids[pid];
+                } else if (A.fi.kx == 1 && A.fi.ky == 1) {
+                    src = frame * A.fhw + p;
+                } else {
+                    const uint32_t y = p / A.fi.W, x = p - y * A.fi.W;
+                    src = frame * A.fhw + (y / A.fi.ky) * A.fi.fw + x / A.fi.kx;
+                }
+            }
+            s_esrc[tid] = src;
+            s_eframe[tid] = frame;
+            if (tid == nact - 1) {
+                // does the chunk's last frame continue in the next chunk of this brick?
+                const uint32_t nxt = idx + 1;
+                s_cont = (nact == RED_THREADS && nxt < bend && A.pids[nxt] / np == frame) ? 1u : 0u;
+            }
+            for (int i = tid; i < RED_WARPS * 64; i += RED_THREADS) s_cnt[i] = 0;
+            if (tid == 0) s_next = 0;
+            __syncthreads();
+            const uint32_t f_first = s_eframe[0], f_last = s_eframe[nact - 1];
+            const bool cont = s_cont != 0;
+
+            if (STAGE) {   // feature rows of the chunk -> shared memory, asynchronously
+                const int per_row = F / VEC;
+                for (int i = tid; i < nact * per_row; i += RED_THREADS) {
+                    const int e = i / per_row, c = (i - e * per_row) * VEC;
+                    cp_async<4 * VEC>(s_feat + e * F + c, A.features + (size_t)s_esrc[e] * F + c);
+                }
+            }
+
+            // ---- lanes = entries: one contribution per voxel parity class ------------------------------
+            uint32_t cv[8];      // local voxel (0..63) or 0xff
+            float cw[8], cw2[8];
 #pragma unroll
-            for (int s = 0; s < 8; ++s) { cv[s] = 0xffu; cw[s] = 0.f; }
+            for (int k = 0; k < 8; ++k) { cv[k] = 0xffu; cw[k] = 0.f; cw2[k] = 0.f; }
             if (active) {
                 const uint4 r = A.rec[pid];
                 const Footprint f = footprint_of(r.x, A.g);
@@ -304,44 +338,54 @@ k_brick_reduce(const ReduceArgs A)
                     wl[a] = low ? __fsub_rn(0.5f, q[a]) : __fsub_rn(1.5f, q[a]);
                     wu[a] = low ? __fadd_rn(q[a], 0.5f) : __fsub_rn(q[a], 0.5f);
                 }
-                const int org[3] = { bx * 4, by * 4, bz * 4 };
+                const int l0lo = f.lo[0] - org0, l1lo = f.lo[1] - org1, l2lo = f.lo[2] - org2;
+                const int l0hi = f.hi[0] - org0, l1hi = f.hi[1] - org1, l2hi = f.hi[2] - org2;
+                const bool clamped = f.lo[0] == f.hi[0] || f.lo[1] == f.hi[1] || f.lo[2] == f.hi[2];
+                if (!clamped) {
+                    // the two neighbours of an axis have opposite parity: class k takes, per axis, the
+                    // neighbour whose coordinate parity equals the class bit
+                    const int p0 = f.lo[0] & 1, p1 = f.lo[1] & 1, p2 = f.lo[2] & 1;
 #pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const int c0 = (s & 4) ? f.hi[0] : f.lo[0], c1 = (s & 2) ? f.hi[1] : f.lo[1],
-                              c2 = (s & 1) ? f.hi[2] : f.lo[2];
-                    const int l0 = c0 - org[0], l1 = c1 - org[1], l2 = c2 - org[2];
-                    if ((unsigned)l0 < 4u && (unsigned)l1 < 4u && (unsigned)l2 < 4u) {
-                        cv[s] = (uint32_t)((l0 << 4) | (l1 << 2) | l2);
-                        const float w0 = (s & 4) ? wu[0] : wl[0], w1 = (s & 2) ? wu[1] : wl[1],
-                                    w2 = (s & 1) ? wu[2] : wl[2];
-                        cw[s] = __fadd_rn(1e-9f, __fmul_rn(__fmul_rn(w0, w1), w2));   // projection.py:319-323
+                    for (int k = 0; k < 8; ++k) {
+                        const bool u0 = (((k >> 2) & 1) != p0), u1 = (((k >> 1) & 1) != p1), u2 = ((k & 1) != p2);
+                        const int l0 = u0 ? l0hi : l0lo, l1 = u1 ? l1hi : l1lo, l2 = u2 ? l2hi : l2lo;
+                        if ((unsigned)l0 < 4u && (unsigned)l1 < 4u && (unsigned)l2 < 4u) {
+                            cv[k] = (uint32_t)((l0 << 4) | (l1 << 2) | l2);
+                            const float w = __fadd_rn(1e-9f, __fmul_rn(__fmul_rn(u0 ? wu[0] : wl[0], u1 ? wu[1] : wl[1]),
+                                                                       u2 ? wu[2] : wl[2]));   // projection.py:319-323
+                            cw[k] = w;
+                            cw2[k] = w * w;
+                        }
                     }
-                }
-                const uint32_t p = pid - f0 * np;
-                if (ONEHOT) {
-                    src = (uint32_t)A.class_ids[pid];
-                } else if (A.fi.kx == 1 && A.fi.ky == 1) {
-                    src = f0 * A.fhw + p;
                 } else {
-                    const uint32_t y = p / A.fi.W, x = p - y * A.fi.W;
-                    src = f0 * A.fhw + (y / A.fi.ky) * A.fi.fw + x / A.fi.kx;
+                    // map border: clamping folds neighbours onto one voxel (projection.py:280-291); the
+                    // folded slots are summed into one contribution of that voxel's class
+                    for (int s = 0; s < 8; ++s) {
+                        const int l0 = (s & 4) ? l0hi : l0lo, l1 = (s & 2) ? l1hi : l1lo, l2 = (s & 1) ? l2hi : l2lo;
+                        if ((unsigned)l0 < 4u && (unsigned)l1 < 4u && (unsigned)l2 < 4u) {
+                            const float w = __fadd_rn(1e-9f, __fmul_rn(__fmul_rn((s & 4) ? wu[0] : wl[0], (s & 2) ? wu[1] : wl[1]),
+                                                                       (s & 1) ? wu[2] : wl[2]));
+                            const int cls = ((l0 & 1) << 2) | ((l1 & 1) << 1) | (l2 & 1);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                if (k == cls) {
+                                    cv[k] = (uint32_t)((l0 << 4) | (l1 << 2) | l2);
+                                    cw[k] += w;
+                                    cw2[k] += w * w;
+                                }
+                        }
+                    }
                 }
             }
 
-            // ---- stable counting sort of the chunk's contributions by voxel ------------------------
-            for (int i = tid; i < RED_WARPS * 64; i += RED_THREADS) s_cnt[i] = 0;
-            __syncthreads();
+            // ---- stable counting sort of the contributions by voxel (entry order inside a voxel) --------
             uint32_t rk[8];
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                const bool ok = cv[s] != 0xffu;
-                const uint32_t m = __match_any_sync(FULL, ok ? cv[s] : 64u + lane);
-                const uint32_t rank = __popc(m & ((1u << lane) - 1u));
-                const uint32_t prev = ok ? s_cnt[warp * 64 + cv[s]] : 0u;
-                __syncwarp();
-                if (ok && rank == 0) s_cnt[warp * 64 + cv[s]] = prev + __popc(m);
-                __syncwarp();
-                rk[s] = prev + rank;
+            for (int k = 0; k < 8; ++k) {
+                const bool ok = cv[k] != 0xffu;
+                const uint32_t m = __match_any_sync(FULL, ok ? cv[k] : 64u + lane);
+                rk[k] = __popc(m & ltmask);
+                if (ok && rk[k] == 0) s_cnt[warp * 64 + cv[k]] = __popc(m);   // classes never share a voxel
             }
             __syncthreads();
             if (tid < 64) {
@@ -368,101 +412,137 @@ k_brick_reduce(const ReduceArgs A)
                 s_start[2 * lane + 1] = ex + t0;
             }
             __syncthreads();
+            {
+                const uint32_t tag = (uint32_t)tid | ((frame - f_first) << 8);
 #pragma unroll
-            for (int s = 0; s < 8; ++s)
-                if (cv[s] != 0xffu)
-                    s_con[s_start[cv[s]] + s_cnt[warp * 64 + cv[s]] + rk[s]] =
-                        make_float2(cw[s], __uint_as_float(src));
+                for (int k = 0; k < 8; ++k)
+                    if (cv[k] != 0xffu)
+                        s_con[s_start[cv[k]] + s_cnt[warp * 64 + cv[k]] + rk[k]] =
+                            make_float4(cw[k], cw2[k], __uint_as_float(tag), 0.f);
+            }
+            if (STAGE) cp_async_wait_all();
             __syncthreads();
 
-            // ---- lanes = channels: one warp per voxel --------------------------------------------------
-            const bool merge = pending == f0;
-            for (int v = warp; v < 64; v += RED_WARPS) {
+            // ---- lanes = channels: one warp per voxel walks its contributions in frame order -----------
+            const uint32_t goff_last = f_last - f_first;
+            for (;;) {
+                int v = 0;
+                if (lane == 0) v = (int)atomicAdd(&s_next, 1u);
+                v = __shfl_sync(FULL, v, 0);
+                if (v >= 64) break;
                 const uint32_t nv = s_total[v];
-                const float Wp = merge ? s_W[v] : 0.f;
-                if (nv == 0 && !(last && Wp > 0.f)) continue;
-                float acc[IT][VEC];
+                const float Wp = pending != NO_FRAME ? s_W[v] : 0.f;
+                if (nv == 0 && !(Wp > 0.f)) continue;
+                if (nv == 0 && cont && goff_last == 0) continue;       // still pending, nothing new
+
+                const size_t vox = ((size_t)(org0 + (v >> 4)) * A.g.S1 + (org1 + ((v >> 2) & 3))) * A.g.S2 +
+                                   (org2 + (v & 3));
+                float *grow = A.map + vox * (size_t)F;
+                float row[IT][VEC], acc[IT][VEC];
 #pragma unroll
-                for (int it = 0; it < IT; ++it)
+                for (int it = 0; it < IT; ++it) {
+                    const int ch = (it * 32 + lane) * VEC;
+                    if (ch < F) vec_load<VEC>(row[it], grow + ch);
+                    else
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) acc[it][j] = 0.f;
-                float W = 0.f, S2 = 0.f;
-                const float2 *con = s_con + s_start[v];
-                for (uint32_t k = 0; k < nv; ++k) {
-                    const float2 c = con[k];
-                    const float w = c.x, w2 = w * w;
-                    W += w;
-                    S2 += w2;
-                    if (ONEHOT) {
-                        const int cls = (int)__float_as_uint(c.y);
-#pragma unroll
-                        for (int it = 0; it < IT; ++it)
-#pragma unroll
-                            for (int j = 0; j < VEC; ++j)
-                                if ((it * 32 + lane) * VEC + j == cls) acc[it][j] += w2;
-                    } else {
-                        const float *frow = A.features + (size_t)__float_as_uint(c.y) * A.F;
-#pragma unroll
-                        for (int it = 0; it < IT; ++it) {
-                            const int ch = (it * 32 + lane) * VEC;
-                            if (ch < A.F) {
-                                float f[VEC];
-                                vec_load<VEC>(f, frow + ch);
-#pragma unroll
-                                for (int j = 0; j < VEC; ++j) acc[it][j] = fmaf(w2, f[j], acc[it][j]);
-                            }
-                        }
-                    }
+                        for (int j = 0; j < VEC; ++j) row[it][j] = 0.f;
                 }
-                if (merge && Wp > 0.f) {                      // earlier chunks of the same frame
-                    W = Wp + W;
-                    S2 = s_S2[v] + S2;
+                float W = 0.f, S2 = 0.f, aprod = 1.0f;
+                bool dirty = false;                                     // row changed: write it back
+                uint32_t cur = 0;                                       // frame offset being accumulated
+                if (Wp > 0.f) {                                         // carried in from the previous chunk
+                    W = Wp;
+                    S2 = s_S2[v];
 #pragma unroll
                     for (int it = 0; it < IT; ++it)
 #pragma unroll
-                        for (int j = 0; j < VEC; ++j) {
-                            acc[it][j] = s_part[v * RS + (it * 32 + lane) * VEC + j] + acc[it][j];
-                            if (last) s_part[v * RS + (it * 32 + lane) * VEC + j] = 0.f;
-                        }
-                }
-                if (last) {
-                    const size_t vox = ((size_t)(bx * 4 + (v >> 4)) * A.g.S1 + (by * 4 + ((v >> 2) & 3))) * A.g.S2 +
-                                       (bz * 4 + (v & 3));
-                    apply_row<VEC, IT>(A, vox, lane, W, S2, acc);
-                    __syncwarp();
-                    if (merge && lane == 0) { s_W[v] = 0.f; s_S2[v] = 0.f; }
+                        for (int j = 0; j < VEC; ++j) acc[it][j] = s_part[v * RS + (it * 32 + lane) * VEC + j];
                 } else {
 #pragma unroll
                     for (int it = 0; it < IT; ++it)
 #pragma unroll
+                        for (int j = 0; j < VEC; ++j) acc[it][j] = 0.f;
+                    if (nv) cur = __float_as_uint(s_con[s_start[v]].z) >> 8;
+                }
+                const float4 *con = s_con + s_start[v];
+                for (uint32_t k = 0; k < nv; ++k) {
+                    const float4 c = con[k];
+                    const uint32_t tag = __float_as_uint(c.z);
+                    const uint32_t e = tag & 255u, g = tag >> 8;
+                    if (g != cur) {                                     // next frame: close the previous one
+                        apply_frame<VEC, IT>(A.alpha, W, S2, row, acc, aprod);
+                        dirty = true;
+                        W = 0.f; S2 = 0.f;
+                        cur = g;
+                    }
+                    W += c.x;
+                    S2 += c.y;
+                    if (ONEHOT) {
+                        const int cls = (int)s_esrc[e];
+#pragma unroll
+                        for (int it = 0; it < IT; ++it)
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j)
+                                if ((it * 32 + lane) * VEC + j == cls) acc[it][j] += c.y;
+                    } else {
+                        const float *frow = STAGE ? s_feat + e * F : A.features + (size_t)s_esrc[e] * F;
+#pragma unroll
+                        for (int it = 0; it < IT; ++it) {
+                            const int ch = (it * 32 + lane) * VEC;
+                            if (ch < F) {
+                                float fv[VEC];
+                                if (STAGE) vec_load<VEC>(fv, frow + ch); else vec_load_nc<VEC>(fv, frow + ch);
+#pragma unroll
+                                for (int j = 0; j < VEC; ++j) acc[it][j] = fmaf(c.y, fv[j], acc[it][j]);
+                            }
+                        }
+                    }
+                }
+                const bool keep = cont && cur == goff_last;            // the frame goes on in the next chunk
+                if (keep) {
+#pragma unroll
+                    for (int it = 0; it < IT; ++it)
+#pragma unroll
                         for (int j = 0; j < VEC; ++j) s_part[v * RS + (it * 32 + lane) * VEC + j] = acc[it][j];
-                    __syncwarp();
-                    if (lane == 0) { s_W[v] = W; s_S2[v] = S2; }
+                } else {
+                    apply_frame<VEC, IT>(A.alpha, W, S2, row, acc, aprod);
+                    dirty = true;
+                }
+                __syncwarp();
+                if (lane == 0) { s_W[v] = keep ? W : 0.f; s_S2[v] = keep ? S2 : 0.f; }
+                if (dirty) {
+#pragma unroll
+                    for (int it = 0; it < IT; ++it) {
+                        const int ch = (it * 32 + lane) * VEC;
+                        if (ch < F) vec_store<VEC>(grow + ch, row[it]);
+                    }
+                    if (A.affine_a != nullptr && lane == 0) A.affine_a[vox] = A.affine_a[vox] * aprod;
                 }
             }
-            pending = last ? NO_FRAME : f0;
-            pos += (uint32_t)nact;
+            pending = cont ? f_last : NO_FRAME;
             __syncthreads();
         }
     }
 }
 
-size_t reduce_smem_bytes(int VEC, int IT)
+size_t reduce_smem_bytes(int VEC, int IT, int F, bool stage)
 {
-    return (size_t)64 * 32 * VEC * IT * 4 + (size_t)RED_CONTRIB * 8 + (size_t)(RED_WARPS * 64 + 64 + 64) * 4 + 2 * 64 * 4;
+    return (size_t)RED_CONTRIB * 16 + (size_t)64 * 32 * VEC * IT * 4 + (size_t)(RED_WARPS * 64 + 64 * 4 + 2 * RED_THREADS) * 4 +
+           (stage ? (size_t)RED_THREADS * F * 4 : 0);
 }
 
-template <int VEC, int IT>
+template <int VEC, int IT, bool STAGE>
 int launch_brick_reduce(cudaStream_t stream, const ReduceArgs &A)
 {
-    const size_t smem = reduce_smem_bytes(VEC, IT);
+    const size_t smem = reduce_smem_bytes(VEC, IT, A.F, STAGE);
     const bool onehot = A.class_ids != nullptr;
-    auto kern = onehot ? k_brick_reduce<VEC, IT, true> : k_brick_reduce<VEC, IT, false>;
-    MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = onehot ? k_brick_reduce<VEC, IT, true, false> : k_brick_reduce<VEC, IT, false, STAGE>;
+    const size_t bytes = onehot ? reduce_smem_bytes(VEC, IT, A.F, false) : smem;
+    MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     int per_sm = 1;
-    MB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RED_THREADS, smem));
+    MB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RED_THREADS, bytes));
     if (per_sm < 1) per_sm = 1;
-    kern<<<MB_NUM_SMS * per_sm, RED_THREADS, smem, stream>>>(A);
+    kern<<<MB_NUM_SMS * per_sm, RED_THREADS, bytes, stream>>>(A);
     MB_LAUNCHED();
     return MB_OK;
 }
@@ -476,26 +556,36 @@ int dispatch_brick_reduce(cudaStream_t stream, const ReduceArgs &A)
     if (F % 4 == 0 && a16 && m16) vec = 4;
     else if (F % 2 == 0 && (uintptr_t)A.features % 8 == 0 && (uintptr_t)A.map % 8 == 0) vec = 2;
     const int need = (F + 32 * vec - 1) / (32 * vec);
-#define MB_GO(V, I) return launch_brick_reduce<V, I>(stream, A)
-    if (vec == 4) { if (need <= 1) MB_GO(4, 1); if (need <= 2) MB_GO(4, 2); if (need <= 4) MB_GO(4, 4); }
-    if (vec == 2) { if (need <= 1) MB_GO(2, 1); if (need <= 2) MB_GO(2, 2); if (need <= 4) MB_GO(2, 4); }
-    if (vec == 1) { if (need <= 1) MB_GO(1, 1); if (need <= 2) MB_GO(1, 2); if (need <= 4) MB_GO(1, 4); if (need <= 8) MB_GO(1, 8); }
+    // feature rows are staged through shared memory while a chunk's rows fit in 64 KB
+    const bool stage = A.features != nullptr && (size_t)RED_THREADS * F * 4 <= 65536;
+#define MB_GO(V, I) return launch_brick_reduce<V, I, false>(stream, A)
+#define MB_GO_STAGED(V, I)                                                                            \
+    do {                                                                                              \
+        if (stage) return launch_brick_reduce<V, I, true>(stream, A);                                 \
+        return launch_brick_reduce<V, I, false>(stream, A);                                           \
+    } while (0)
+    if (vec == 4) { if (need <= 1) MB_GO_STAGED(4, 1); if (need <= 2) MB_GO(4, 2); if (need <= 4) MB_GO(4, 4); }
+    if (vec == 2) { if (need <= 1) MB_GO_STAGED(2, 1); if (need <= 2) MB_GO(2, 2); if (need <= 4) MB_GO(2, 4); }
+    if (vec == 1) { if (need <= 1) MB_GO_STAGED(1, 1); if (need <= 2) MB_GO_STAGED(1, 2); if (need <= 4) MB_GO(1, 4); if (need <= 8) MB_GO(1, 8); }
 #undef MB_GO
+#undef MB_GO_STAGED
     mb_set_error("feature_size %d not supported by the batched path (<= 512 if a multiple of 4, <= 256 otherwise)", F);
     return MB_ERR_ARG;
 }
 
 struct BatchBuffers {
     uint4 *rec;
-    uint32_t *cnt, *offs, *keys_a, *keys_b, *pids_a, *pids_b, *starts, *counters;
+    uint32_t *cnt, *offs, *keys_a, *keys_b, *pids_a, *pids_b, *order, *counters;
+    uint2 *bricks;
     char *scan_ws, *sort_ws;
     size_t scan_bytes, sort_bytes;
 };
 
-size_t carve_batch(BatchBuffers &b, void *ws, size_t bytes, uint32_t ntotal)
+size_t carve_batch(BatchBuffers &b, void *ws, size_t bytes, uint32_t ntotal, size_t nbrick_cap)
 {
     MbArena a(ws, bytes);
     const size_t nent = (size_t)ntotal * 8;           // upper bound: 8 bricks per pixel
+    if (nbrick_cap > nent) nbrick_cap = nent;
     b.rec = a.take<uint4>(ntotal);
     b.cnt = a.take<uint32_t>(ntotal);
     b.offs = a.take<uint32_t>(ntotal);
@@ -503,8 +593,9 @@ size_t carve_batch(BatchBuffers &b, void *ws, size_t bytes, uint32_t ntotal)
     b.keys_b = a.take<uint32_t>(nent);
     b.pids_a = a.take<uint32_t>(nent);
     b.pids_b = a.take<uint32_t>(nent);
-    b.starts = a.take<uint32_t>(nent);        // one per touched brick (<= entries)
-    b.counters = a.take<uint32_t>(64);
+    b.bricks = a.take<uint2>(nbrick_cap);     // one per touched brick
+    b.order = a.take<uint32_t>(nbrick_cap);
+    b.counters = a.take<uint32_t>(MB_NUM_COUNTERS);
     b.scan_bytes = mb_scan_workspace_bytes(ntotal);
     b.scan_ws = a.take<char>(b.scan_bytes);
     b.sort_bytes = mb_sort_workspace_bytes((uint32_t)nent);
@@ -514,27 +605,31 @@ size_t carve_batch(BatchBuffers &b, void *ws, size_t bytes, uint32_t ntotal)
 
 }  // namespace
 
-// frames per internal chunk for a given workspace; 0 if even one frame does not fit
-int mbk_batch_frames_that_fit(uint32_t npix, size_t workspace_bytes, int T)
+static size_t total_bricks(int nx, int ny, int nz)
 {
-    {
-        BatchBuffers all;
-        if ((uint64_t)T * npix * 8 < 0xffffffffull && carve_batch(all, nullptr, 0, (uint32_t)T * npix) <= workspace_bytes)
-            return T;
-    }
+    const MbBricks g = make_bricks(ny - 1, nx - 1, nz - 1);
+    return (size_t)g.N0 * g.N1 * g.N2;
+}
+
+// frames per internal chunk for a given workspace; 0 if even one frame does not fit
+int mbk_batch_frames_that_fit(uint32_t npix, int nx, int ny, int nz, size_t workspace_bytes, int T)
+{
+    const size_t cap = total_bricks(nx, ny, nz);
+    BatchBuffers b;
+    if ((uint64_t)T * npix * 8 < 0xffffffffull && carve_batch(b, nullptr, 0, (uint32_t)T * npix, cap) <= workspace_bytes)
+        return T;
     int best = 0;
     for (int t = 1; t <= T; t = t < 8 ? t + 1 : t * 2) {
         if ((uint64_t)t * npix * 8 >= 0xffffffffull) break;
-        BatchBuffers b;
-        if (carve_batch(b, nullptr, 0, (uint32_t)t * npix) <= workspace_bytes) best = t; else break;
+        if (carve_batch(b, nullptr, 0, (uint32_t)t * npix, cap) <= workspace_bytes) best = t; else break;
     }
     return best;
 }
 
-size_t mbk_batch_workspace_bytes(uint32_t npix, int T)
+size_t mbk_batch_workspace_bytes(uint32_t npix, int nx, int ny, int nz, int T)
 {
     BatchBuffers b;
-    return carve_batch(b, nullptr, 0, (uint32_t)T * npix);
+    return carve_batch(b, nullptr, 0, (uint32_t)T * npix, total_bricks(nx, ny, nz));
 }
 
 // One chunk of T frames (T * npix * 8 < 2^32).
@@ -550,7 +645,8 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     MB_REQUIRE(g.S0 <= 2046 && g.S1 <= 2046 && g.S2 <= 1022, "map too large for the packed voxel record");
     MB_REQUIRE(class_ids != nullptr || (uint64_t)T * fh * fw < 0xffffffffull, "too many feature rows per chunk");
     BatchBuffers b;
-    MB_REQUIRE(carve_batch(b, workspace, workspace_bytes, ntotal) <= workspace_bytes, "batch workspace too small");
+    MB_REQUIRE(carve_batch(b, workspace, workspace_bytes, ntotal, (size_t)g.N0 * g.N1 * g.N2) <= workspace_bytes,
+               "batch workspace too small");
     const uint32_t nent = ntotal * 8u;
 
     dim3 grid((npix + 255) / 256, (unsigned)T);
@@ -568,11 +664,17 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     rc = mb_sort_pairs(stream, b.keys_a, b.pids_a, b.keys_b, b.pids_b, nent, b.counters + MB_CNT_ENTRIES, bits, false,
                        b.sort_ws, b.sort_bytes, &keys, &pids);
     if (rc) return rc;
-    k_brick_heads<<<(nent + 255) / 256, 256, 0, stream>>>(keys, nent, b.starts, b.counters);
+    k_brick_heads<<<(nent + 255) / 256, 256, 0, stream>>>(keys, nent, b.bricks, b.counters);
     MB_LAUNCHED();
+    {
+        size_t cap = (size_t)g.N0 * g.N1 * g.N2;
+        if (cap > nent) cap = nent;
+        k_brick_order<<<(unsigned)((cap + 255) / 256), 256, 0, stream>>>(b.bricks, b.order, b.counters);
+        MB_LAUNCHED();
+    }
 
     ReduceArgs A;
-    A.keys = keys; A.pids = pids; A.starts = b.starts; A.counters = b.counters; A.nmax = nent; A.rec = b.rec;
+    A.keys = keys; A.pids = pids; A.bricks = b.bricks; A.order = b.order; A.counters = b.counters; A.nmax = nent; A.rec = b.rec;
     A.fi = MbFeatIndex{ npix, (uint32_t)W, (uint32_t)(H / fh), (uint32_t)(W / fw), (uint32_t)fw };
     A.fhw = (uint32_t)fh * (uint32_t)fw;
     A.features = features; A.class_ids = class_ids; A.F = F; A.map = map; A.affine_a = affine_a; A.g = g;

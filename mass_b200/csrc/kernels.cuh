@@ -7,7 +7,9 @@ constexpr int MB_CNT_HEADS = 0;      // number of voxel segments (= voxels touch
 constexpr int MB_CNT_ENTRIES = 1;    // batched path: (brick, pixel) entries emitted
 constexpr int MB_CNT_BRICKS = 2;     // batched path: bricks touched
 constexpr int MB_CNT_TICKET = 3;     // batched path: next brick to hand to a CTA
-constexpr int MB_NUM_COUNTERS = 8;
+constexpr int MB_CNT_BUCKET = 8;     // [32] bricks per log2(entries) bucket
+constexpr int MB_CNT_FILL = 40;      // [32] placement cursors of the buckets
+constexpr int MB_NUM_COUNTERS = 72;
 
 // How a contribution's point id maps to its feature row.
 //   dense:   row = point id (upsample == 0), or the nearest-upsampled source pixel
@@ -46,8 +48,8 @@ int mbk_voxel_reduce(cudaStream_t stream, const uint32_t *keys, const uint32_t *
                      float *map, const MbGrid &g, float alpha, int mode);
 
 // batch.cu: batched brick pipeline (affine form of the update; see the file header)
-int mbk_batch_frames_that_fit(uint32_t npix, size_t workspace_bytes, int T);
-size_t mbk_batch_workspace_bytes(uint32_t npix, int T);
+int mbk_batch_frames_that_fit(uint32_t npix, int nx, int ny, int nz, size_t workspace_bytes, int T);
+size_t mbk_batch_workspace_bytes(uint32_t npix, int nx, int ny, int nz, int T);
 int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth, const float *features,
                      const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw, int F,
                      const float *bins_x, int nx, const float *bins_y, int ny, const float *bins_z, int nz,
