@@ -97,6 +97,11 @@ int mb_layer_update(void *stream, const float *rays, const float *depth, const f
                     float min_ray_depth, float max_ray_depth, int mode, void *workspace,
                     size_t workspace_bytes);
 
+/* Synchronises `stream` and returns the sticky error bits the batched kernels left in the workspace of
+ * the last MB_MODE_FAST call: 0 = fine, bit 0 = an in-order row update gave up waiting for its
+ * predecessor (never expected; the map is then not trustworthy). */
+int mb_layer_update_status(void *stream, const void *workspace, uint32_t *error_bits_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "mb_update_feature_map": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _i32,
                                      _i32, _f32, _i32, _vp, _sz]),
     "mb_layer_update_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "mb_layer_update_status": (_i32, [_vp, _vp, _vp]),
     "mb_layer_update": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32,
                                _vp, _i32, _vp, _i32, _vp, _f32, _f32, _f32, _i32, _vp, _sz]),
 }

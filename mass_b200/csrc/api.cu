@@ -162,6 +162,18 @@ MB_API int mb_update_feature_map(void *stream_, const int64_t *ind0, const int64
                            mode);
 }
 
+// Waits for `stream` and reports the sticky error bits the batched kernels left in the workspace
+// of the last MB_MODE_FAST call (0 = fine; bit 0: an in-order update wait timed out).
+MB_API int mb_layer_update_status(void *stream_, const void *workspace, uint32_t *error_bits_host)
+{
+    MB_REQUIRE(workspace && error_bits_host, "mb_layer_update_status: null pointer");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MB_CHECK_CUDA(cudaMemcpyAsync(error_bits_host, (const uint32_t *)workspace + MB_CNT_ERROR, sizeof(uint32_t),
+                                  cudaMemcpyDeviceToHost, stream));
+    MB_CHECK_CUDA(cudaStreamSynchronize(stream));
+    return MB_OK;
+}
+
 // ---- a6..a9 ---------------------------------------------------------------------------------
 // frames the batched path fuses per internal chunk when the caller sizes the workspace with
 // mb_layer_update_workspace_bytes (a larger workspace is used if given)

@@ -23,6 +23,19 @@
 #include "kernels.cuh"
 #include "geometry.cuh"
 
+// Optional phase timing of k_brick_reduce_qw (build with -DMB_PHASE_TIMING; read with
+// mb_debug_phase_cycles).  Not compiled into the shipped library.
+#ifdef MB_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define MB_T0() long long t_prev = clock64(); long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define MB_TICK(i) do { const long long t_now = clock64(); t_acc[i] += t_now - t_prev; t_prev = t_now; } while (0)
+#define MB_TFLUSH() do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&g_phase_cycles[i_], (unsigned long long)t_acc[i_]); } while (0)
+#else
+#define MB_T0()
+#define MB_TICK(i)
+#define MB_TFLUSH()
+#endif
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -180,6 +193,7 @@ struct ReduceArgs {
     MbFeatIndex fi;             // np = pixels per frame
     uint32_t fhw;               // feature rows per frame
     const float *features;      // [T][fhw][F] or null
+    const float *features_end;  // one past the last feature row
     const int64_t *class_ids;   // [T][np] or null
     int F;
     float *map;                 // [S0][S1][S2][F], updated in place
@@ -525,6 +539,447 @@ k_brick_reduce(const ReduceArgs A)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K2, group form (even feature sizes).  The work item is one (brick, frame) group of the sorted
+// entry list.  Everything expensive about a group -- its per-voxel sums W, S2, B -- does not
+// depend on the map, so groups are reduced fully in parallel by whichever CTA draws them; only the
+// final row update  new = a*old + b  has to follow the frame order of the brick.  That order is
+// enforced by a per-brick progress counter: a group applies its update when the counter has
+// reached its first entry, then advances it past its last entry (release/acquire through L2).
+// Groups are handed out frame-major, so a group's predecessor was always handed out earlier, to a
+// CTA that never waits on a later ticket: the wait cannot deadlock (and is bounded anyway).
+// Frame-major dispatch also means each frame's feature rows are consumed by all bricks at about
+// the same time: they are read from HBM once and re-read from L2.
+//
+// Inside a group: 128 entries per chunk, two threads per entry (4 voxel parity classes each);
+// LPV lanes own one voxel with 8 channels per lane (four packed f32x2 FMAs per contribution),
+// 32/LPV voxels per warp pass; feature rows of the chunk are staged in shared memory by cp.async.
+constexpr int GRP_CHUNK = 128;                 // entries per chunk
+constexpr int GRP_CONTRIB = GRP_CHUNK * 8;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;      // polls (~ seconds) before a wait gives up and flags an error
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// group heads of the brick-sorted entry list: entry i starts a group if its brick or its frame differs
+// from entry i-1.  One 32-bit mask + count per 32 entries; brick heads also reset the brick's
+// progress counter to the brick's first entry.
+__global__ void __launch_bounds__(256)
+k_group_flags(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pids, uint32_t nmax, uint32_t np,
+              uint32_t *__restrict__ masks, uint32_t *__restrict__ wcount, uint32_t *__restrict__ progress,
+              uint32_t *__restrict__ counters)
+{
+    const uint32_t n = min(nmax, counters[MB_CNT_ENTRIES]);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool head = false;
+    if (i < n) {
+        const uint32_t k = keys[i];
+        const bool bhead = i == 0 || keys[i - 1] != k;
+        head = bhead || pids[i - 1] / np != pids[i] / np;
+        if (bhead) progress[k] = i;
+    }
+    const uint32_t m = __ballot_sync(FULL, head);
+    if ((threadIdx.x & 31) == 0) {
+        masks[i >> 5] = m;
+        wcount[i >> 5] = __popc(m);
+    }
+}
+
+// ordered list of group starts (+ sentinel n at the end) and the per-frame group histogram
+__global__ void __launch_bounds__(256)
+k_group_emit(const uint32_t *__restrict__ masks, const uint32_t *__restrict__ woffs, const uint32_t *__restrict__ pids,
+             uint32_t nmax, uint32_t np, uint32_t *__restrict__ gstart, uint32_t *__restrict__ frame_hist,
+             uint32_t *__restrict__ counters)
+{
+    const uint32_t n = min(nmax, counters[MB_CNT_ENTRIES]);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if ((i & ~31u) >= n) return;
+    const uint32_t m = masks[i >> 5];
+    const uint32_t base = woffs[i >> 5];
+    if (i < n && ((m >> lane) & 1u)) {
+        gstart[base + __popc(m & ((1u << lane) - 1u))] = i;
+        atomicAdd(&frame_hist[pids[i] / np], 1u);
+    }
+    if (n > 0 && i == n - 1) {
+        const uint32_t total = base + __popc(m & (lane == 31 ? 0xffffffffu : ((2u << lane) - 1u)));
+        counters[MB_CNT_GROUPS] = total;
+        gstart[total] = n;
+    }
+}
+
+// frame-major dispatch order (any order inside a frame: its groups belong to different bricks)
+__global__ void __launch_bounds__(256)
+k_group_order(const uint32_t *__restrict__ gstart, const uint32_t *__restrict__ pids, uint32_t np, int T,
+              const uint32_t *__restrict__ frame_hist, uint32_t *__restrict__ frame_fill, uint32_t *__restrict__ order,
+              const uint32_t *__restrict__ counters)
+{
+    extern __shared__ uint32_t s_base[];      // exclusive prefix of frame_hist
+    for (int t = threadIdx.x; t < T; t += blockDim.x) s_base[t] = frame_hist[t];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int t = 0; t < T; ++t) { const uint32_t c = s_base[t]; s_base[t] = run; run += c; }
+    }
+    __syncthreads();
+    const uint32_t ngroups = counters[MB_CNT_GROUPS];
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
+        const uint32_t f = pids[gstart[g]] / np;
+        order[s_base[f] + atomicAdd(&frame_fill[f], 1u)] = g;
+    }
+}
+
+struct GroupArgs {
+    const uint32_t *keys, *pids, *gstart, *order;
+    uint32_t *progress, *counters;
+    const uint4 *rec;
+    MbFeatIndex fi;
+    uint32_t fhw;
+    const float *features, *features_end;
+    int F;
+    float *map, *affine_a;
+    MbBricks g;
+    float alpha;
+};
+
+template <int LPV, bool STAGE>
+__global__ void __launch_bounds__(RED_THREADS)
+k_group_reduce(const GroupArgs A)
+{
+    constexpr int G = 32 / LPV;               // voxels per warp pass
+    constexpr int RSP = LPV * 8;              // floats per voxel row in s_out
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *s_con = (float4 *)smem_raw;                         // [GRP_CONTRIB] sorted {w, w^2, feature row tag, -}
+    float *s_out = (float *)(s_con + GRP_CONTRIB);              // [64][RSP] per-voxel B of the group
+    uint32_t *s_cnt = (uint32_t *)(s_out + 64 * RSP);           // [RED_WARPS][64]
+    uint32_t *s_start = s_cnt + RED_WARPS * 64;                 // [64]
+    uint32_t *s_total = s_start + 64;                           // [64]
+    uint32_t *s_vorder = s_total + 64;                          // [64]
+    float *s_W = (float *)(s_vorder + 64);                      // [64]
+    float *s_S2 = s_W + 64;                                     // [64]
+    uint32_t *s_esrc = (uint32_t *)(s_S2 + 64);                 // [GRP_CHUNK]
+    float *s_feat = (float *)(s_esrc + GRP_CHUNK);              // [GRP_CHUNK][RSF] staged feature rows
+    __shared__ uint32_t s_ticket, s_next;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sub = lane % LPV, grp = lane / LPV;
+    const int ent = tid & (GRP_CHUNK - 1), half = tid >> 7;     // entry of this thread, class half (0: 0-3, 1: 4-7)
+    const uint32_t ltmask = (1u << lane) - 1u;
+    const uint32_t ngroups = A.counters[MB_CNT_GROUPS];
+    const uint32_t np = A.fi.np;
+    const int F = A.F;
+    const int RSF = (F + 3) & ~3;
+    const int cb = sub * 8;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_ticket = atomicAdd(&A.counters[MB_CNT_TICKET], 1u);
+        if (tid < 64) { s_W[tid] = 0.f; s_S2[tid] = 0.f; }
+        __syncthreads();
+        const uint32_t ticket = s_ticket;
+        if (ticket >= ngroups) break;
+        const uint32_t gi = A.order[ticket];
+        const uint32_t gbeg = A.gstart[gi], gend = A.gstart[gi + 1];
+        const uint32_t bkey = A.keys[gbeg];
+        const uint32_t frame = A.pids[gbeg] / np;
+        const int bz = bkey % A.g.N2, by = (bkey / A.g.N2) % A.g.N1, bx = bkey / (A.g.N2 * A.g.N1);
+        const int org0 = bx * 4, org1 = by * 4, org2 = bz * 4;
+
+        for (uint32_t pos = gbeg; pos < gend; pos += GRP_CHUNK) {
+            const int nact = min((uint32_t)GRP_CHUNK, gend - pos);
+            const bool active = ent < nact;
+            const uint32_t pid = active ? A.pids[pos + ent] : 0u;
+            uint32_t src = 0;
+            if (active) {
+                const uint32_t p = pid - frame * np;
+                if (A.fi.kx == 1 && A.fi.ky == 1) {
+                    src = frame * A.fhw + p;
+                } else {
+                    const uint32_t y = p / A.fi.W, x = p - y * A.fi.W;
+                    src = frame * A.fhw + (y / A.fi.ky) * A.fi.fw + x / A.fi.kx;
+                }
+            }
+            if (half == 0) s_esrc[ent] = src;
+            for (int i = tid; i < RED_WARPS * 64; i += RED_THREADS) s_cnt[i] = 0;
+            if (tid == 0) s_next = 0;
+            __syncthreads();
+
+            if (STAGE) {
+                // feature rows -> shared memory in 16-byte pieces, from the 16-byte boundary at or before
+                // the row (rows are 8-byte aligned: the data starts 0 or 2 floats into the slot)
+                const int per_row = RSF >> 2;
+                for (int i = tid; i < nact * per_row; i += RED_THREADS) {
+                    const int e = i / per_row, c = i - e * per_row;
+                    const size_t first = ((size_t)s_esrc[e] * F) & ~(size_t)3;
+                    const float *gp = A.features + first + 4 * c;
+                    float *d = s_feat + e * RSF + 4 * c;
+                    if (gp + 4 <= A.features_end) cp_async<16>(d, gp);
+                    else if (gp + 2 <= A.features_end) cp_async<8>(d, gp);         // tail of the very last row
+                }
+            }
+
+            // ---- two threads per entry: one contribution per voxel parity class (4 classes each) -------
+            uint32_t cv[4];
+            float cw[4], cw2[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { cv[k] = 0xffu; cw[k] = 0.f; cw2[k] = 0.f; }
+            if (active) {
+                const uint4 r = A.rec[pid];
+                const Footprint f = footprint_of(r.x, A.g);
+                const float q[3] = { __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w) };
+                float wl[3], wu[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {               // projection.py:300-316
+                    const bool low = q[a] < 0.5f;
+                    wl[a] = low ? __fsub_rn(0.5f, q[a]) : __fsub_rn(1.5f, q[a]);
+                    wu[a] = low ? __fadd_rn(q[a], 0.5f) : __fsub_rn(q[a], 0.5f);
+                }
+                const int l0lo = f.lo[0] - org0, l1lo = f.lo[1] - org1, l2lo = f.lo[2] - org2;
+                const int l0hi = f.hi[0] - org0, l1hi = f.hi[1] - org1, l2hi = f.hi[2] - org2;
+                const bool clamped = f.lo[0] == f.hi[0] || f.lo[1] == f.hi[1] || f.lo[2] == f.hi[2];
+                if (!clamped) {
+                    // the two neighbours of an axis have opposite parity: class (half, k) takes, per axis,
+                    // the neighbour whose coordinate parity equals the class bit
+                    const int p0 = f.lo[0] & 1, p1 = f.lo[1] & 1, p2 = f.lo[2] & 1;
+                    const bool u0 = half != p0;
+                    const int l0 = u0 ? l0hi : l0lo;
+                    const float w0 = u0 ? wu[0] : wl[0];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const bool u1 = (((k >> 1) & 1) != p1), u2 = ((k & 1) != p2);
+                        const int l1 = u1 ? l1hi : l1lo, l2 = u2 ? l2hi : l2lo;
+                        if ((unsigned)l0 < 4u && (unsigned)l1 < 4u && (unsigned)l2 < 4u) {
+                            cv[k] = (uint32_t)((l0 << 4) | (l1 << 2) | l2);
+                            const float w = __fadd_rn(1e-9f, __fmul_rn(__fmul_rn(w0, u1 ? wu[1] : wl[1]),
+                                                                       u2 ? wu[2] : wl[2]));   // projection.py:319-323
+                            cw[k] = w;
+                            cw2[k] = w * w;
+                        }
+                    }
+                } else {
+                    // map border: clamping folds neighbours onto one voxel (projection.py:280-291); folded
+                    // slots are summed into one contribution of that voxel's class
+                    for (int s = 0; s < 8; ++s) {
+                        const int l0 = (s & 4) ? l0hi : l0lo, l1 = (s & 2) ? l1hi : l1lo, l2 = (s & 1) ? l2hi : l2lo;
+                        if ((unsigned)l0 < 4u && (unsigned)l1 < 4u && (unsigned)l2 < 4u && (l0 & 1) == half) {
+                            const float w = __fadd_rn(1e-9f, __fmul_rn(__fmul_rn((s & 4) ? wu[0] : wl[0], (s & 2) ? wu[1] : wl[1]),
+                                                                       (s & 1) ? wu[2] : wl[2]));
+                            const int cls = ((l1 & 1) << 1) | (l2 & 1);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (k == cls) {
+                                    cv[k] = (uint32_t)((l0 << 4) | (l1 << 2) | l2);
+                                    cw[k] += w;
+                                    cw2[k] += w * w;
+                                }
+                        }
+                    }
+                }
+            }
+
+            // ---- stable counting sort of the contributions by voxel (entry order inside a voxel) ---------
+            uint32_t rk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool ok = cv[k] != 0xffu;
+                const uint32_t m = __match_any_sync(FULL, ok ? cv[k] : 64u + lane);
+                rk[k] = __popc(m & ltmask);
+                if (ok && rk[k] == 0) s_cnt[warp * 64 + cv[k]] = __popc(m);   // classes never share a voxel
+            }
+            __syncthreads();
+            if (tid < 64) {
+                uint32_t run = 0;
+#pragma unroll
+                for (int w = 0; w < RED_WARPS; ++w) {
+                    const uint32_t c = s_cnt[w * 64 + tid];
+                    s_cnt[w * 64 + tid] = run;
+                    run += c;
+                }
+                s_total[tid] = run;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t t0 = s_total[2 * lane], t1 = s_total[2 * lane + 1];
+                uint32_t inc = t0 + t1;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t u = __shfl_up_sync(FULL, inc, d);
+                    if (lane >= d) inc += u;
+                }
+                const uint32_t ex = inc - (t0 + t1);
+                s_start[2 * lane] = ex;
+                s_start[2 * lane + 1] = ex + t0;
+            } else if (tid >= 64 && tid < 128) {
+                // voxels by decreasing contribution count: a warp pass takes G neighbours of this order, so
+                // the G segments walked in lock-step have similar lengths
+                const int v = tid - 64;
+                const uint32_t mine = s_total[v];
+                int rank = 0;
+                for (int u = 0; u < 64; ++u) {
+                    const uint32_t o = s_total[u];
+                    rank += (o > mine || (o == mine && u < v)) ? 1 : 0;
+                }
+                s_vorder[rank] = (uint32_t)v;
+            }
+            __syncthreads();
+            {
+                // tag: where the entry's feature row sits (staged: float offset in s_feat; else entry slot)
+                uint32_t tag = (uint32_t)ent;
+                if (STAGE) tag = (uint32_t)(ent * RSF) + (uint32_t)(((size_t)src * F) & 3);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (cv[k] != 0xffu)
+                        s_con[s_start[cv[k]] + s_cnt[warp * 64 + cv[k]] + rk[k]] =
+                            make_float4(cw[k], cw2[k], __uint_as_float(tag), 0.f);
+            }
+            if (STAGE) cp_async_wait_all();
+            __syncthreads();
+
+            // ---- LPV lanes per voxel, G voxels per warp pass -----------------------------------------------
+            for (;;) {
+                int t = 0;
+                if (lane == 0) t = (int)atomicAdd(&s_next, (uint32_t)G);
+                t = __shfl_sync(FULL, t, 0);
+                if (t >= 64) break;
+                const int v = (int)s_vorder[t + grp];
+                const uint32_t nv = s_total[v];
+                const uint32_t maxnv = __reduce_max_sync(FULL, nv);
+                if (maxnv == 0) break;                                   // sorted by count: nothing left
+                float2 acc[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = make_float2(0.f, 0.f);
+                float W = 0.f, S2 = 0.f;
+                const float Wp = s_W[v], S2p = s_S2[v];                  // sums of earlier chunks of a long group
+                const float4 *con = s_con + s_start[v];
+                for (uint32_t k = 0; k < maxnv; ++k) {
+                    if (k < nv) {
+                        const float4 c = con[k];
+                        const uint32_t tag = __float_as_uint(c.z);
+                        W += c.x;
+                        S2 += c.y;
+                        const float2 w2 = make_float2(c.y, c.y);
+                        if (STAGE) {
+                            const float *frow = s_feat + tag + cb;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[j] = ffma2(w2, *(const float2 *)(frow + 2 * j), acc[j]);
+                        } else {
+                            const float *frow = A.features + (size_t)s_esrc[tag] * F + cb;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (cb + 2 * j < F) acc[j] = ffma2(w2, __ldg((const float2 *)(frow + 2 * j)), acc[j]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (nv) {
+                    float *o = s_out + v * RSP + cb;
+                    if (Wp > 0.f) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 p = *(const float2 *)(o + 2 * j);
+                            acc[j] = make_float2(p.x + acc[j].x, p.y + acc[j].y);
+                        }
+                        W = Wp + W;
+                        S2 = S2p + S2;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) *(float2 *)(o + 2 * j) = acc[j];
+                    if (sub == 0) { s_W[v] = W; s_S2[v] = S2; }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- the brick's turn: all earlier frames of this brick have been applied ---------------------
+        if (tid == 0) {
+            uint32_t spins = 0;
+            while (ld_acquire(A.progress + bkey) != gbeg) {
+                __nanosleep(64);
+                if (++spins > SPIN_LIMIT) { atomicOr(&A.counters[MB_CNT_ERROR], 1u); break; }
+            }
+        }
+        __syncthreads();
+        for (int t = warp * G; t < 64; t += RED_WARPS * G) {
+            const int v = t + grp;
+            const float W = s_W[v];
+            if (W > 0.f) {
+                const float r = __frcp_rn(W);
+                const float sc = A.alpha * r;
+                const float a = 1.0f - sc * s_S2[v];
+                const size_t vox = ((size_t)(org0 + (v >> 4)) * A.g.S1 + (org1 + ((v >> 2) & 3))) * A.g.S2 +
+                                   (org2 + (v & 3));
+                float *grow = A.map + vox * (size_t)F + cb;
+                const float *o = s_out + v * RSP + cb;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (cb + 2 * j < F) {
+                        const float2 old = __ldcg((const float2 *)(grow + 2 * j));       // L2: written by other SMs
+                        const float2 b = *(const float2 *)(o + 2 * j);
+                        *(float2 *)(grow + 2 * j) = ffma2(make_float2(a, a), old, make_float2(sc * b.x, sc * b.y));
+                    }
+                if (A.affine_a != nullptr && sub == 0) A.affine_a[vox] = __ldcg(A.affine_a + vox) * a;
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release(A.progress + bkey, gend);
+    }
+}
+
+size_t group_smem_bytes(int LPV, int F, bool stage)
+{
+    const int RSF = (F + 3) & ~3;
+    return (size_t)GRP_CONTRIB * 16 + (size_t)64 * LPV * 8 * 4 + (size_t)(RED_WARPS * 64 + 64 * 5 + GRP_CHUNK) * 4 +
+           (stage ? (size_t)(GRP_CHUNK * RSF + LPV * 8 + 4) * 4 : 0);
+}
+
+template <int LPV>
+int launch_group_reduce(cudaStream_t stream, const GroupArgs &A, bool stage)
+{
+    const size_t smem = group_smem_bytes(LPV, A.F, stage);
+    auto kern = stage ? k_group_reduce<LPV, true> : k_group_reduce<LPV, false>;
+    MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    MB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RED_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    kern<<<MB_NUM_SMS * per_sm, RED_THREADS, smem, stream>>>(A);
+    MB_LAUNCHED();
+    return MB_OK;
+}
+
+bool group_form_applies(const float *features, const float *map, int F)
+{
+    return features != nullptr && F % 2 == 0 && F <= 256 && (uintptr_t)features % 16 == 0 && (uintptr_t)map % 8 == 0;
+}
+
+int dispatch_group_reduce(cudaStream_t stream, const GroupArgs &A)
+{
+    const int lanes = (A.F + 7) / 8;
+    const bool stage = (size_t)GRP_CHUNK * ((A.F + 3) & ~3) * 4 <= 49152;
+    if (lanes <= 1) return launch_group_reduce<1>(stream, A, stage);
+    if (lanes <= 2) return launch_group_reduce<2>(stream, A, stage);
+    if (lanes <= 4) return launch_group_reduce<4>(stream, A, stage);
+    if (lanes <= 8) return launch_group_reduce<8>(stream, A, stage);
+    if (lanes <= 16) return launch_group_reduce<16>(stream, A, stage);
+    return launch_group_reduce<32>(stream, A, stage);
+}
+
 size_t reduce_smem_bytes(int VEC, int IT, int F, bool stage)
 {
     return (size_t)RED_CONTRIB * 16 + (size_t)64 * 32 * VEC * IT * 4 + (size_t)(RED_WARPS * 64 + 64 * 4 + 2 * RED_THREADS) * 4 +
@@ -576,16 +1031,19 @@ int dispatch_brick_reduce(cudaStream_t stream, const ReduceArgs &A)
 struct BatchBuffers {
     uint4 *rec;
     uint32_t *cnt, *offs, *keys_a, *keys_b, *pids_a, *pids_b, *order, *counters;
+    uint32_t *masks, *wcount, *woffs, *gstart, *progress, *frame_hist;   // group form
     uint2 *bricks;
     char *scan_ws, *sort_ws;
     size_t scan_bytes, sort_bytes;
 };
 
-size_t carve_batch(BatchBuffers &b, void *ws, size_t bytes, uint32_t ntotal, size_t nbrick_cap)
+size_t carve_batch(BatchBuffers &b, void *ws, size_t bytes, uint32_t ntotal, size_t nbricks_total, int T)
 {
     MbArena a(ws, bytes);
     const size_t nent = (size_t)ntotal * 8;           // upper bound: 8 bricks per pixel
+    size_t nbrick_cap = nbricks_total;
     if (nbrick_cap > nent) nbrick_cap = nent;
+    b.counters = a.take<uint32_t>(MB_NUM_COUNTERS);   // first: mb_layer_update_status finds them at offset 0
     b.rec = a.take<uint4>(ntotal);
     b.cnt = a.take<uint32_t>(ntotal);
     b.offs = a.take<uint32_t>(ntotal);
@@ -594,9 +1052,14 @@ size_t carve_batch(BatchBuffers &b, void *ws, size_t bytes, uint32_t ntotal, siz
     b.pids_a = a.take<uint32_t>(nent);
     b.pids_b = a.take<uint32_t>(nent);
     b.bricks = a.take<uint2>(nbrick_cap);     // one per touched brick
-    b.order = a.take<uint32_t>(nbrick_cap);
-    b.counters = a.take<uint32_t>(MB_NUM_COUNTERS);
-    b.scan_bytes = mb_scan_workspace_bytes(ntotal);
+    b.order = a.take<uint32_t>(nent);         // brick form: one per brick; group form: one per group
+    b.masks = a.take<uint32_t>(nent / 32 + 1);
+    b.wcount = a.take<uint32_t>(nent / 32 + 1);
+    b.woffs = a.take<uint32_t>(nent / 32 + 1);
+    b.gstart = a.take<uint32_t>(nent + 1);
+    b.progress = a.take<uint32_t>(nbricks_total);
+    b.frame_hist = a.take<uint32_t>(2 * (size_t)T);
+    b.scan_bytes = mb_scan_workspace_bytes(ntotal);          // >= the group-word scan (nent / 32 words)
     b.scan_ws = a.take<char>(b.scan_bytes);
     b.sort_bytes = mb_sort_workspace_bytes((uint32_t)nent);
     b.sort_ws = a.take<char>(b.sort_bytes);
@@ -616,12 +1079,12 @@ int mbk_batch_frames_that_fit(uint32_t npix, int nx, int ny, int nz, size_t work
 {
     const size_t cap = total_bricks(nx, ny, nz);
     BatchBuffers b;
-    if ((uint64_t)T * npix * 8 < 0xffffffffull && carve_batch(b, nullptr, 0, (uint32_t)T * npix, cap) <= workspace_bytes)
+    if ((uint64_t)T * npix * 8 < 0xffffffffull && carve_batch(b, nullptr, 0, (uint32_t)T * npix, cap, T) <= workspace_bytes)
         return T;
     int best = 0;
     for (int t = 1; t <= T; t = t < 8 ? t + 1 : t * 2) {
         if ((uint64_t)t * npix * 8 >= 0xffffffffull) break;
-        if (carve_batch(b, nullptr, 0, (uint32_t)t * npix, cap) <= workspace_bytes) best = t; else break;
+        if (carve_batch(b, nullptr, 0, (uint32_t)t * npix, cap, t) <= workspace_bytes) best = t; else break;
     }
     return best;
 }
@@ -629,7 +1092,7 @@ int mbk_batch_frames_that_fit(uint32_t npix, int nx, int ny, int nz, size_t work
 size_t mbk_batch_workspace_bytes(uint32_t npix, int nx, int ny, int nz, int T)
 {
     BatchBuffers b;
-    return carve_batch(b, nullptr, 0, (uint32_t)T * npix, total_bricks(nx, ny, nz));
+    return carve_batch(b, nullptr, 0, (uint32_t)T * npix, total_bricks(nx, ny, nz), T);
 }
 
 // One chunk of T frames (T * npix * 8 < 2^32).
@@ -644,8 +1107,9 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     const MbBricks g = make_bricks(ny - 1, nx - 1, nz - 1);
     MB_REQUIRE(g.S0 <= 2046 && g.S1 <= 2046 && g.S2 <= 1022, "map too large for the packed voxel record");
     MB_REQUIRE(class_ids != nullptr || (uint64_t)T * fh * fw < 0xffffffffull, "too many feature rows per chunk");
+    MB_REQUIRE(T <= 8192, "too many frames per chunk");
     BatchBuffers b;
-    MB_REQUIRE(carve_batch(b, workspace, workspace_bytes, ntotal, (size_t)g.N0 * g.N1 * g.N2) <= workspace_bytes,
+    MB_REQUIRE(carve_batch(b, workspace, workspace_bytes, ntotal, (size_t)g.N0 * g.N1 * g.N2, T) <= workspace_bytes,
                "batch workspace too small");
     const uint32_t nent = ntotal * 8u;
 
@@ -664,6 +1128,29 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     rc = mb_sort_pairs(stream, b.keys_a, b.pids_a, b.keys_b, b.pids_b, nent, b.counters + MB_CNT_ENTRIES, bits, false,
                        b.sort_ws, b.sort_bytes, &keys, &pids);
     if (rc) return rc;
+    if (group_form_applies(features, map, F)) {
+        const uint32_t nwords = nent / 32 + 1;
+        MB_CHECK_CUDA(cudaMemsetAsync(b.frame_hist, 0, 2 * (size_t)T * sizeof(uint32_t), stream));
+        k_group_flags<<<(nent + 255) / 256, 256, 0, stream>>>(keys, pids, nent, npix, b.masks, b.wcount, b.progress,
+                                                              b.counters);
+        MB_LAUNCHED();
+        rc = mb_exclusive_scan_u32(stream, b.wcount, b.woffs, nwords, b.scan_ws, b.scan_bytes);
+        if (rc) return rc;
+        k_group_emit<<<(nent + 255) / 256, 256, 0, stream>>>(b.masks, b.woffs, pids, nent, npix, b.gstart, b.frame_hist,
+                                                             b.counters);
+        MB_LAUNCHED();
+        k_group_order<<<MB_NUM_SMS * 2, 256, (size_t)T * sizeof(uint32_t), stream>>>(
+            b.gstart, pids, npix, T, b.frame_hist, b.frame_hist + T, b.order, b.counters);
+        MB_LAUNCHED();
+        GroupArgs G;
+        G.keys = keys; G.pids = pids; G.gstart = b.gstart; G.order = b.order; G.progress = b.progress;
+        G.counters = b.counters; G.rec = b.rec;
+        G.fi = MbFeatIndex{ npix, (uint32_t)W, (uint32_t)(H / fh), (uint32_t)(W / fw), (uint32_t)fw };
+        G.fhw = (uint32_t)fh * (uint32_t)fw;
+        G.features = features; G.features_end = features + (size_t)T * fh * fw * F;
+        G.F = F; G.map = map; G.affine_a = affine_a; G.g = g; G.alpha = alpha;
+        return dispatch_group_reduce(stream, G);
+    }
     k_brick_heads<<<(nent + 255) / 256, 256, 0, stream>>>(keys, nent, b.bricks, b.counters);
     MB_LAUNCHED();
     {
@@ -677,7 +1164,18 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     A.keys = keys; A.pids = pids; A.bricks = b.bricks; A.order = b.order; A.counters = b.counters; A.nmax = nent; A.rec = b.rec;
     A.fi = MbFeatIndex{ npix, (uint32_t)W, (uint32_t)(H / fh), (uint32_t)(W / fw), (uint32_t)fw };
     A.fhw = (uint32_t)fh * (uint32_t)fw;
-    A.features = features; A.class_ids = class_ids; A.F = F; A.map = map; A.affine_a = affine_a; A.g = g;
+    A.features = features; A.features_end = features ? features + (size_t)T * fh * fw * F : nullptr;
+    A.class_ids = class_ids; A.F = F; A.map = map; A.affine_a = affine_a; A.g = g;
     A.alpha = alpha;
     return dispatch_brick_reduce(stream, A);
 }
+
+#ifdef MB_PHASE_TIMING
+extern "C" __attribute__((visibility("default"))) int mb_debug_phase_cycles(unsigned long long *out, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
+    return 0;
+}
+#endif

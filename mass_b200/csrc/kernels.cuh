@@ -6,7 +6,9 @@
 constexpr int MB_CNT_HEADS = 0;      // number of voxel segments (= voxels touched by the frame)
 constexpr int MB_CNT_ENTRIES = 1;    // batched path: (brick, pixel) entries emitted
 constexpr int MB_CNT_BRICKS = 2;     // batched path: bricks touched
-constexpr int MB_CNT_TICKET = 3;     // batched path: next brick to hand to a CTA
+constexpr int MB_CNT_TICKET = 3;     // batched path: next brick / group to hand to a CTA
+constexpr int MB_CNT_GROUPS = 4;     // batched path: (brick, frame) groups
+constexpr int MB_CNT_ERROR = 5;      // batched path: sticky error bits (1: an ordering wait timed out)
 constexpr int MB_CNT_BUCKET = 8;     // [32] bricks per log2(entries) bucket
 constexpr int MB_CNT_FILL = 40;      // [32] placement cursors of the buckets
 constexpr int MB_NUM_COUNTERS = 72;

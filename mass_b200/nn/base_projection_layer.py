@@ -116,6 +116,20 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
             mode, _lib.ptr(ws), ws.numel()))
         return self
 
+    def check(self):
+        """Synchronises and raises if the batched kernels flagged an error during the last
+        non-exact update (an in-order row update that timed out: never expected)."""
+        if self.exact or self._ws.buf is None:
+            torch.cuda.synchronize(self.data.device)
+            return self
+        import ctypes
+        bits = ctypes.c_uint32(0)
+        _lib.check(_lib.lib().mb_layer_update_status(_lib.stream_ptr(self.data.device), _lib.ptr(self._ws.buf),
+                                                     ctypes.byref(bits)))
+        if bits.value:
+            raise RuntimeError("libmassb200: batched update reported error bits 0x%x" % bits.value)
+        return self
+
     def update(self, observation: Dict[str, Any]):
         """Fuse one observation into the map; returns self.
         Reference: base_projection_layer.py:282-343.  Keys: position [3] (x, y, z-up),

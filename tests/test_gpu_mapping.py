@@ -297,7 +297,7 @@ def test_batched_fast_path_vs_oracle(dev, oracle, F, fdiv):
     frames = _random_frames(rng, T, H, W, H // fdiv, W // fdiv, F)
     ref = _oracle_run(oracle, kw, frames, T)
     batch = make_layer(kw, dev, exact=False)
-    batch.update_batch(frames)
+    batch.update_batch(frames).check()
     got = batch.data.cpu().numpy()
     assert np.array_equal((got != 0).any(-1), (ref != 0).any(-1))
     assert_close_rel(got, ref)
@@ -360,7 +360,7 @@ def test_batched_c2_prefix_vs_oracle(dev, oracle):
     for f in frames:
         ref.update(f)
     L = make_layer(kw, dev, exact=False)
-    L.update_batch(frames)
+    L.update_batch(frames).check()
     got = L.data.cpu().numpy()
     assert np.array_equal((got != 0).any(-1), (ref.data != 0).any(-1))
     idx = np.flatnonzero((ref.data != 0).any(-1).reshape(-1))
