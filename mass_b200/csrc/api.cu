@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -177,14 +178,19 @@ MB_API int mb_layer_update_status(void *stream_, const void *workspace, uint32_t
 // ---- a6..a9 ---------------------------------------------------------------------------------
 // frames the batched path fuses per internal chunk when the caller sizes the workspace with
 // mb_layer_update_workspace_bytes (a larger workspace is used if given)
-static const int MB_DEFAULT_CHUNK_FRAMES = 64;
+static const int MB_DEFAULT_CHUNK_FRAMES = 128;
 
 MB_API size_t mb_layer_update_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int mode)
 {
     if (H <= 0 || W <= 0 || T <= 0 || nx < 2 || ny < 2 || nz < 2) return 256;
     const uint32_t npix = (uint32_t)H * (uint32_t)W;
     if (mode == MB_MODE_EXACT) return splat_workspace_bytes(npix);
-    int chunk = T < MB_DEFAULT_CHUNK_FRAMES ? T : MB_DEFAULT_CHUNK_FRAMES;
+    int limit = MB_DEFAULT_CHUNK_FRAMES;
+    if (const char *e = getenv("MASSB200_CHUNK_FRAMES")) {      // tuning aid
+        const int v = atoi(e);
+        if (v >= 1 && v <= 4096) limit = v;
+    }
+    int chunk = T < limit ? T : limit;
     while (chunk > 1 && (uint64_t)chunk * npix * 8 >= 0xffffffffull) chunk /= 2;
     return mbk_batch_workspace_bytes(npix, nx, ny, nz, chunk);
 }

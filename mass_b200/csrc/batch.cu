@@ -625,10 +625,12 @@ k_group_emit(const uint32_t *__restrict__ masks, const uint32_t *__restrict__ wo
 }
 
 // frame-major dispatch order (any order inside a frame: its groups belong to different bricks)
+// One descriptor per group, in dispatch order: {first entry, entries | frame << 20, brick id,
+// brick coordinates packed 10 + 10 + 10 bits}.
 __global__ void __launch_bounds__(256)
-k_group_order(const uint32_t *__restrict__ gstart, const uint32_t *__restrict__ pids, uint32_t np, int T,
-              const uint32_t *__restrict__ frame_hist, uint32_t *__restrict__ frame_fill, uint32_t *__restrict__ order,
-              const uint32_t *__restrict__ counters)
+k_group_order(const uint32_t *__restrict__ gstart, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pids,
+              uint32_t np, int T, MbBricks g, const uint32_t *__restrict__ frame_hist,
+              uint32_t *__restrict__ frame_fill, uint4 *__restrict__ desc, const uint32_t *__restrict__ counters)
 {
     extern __shared__ uint32_t s_base[];      // exclusive prefix of frame_hist
     for (int t = threadIdx.x; t < T; t += blockDim.x) s_base[t] = frame_hist[t];
@@ -639,14 +641,18 @@ k_group_order(const uint32_t *__restrict__ gstart, const uint32_t *__restrict__ 
     }
     __syncthreads();
     const uint32_t ngroups = counters[MB_CNT_GROUPS];
-    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
-        const uint32_t f = pids[gstart[g]] / np;
-        order[s_base[f] + atomicAdd(&frame_fill[f], 1u)] = g;
+    for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += gridDim.x * blockDim.x) {
+        const uint32_t beg = gstart[gi], end = gstart[gi + 1];
+        const uint32_t f = pids[beg] / np, key = keys[beg];
+        const uint32_t bz = key % g.N2, by = (key / g.N2) % g.N1, bx = key / (g.N2 * g.N1);
+        desc[s_base[f] + atomicAdd(&frame_fill[f], 1u)] =
+            make_uint4(beg, (end - beg) | (f << 20), key, bx | (by << 10) | (bz << 20));
     }
 }
 
 struct GroupArgs {
-    const uint32_t *keys, *pids, *gstart, *order;
+    const uint32_t *pids;
+    const uint4 *desc;
     uint32_t *progress, *counters;
     const uint4 *rec;
     MbFeatIndex fi;
@@ -675,7 +681,8 @@ k_group_reduce(const GroupArgs A)
     float *s_S2 = s_W + 64;                                     // [64]
     uint32_t *s_esrc = (uint32_t *)(s_S2 + 64);                 // [GRP_CHUNK]
     float *s_feat = (float *)(s_esrc + GRP_CHUNK);              // [GRP_CHUNK][RSF] staged feature rows
-    __shared__ uint32_t s_ticket, s_next;
+    __shared__ uint32_t s_next, s_turn;
+    __shared__ uint4 s_desc[2];               // descriptor of the current and of the prefetched next group
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sub = lane % LPV, grp = lane / LPV;
@@ -686,20 +693,27 @@ k_group_reduce(const GroupArgs A)
     const int F = A.F;
     const int RSF = (F + 3) & ~3;
     const int cb = sub * 8;
+    MB_T0();
 
-    for (;;) {
+    if (tid == 0) {
+        const uint32_t t = atomicAdd(&A.counters[MB_CNT_TICKET], 1u);
+        s_desc[0] = t < ngroups ? A.desc[t] : make_uint4(0u, 0u, 0xffffffffu, 0u);
+    }
+    for (uint32_t it = 0;; ++it) {
         __syncthreads();
-        if (tid == 0) s_ticket = atomicAdd(&A.counters[MB_CNT_TICKET], 1u);
+        const uint4 d = s_desc[it & 1];
+        if (d.z == 0xffffffffu) break;
+        const uint32_t gbeg = d.x, gend = d.x + (d.y & 0xfffffu), bkey = d.z, frame = d.y >> 20;
+        const int org0 = (int)(d.w & 1023u) * 4, org1 = (int)((d.w >> 10) & 1023u) * 4, org2 = (int)(d.w >> 20) * 4;
+        if (tid == 0) {
+            // draw the next group now (its descriptor load overlaps this group's work) and take a first
+            // look at the brick's progress counter
+            const uint32_t t = atomicAdd(&A.counters[MB_CNT_TICKET], 1u);
+            s_desc[(it + 1) & 1] = t < ngroups ? A.desc[t] : make_uint4(0u, 0u, 0xffffffffu, 0u);
+            s_turn = ld_acquire(A.progress + bkey) == gbeg ? 1u : 0u;
+        }
         if (tid < 64) { s_W[tid] = 0.f; s_S2[tid] = 0.f; }
-        __syncthreads();
-        const uint32_t ticket = s_ticket;
-        if (ticket >= ngroups) break;
-        const uint32_t gi = A.order[ticket];
-        const uint32_t gbeg = A.gstart[gi], gend = A.gstart[gi + 1];
-        const uint32_t bkey = A.keys[gbeg];
-        const uint32_t frame = A.pids[gbeg] / np;
-        const int bz = bkey % A.g.N2, by = (bkey / A.g.N2) % A.g.N1, bx = bkey / (A.g.N2 * A.g.N1);
-        const int org0 = bx * 4, org1 = by * 4, org2 = bz * 4;
+        MB_TICK(0);
 
         for (uint32_t pos = gbeg; pos < gend; pos += GRP_CHUNK) {
             const int nact = min((uint32_t)GRP_CHUNK, gend - pos);
@@ -719,6 +733,7 @@ k_group_reduce(const GroupArgs A)
             for (int i = tid; i < RED_WARPS * 64; i += RED_THREADS) s_cnt[i] = 0;
             if (tid == 0) s_next = 0;
             __syncthreads();
+            MB_TICK(1);
 
             if (STAGE) {
                 // feature rows -> shared memory in 16-byte pieces, from the 16-byte boundary at or before
@@ -803,6 +818,7 @@ k_group_reduce(const GroupArgs A)
                 if (ok && rk[k] == 0) s_cnt[warp * 64 + cv[k]] = __popc(m);   // classes never share a voxel
             }
             __syncthreads();
+            MB_TICK(2);
             if (tid < 64) {
                 uint32_t run = 0;
 #pragma unroll
@@ -848,8 +864,10 @@ k_group_reduce(const GroupArgs A)
                         s_con[s_start[cv[k]] + s_cnt[warp * 64 + cv[k]] + rk[k]] =
                             make_float4(cw[k], cw2[k], __uint_as_float(tag), 0.f);
             }
+            MB_TICK(3);
             if (STAGE) cp_async_wait_all();
             __syncthreads();
+            MB_TICK(4);
 
             // ---- LPV lanes per voxel, G voxels per warp pass -----------------------------------------------
             for (;;) {
@@ -904,10 +922,11 @@ k_group_reduce(const GroupArgs A)
                 }
             }
             __syncthreads();
+            MB_TICK(5);
         }
 
         // ---- the brick's turn: all earlier frames of this brick have been applied ---------------------
-        if (tid == 0) {
+        if (tid == 0 && s_turn == 0u) {
             uint32_t spins = 0;
             while (ld_acquire(A.progress + bkey) != gbeg) {
                 __nanosleep(64);
@@ -915,6 +934,7 @@ k_group_reduce(const GroupArgs A)
             }
         }
         __syncthreads();
+        MB_TICK(6);
         for (int t = warp * G; t < 64; t += RED_WARPS * G) {
             const int v = t + grp;
             const float W = s_W[v];
@@ -936,10 +956,14 @@ k_group_reduce(const GroupArgs A)
                 if (A.affine_a != nullptr && sub == 0) A.affine_a[vox] = __ldcg(A.affine_a + vox) * a;
             }
         }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) st_release(A.progress + bkey, gend);
+        __syncthreads();                                  // every row store of the CTA is ordered before ...
+        if (tid == 0) {
+            __threadfence();                              // ... this fence, which publishes them at GPU scope
+            st_release(A.progress + bkey, gend);
+        }
+        MB_TICK(7);
     }
+    MB_TFLUSH();
 }
 
 size_t group_smem_bytes(int LPV, int F, bool stage)
@@ -1032,6 +1056,7 @@ struct BatchBuffers {
     uint4 *rec;
     uint32_t *cnt, *offs, *keys_a, *keys_b, *pids_a, *pids_b, *order, *counters;
     uint32_t *masks, *wcount, *woffs, *gstart, *progress, *frame_hist;   // group form
+    uint4 *desc;
     uint2 *bricks;
     char *scan_ws, *sort_ws;
     size_t scan_bytes, sort_bytes;
@@ -1057,6 +1082,7 @@ size_t carve_batch(BatchBuffers &b, void *ws, size_t bytes, uint32_t ntotal, siz
     b.wcount = a.take<uint32_t>(nent / 32 + 1);
     b.woffs = a.take<uint32_t>(nent / 32 + 1);
     b.gstart = a.take<uint32_t>(nent + 1);
+    b.desc = a.take<uint4>(nent);
     b.progress = a.take<uint32_t>(nbricks_total);
     b.frame_hist = a.take<uint32_t>(2 * (size_t)T);
     b.scan_bytes = mb_scan_workspace_bytes(ntotal);          // >= the group-word scan (nent / 32 words)
@@ -1107,7 +1133,9 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     const MbBricks g = make_bricks(ny - 1, nx - 1, nz - 1);
     MB_REQUIRE(g.S0 <= 2046 && g.S1 <= 2046 && g.S2 <= 1022, "map too large for the packed voxel record");
     MB_REQUIRE(class_ids != nullptr || (uint64_t)T * fh * fw < 0xffffffffull, "too many feature rows per chunk");
-    MB_REQUIRE(T <= 8192, "too many frames per chunk");
+    MB_REQUIRE(T <= 4096, "too many frames per chunk");
+    MB_REQUIRE(npix < (1u << 20), "frames of 2^20 pixels or more are not supported by the batched path");
+    MB_REQUIRE(g.N0 <= 1024 && g.N1 <= 1024 && g.N2 <= 1024, "map too large for the packed brick coordinates");
     BatchBuffers b;
     MB_REQUIRE(carve_batch(b, workspace, workspace_bytes, ntotal, (size_t)g.N0 * g.N1 * g.N2, T) <= workspace_bytes,
                "batch workspace too small");
@@ -1140,10 +1168,10 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
                                                              b.counters);
         MB_LAUNCHED();
         k_group_order<<<MB_NUM_SMS * 2, 256, (size_t)T * sizeof(uint32_t), stream>>>(
-            b.gstart, pids, npix, T, b.frame_hist, b.frame_hist + T, b.order, b.counters);
+            b.gstart, keys, pids, npix, T, g, b.frame_hist, b.frame_hist + T, b.desc, b.counters);
         MB_LAUNCHED();
         GroupArgs G;
-        G.keys = keys; G.pids = pids; G.gstart = b.gstart; G.order = b.order; G.progress = b.progress;
+        G.pids = pids; G.desc = b.desc; G.progress = b.progress;
         G.counters = b.counters; G.rec = b.rec;
         G.fi = MbFeatIndex{ npix, (uint32_t)W, (uint32_t)(H / fh), (uint32_t)(W / fw), (uint32_t)fw };
         G.fhw = (uint32_t)fh * (uint32_t)fw;

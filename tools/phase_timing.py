@@ -21,8 +21,8 @@ layer.update_batch(obs); L.mb_debug_phase_cycles(out, 1)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); layer.update_batch(obs); e1.record(); torch.cuda.synchronize()
 L.mb_debug_phase_cycles(out, 1)
-names = ["ticket+brick setup", "chunk load+sync", "stage issue+weights+rank+sync", "prefix/scan/scatter", "cp.async wait+sync", "reduce", "end sync", "-"]
+names = ["ticket+group setup", "chunk load+sync", "stage issue+weights+rank+sync", "prefix/scan/scatter", "cp.async wait+sync", "reduce+sync", "turn wait+sync", "apply+fence+publish"]
 tot = sum(out[i] for i in range(8))
 print("frames %d: %.3f ms; summed CTA cycles %.3g" % (T, e0.elapsed_time(e1), tot))
-for i in range(7):
+for i in range(8):
     print("  %-32s %5.1f%%" % (names[i], 100.0 * out[i] / max(tot, 1)))
