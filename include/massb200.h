@@ -97,6 +97,34 @@ int mb_layer_update(void *stream, const float *rays, const float *depth, const f
                     float min_ray_depth, float max_ray_depth, int mode, void *workspace,
                     size_t workspace_bytes);
 
+/* ---- a11: SemanticProjectionLayer.find (mass/nn/applications/semantic_projection_layer.py:257-362) ----
+ * Step 1, lines 309-317: image[y][x] = any over z of (box mean of map[..., category] with kernel
+ * 2*contour_padding+1, zero padded, divisor k^3) > contour_threshold; uint8 [S0][S1].
+ * Step 2 (host, as in the reference): cv2.findContours + cv2.boundingRect on that image.
+ * Step 3, lines 329-357: per bounding box (x, y, w, h) over the full map depth,
+ *   out[box] = {confidence, coord_x, coord_y, coord_z, size, feature[FF]} with
+ *   weights = mask / (sum(mask) + 1e-9), confidence = sum(mask*weights), coord = sum(centre*weights),
+ *   size = sum(mask), feature = sum(feat_map[box]*weights) (feat_map may be NULL, then FF is ignored and
+ *   rows are 5 floats).  centres_* are the per-axis cell-centre tables (y already flipped). */
+size_t mb_class_presence_workspace_bytes(int S0, int S1, int S2, int contour_padding);
+int mb_class_presence(void *stream, const float *map, int S0, int S1, int S2, int F, int semantic_category,
+                      int contour_padding, float contour_threshold, uint8_t *image, void *workspace,
+                      size_t workspace_bytes);
+int mb_instance_pool(void *stream, const int32_t *boxes, int nboxes, const float *sem_map, int S0, int S1, int S2,
+                     int F, int semantic_category, const float *feat_map, int FF, const float *centres_x,
+                     const float *centres_y, const float *centres_z, float *out);
+
+/* ---- a12: predict_scene_differences (mass/utils/experimentation.py:261-287) ------------------------------
+ * mb_pairwise_l2: out[i][j] = ||a[i] - b[j]||_2 from direct differences (torch.linalg.norm of the
+ *   broadcast difference), a [n][d], b [m][d], out [n][m].
+ * mb_lsap: scipy.optimize.linear_sum_assignment on an n x m cost matrix (float32 as the reference hands
+ *   it over, or float64): same row order, scan order and tie rule.  Writes
+ *   min(n, m) (row, col) pairs sorted by row; *status = 1 if the matrix is infeasible. */
+int mb_pairwise_l2(void *stream, const float *a, int n, const float *b, int m, int d, float *out);
+size_t mb_lsap_workspace_bytes(int n, int m);
+int mb_lsap(void *stream, const float *cost32, const double *cost64, int n, int m, int64_t *rows, int64_t *cols,
+            int32_t *status, void *workspace, size_t workspace_bytes);
+
 /* Synchronises `stream` and returns the sticky error bits the batched kernels left in the workspace of
  * the last MB_MODE_FAST call: 0 = fine, bit 0 = an in-order row update gave up waiting for its
  * predecessor (never expected; the map is then not trustworthy). */

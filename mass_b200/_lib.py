@@ -53,6 +53,12 @@ _SIGNATURES = {
                                      _i32, _f32, _i32, _vp, _sz]),
     "mb_layer_update_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "mb_layer_update_status": (_i32, [_vp, _vp, _vp]),
+    "mb_class_presence_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "mb_class_presence": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _sz]),
+    "mb_instance_pool": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "mb_pairwise_l2": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp]),
+    "mb_lsap_workspace_bytes": (_sz, [_i32, _i32]),
+    "mb_lsap": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz]),
     "mb_layer_update": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32,
                                _vp, _i32, _vp, _i32, _vp, _f32, _f32, _f32, _i32, _vp, _sz]),
 }

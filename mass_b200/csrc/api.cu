@@ -254,3 +254,62 @@ MB_API int mb_layer_update(void *stream_, const float *rays, const float *depth,
     }
     return MB_OK;
 }
+
+// ---- a11: SemanticProjectionLayer.find -------------------------------------------------------------
+MB_API size_t mb_class_presence_workspace_bytes(int S0, int S1, int S2, int contour_padding)
+{
+    if (S0 <= 0 || S1 <= 0 || S2 <= 0) return 256;
+    return mbk_class_presence_workspace_bytes(S0, S1, S2, contour_padding);
+}
+
+MB_API int mb_class_presence(void *stream, const float *map, int S0, int S1, int S2, int F, int semantic_category,
+                             int contour_padding, float contour_threshold, uint8_t *image, void *workspace,
+                             size_t workspace_bytes)
+{
+    MB_REQUIRE(map && image, "mb_class_presence: null pointer");
+    MB_REQUIRE(S0 > 0 && S1 > 0 && S2 > 0 && F > 0, "mb_class_presence: bad map shape");
+    MB_REQUIRE(semantic_category >= 0 && semantic_category < F, "mb_class_presence: category %d outside [0, %d)",
+               semantic_category, F);
+    MB_REQUIRE(contour_padding >= 0 && contour_padding <= 64, "mb_class_presence: bad contour_padding %d", contour_padding);
+    return mbk_class_presence((cudaStream_t)stream, map, S0, S1, S2, F, semantic_category, contour_padding,
+                              contour_threshold, image, workspace, workspace_bytes);
+}
+
+MB_API int mb_instance_pool(void *stream, const int32_t *boxes, int nboxes, const float *sem_map, int S0, int S1, int S2,
+                            int F, int semantic_category, const float *feat_map, int FF, const float *centres_x,
+                            const float *centres_y, const float *centres_z, float *out)
+{
+    MB_REQUIRE(nboxes >= 0, "mb_instance_pool: negative box count");
+    if (nboxes == 0) return MB_OK;
+    MB_REQUIRE(boxes && sem_map && centres_x && centres_y && centres_z && out, "mb_instance_pool: null pointer");
+    MB_REQUIRE(S0 > 0 && S1 > 0 && S2 > 0 && F > 0 && semantic_category >= 0 && semantic_category < F,
+               "mb_instance_pool: bad map shape or category");
+    MB_REQUIRE(feat_map == nullptr || FF > 0, "mb_instance_pool: feature map without a feature size");
+    return mbk_instance_pool((cudaStream_t)stream, boxes, nboxes, sem_map, S0, S1, S2, F, semantic_category, feat_map,
+                             FF, centres_x, centres_y, centres_z, out);
+}
+
+// ---- a12: predict_scene_differences --------------------------------------------------------------------
+MB_API int mb_pairwise_l2(void *stream, const float *a, int n, const float *b, int m, int d, float *out)
+{
+    MB_REQUIRE(n >= 0 && m >= 0 && d >= 0, "mb_pairwise_l2: negative size");
+    if (n == 0 || m == 0) return MB_OK;
+    MB_REQUIRE(a && b && out, "mb_pairwise_l2: null pointer");
+    return mbk_pairwise_l2((cudaStream_t)stream, a, n, b, m, d, out);
+}
+
+MB_API size_t mb_lsap_workspace_bytes(int n, int m)
+{
+    if (n <= 0 || m <= 0) return 256;
+    return mbk_lsap_workspace_bytes(n, m);
+}
+
+MB_API int mb_lsap(void *stream, const float *cost32, const double *cost64, int n, int m, int64_t *rows, int64_t *cols,
+                   int32_t *status, void *workspace, size_t workspace_bytes)
+{
+    MB_REQUIRE(n >= 0 && m >= 0, "mb_lsap: negative size");
+    if (n == 0 || m == 0) return MB_OK;
+    MB_REQUIRE((cost32 != nullptr) != (cost64 != nullptr), "mb_lsap: pass exactly one of cost32 / cost64");
+    MB_REQUIRE(rows && cols && status, "mb_lsap: null pointer");
+    return mbk_lsap((cudaStream_t)stream, cost32, cost64, n, m, rows, cols, status, workspace, workspace_bytes);
+}

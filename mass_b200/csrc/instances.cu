@@ -1,0 +1,445 @@
+// K3 / K4: instance extraction and matching kernels (sm_100a).
+//
+//   mbk_class_presence   /root/reference/mass/nn/applications/semantic_projection_layer.py:309-317
+//                        (avg_pool3d box mean of one class channel, threshold, any over z)
+//   mbk_instance_pool    semantic_projection_layer.py:329-357 (per bounding box: confidence, expected
+//                        position, size, pooled instance feature)
+//   mbk_pairwise_l2      /root/reference/mass/utils/experimentation.py:261-265, 277-280
+//   mbk_lsap             experimentation.py:284-287 -> scipy.optimize.linear_sum_assignment (third party;
+//                        Crouse 2016 shortest augmenting path), one CTA, float64 duals
+//
+// All reductions run in a fixed order (per-thread strided partial sums, then a fixed shared-memory
+// tree), so results are reproducible run to run.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// class presence.  Pass 1 (pad == 0): image[y][x] = any_z(map[y][x][z][c] > thr).
+__global__ void __launch_bounds__(256)
+k_presence_nopad(const float *__restrict__ map, int S0, int S1, int S2, int F, int c, float thr,
+                 uint8_t *__restrict__ image)
+{
+    // one warp per (y, x) column, lanes stride over z
+    const int lane = threadIdx.x & 31;
+    const size_t col = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (col >= (size_t)S0 * S1) return;
+    const float *p = map + col * (size_t)S2 * F + c;
+    bool any = false;
+    for (int z = lane; z < S2; z += 32) any |= p[(size_t)z * F] > thr;
+    any = __any_sync(FULL, any);
+    if (lane == 0) image[col] = any ? 1 : 0;
+}
+
+// Box sums for pad > 0 are separable: along z (from the strided class channel), along x, along y.
+// out[y][x][z] = sum_{dz=-pad..pad} map[y][x][z+dz][c]   (zero outside the map)
+__global__ void __launch_bounds__(128)
+k_boxsum_z(const float *__restrict__ map, int S0, int S1, int S2, int F, int c, int pad, float *__restrict__ out)
+{
+    extern __shared__ float s_col[];
+    const size_t col = blockIdx.x;
+    const float *p = map + col * (size_t)S2 * F + c;
+    for (int z = threadIdx.x; z < S2; z += blockDim.x) s_col[z] = p[(size_t)z * F];
+    __syncthreads();
+    for (int z = threadIdx.x; z < S2; z += blockDim.x) {
+        float s = 0.f;
+        for (int d = -pad; d <= pad; ++d) {
+            const int zz = z + d;
+            if (zz >= 0 && zz < S2) s += s_col[zz];
+        }
+        out[col * S2 + z] = s;
+    }
+}
+
+// sums along one of the two planar axes: `stride` elements between neighbours, `len` positions
+__global__ void __launch_bounds__(256)
+k_boxsum_axis(const float *__restrict__ in, size_t total, int len, size_t stride, int pad, float *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int pos = (int)((i / stride) % (size_t)len);
+    float s = 0.f;
+    for (int d = -pad; d <= pad; ++d) {
+        const int q = pos + d;
+        if (q >= 0 && q < len) s += in[i + (ptrdiff_t)d * (ptrdiff_t)stride];
+    }
+    out[i] = s;
+}
+
+__global__ void __launch_bounds__(256)
+k_presence_from_sums(const float *__restrict__ sums, int S0, int S1, int S2, float count, float thr,
+                     uint8_t *__restrict__ image)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t col = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (col >= (size_t)S0 * S1) return;
+    bool any = false;
+    for (int z = lane; z < S2; z += 32) any |= __fdiv_rn(sums[col * S2 + z], count) > thr;
+    any = __any_sync(FULL, any);
+    if (lane == 0) image[col] = any ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// instance pooling: one CTA per bounding box (x, y, w, h) over the full depth of the map.
+//   out row = [confidence, coord_x, coord_y, coord_z, size, feature[FF]]
+constexpr int POOL_THREADS = 256;
+constexpr int POOL_LIST = 2048;      // non-zero voxels of the box processed per round
+
+__device__ __forceinline__ double block_sum(double v, double *s_red)
+{
+    const int tid = threadIdx.x;
+    s_red[tid] = v;
+    __syncthreads();
+    for (int step = POOL_THREADS / 2; step > 0; step >>= 1) {
+        if (tid < step) s_red[tid] += s_red[tid + step];
+        __syncthreads();
+    }
+    const double r = s_red[0];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(POOL_THREADS)
+k_instance_pool(const int *__restrict__ boxes, const float *__restrict__ sem, int S0, int S1, int S2, int F, int c,
+                const float *__restrict__ feat, int FF, const float *__restrict__ mx, const float *__restrict__ my,
+                const float *__restrict__ mz, float *__restrict__ out)
+{
+    __shared__ double s_red[POOL_THREADS];
+    __shared__ uint32_t s_list[POOL_LIST];     // box-local voxel ids with a non-zero mask
+    __shared__ float s_lw[POOL_LIST];          // their mask values
+    __shared__ uint32_t s_count;
+    extern __shared__ float s_facc[];          // [POOL_THREADS / 32][FF] per-warp feature sums
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bx = boxes[4 * blockIdx.x], by = boxes[4 * blockIdx.x + 1], bw = boxes[4 * blockIdx.x + 2],
+              bh = boxes[4 * blockIdx.x + 3];
+    const uint32_t nvox = (uint32_t)bw * bh * S2;
+    float *orow = out + (size_t)blockIdx.x * (5 + FF);
+
+    // pass 1: total, sum of squares, first moments (double accumulators, fixed order)
+    double t = 0, t2 = 0, tx = 0, ty = 0, tz = 0;
+    for (uint32_t i = tid; i < nvox; i += POOL_THREADS) {
+        const int z = i % S2;
+        const int x = (i / S2) % bw, y = i / (S2 * bw);
+        const float m = sem[(((size_t)(by + y) * S1 + (bx + x)) * S2 + z) * F + c];
+        t += m;
+        t2 += (double)m * m;
+        tx += (double)m * mx[bx + x];
+        ty += (double)m * my[by + y];
+        tz += (double)m * mz[z];
+    }
+    t = block_sum(t, s_red);
+    t2 = block_sum(t2, s_red);
+    tx = block_sum(tx, s_red);
+    ty = block_sum(ty, s_red);
+    tz = block_sum(tz, s_red);
+    const double denom = (double)((float)t + 1e-9f);       // mask_roi.sum() + 1e-9 in fp32
+    if (tid == 0) {
+        orow[0] = (float)(t2 / denom);
+        orow[1] = (float)(tx / denom);
+        orow[2] = (float)(ty / denom);
+        orow[3] = (float)(tz / denom);
+        orow[4] = (float)t;
+    }
+    if (feat == nullptr || FF == 0) return;
+
+    // pass 2: pooled feature = sum_vox mask * feat[vox] / denom over the non-zero voxels only
+    const int nwarps = POOL_THREADS / 32;
+    for (int k = tid; k < nwarps * FF; k += POOL_THREADS) s_facc[k] = 0.f;
+    for (uint32_t base = 0; base < nvox; base += POOL_LIST) {
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        // ordered compaction of the non-zero voxels of this slice (deterministic list order)
+        for (uint32_t off = 0; off < POOL_LIST; off += POOL_THREADS) {
+            const uint32_t i = base + off + tid;
+            float m = 0.f;
+            if (i < nvox) {
+                const int z = i % S2;
+                const int x = (i / S2) % bw, y = i / (S2 * bw);
+                m = sem[(((size_t)(by + y) * S1 + (bx + x)) * S2 + z) * F + c];
+            }
+            const bool nz = m != 0.f;
+            const uint32_t bal = __ballot_sync(FULL, nz);
+            __shared__ uint32_t s_wbase[POOL_THREADS / 32];
+            if (lane == 0) s_wbase[warp] = __popc(bal);
+            __syncthreads();
+            uint32_t before = s_count;
+            for (int w = 0; w < warp; ++w) before += s_wbase[w];
+            if (nz) {
+                const uint32_t slot = before + __popc(bal & ((1u << lane) - 1u));
+                s_list[slot] = i;
+                s_lw[slot] = m;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t add = 0;
+                for (int w = 0; w < nwarps; ++w) add += s_wbase[w];
+                s_count += add;
+            }
+            __syncthreads();
+        }
+        const uint32_t cnt = s_count;
+        // warp w takes list items w, w + nwarps, ...; lanes are channels
+        for (uint32_t k = warp; k < cnt; k += nwarps) {
+            const uint32_t i = s_list[k];
+            const float m = s_lw[k];
+            const int z = i % S2;
+            const int x = (i / S2) % bw, y = i / (S2 * bw);
+            const float *frow = feat + (((size_t)(by + y) * S1 + (bx + x)) * S2 + z) * FF;
+            for (int ch = lane; ch < FF; ch += 32) s_facc[warp * FF + ch] = fmaf(m, __ldg(frow + ch), s_facc[warp * FF + ch]);
+        }
+        __syncthreads();
+    }
+    for (int ch = tid; ch < FF; ch += POOL_THREADS) {
+        double s = 0;
+        for (int w = 0; w < nwarps; ++w) s += s_facc[w * FF + ch];
+        orow[5 + ch] = (float)(s / denom);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pairwise L2: one warp per (i, j), direct differences (the GEMM form drifts: SURVEY.md section 7)
+__global__ void __launch_bounds__(256)
+k_pairwise_l2(const float *__restrict__ a, int n, const float *__restrict__ b, int m, int d, float *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t pair = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (pair >= (size_t)n * m) return;
+    const int i = (int)(pair / m), j = (int)(pair % m);
+    const float *pa = a + (size_t)i * d, *pb = b + (size_t)j * d;
+    double s = 0;
+    for (int k = lane; k < d; k += 32) {
+        const float diff = __fsub_rn(pa[k], pb[k]);
+        s += (double)diff * (double)diff;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (lane == 0) out[pair] = (float)sqrt(s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// rectangular linear sum assignment, nr <= nc (the host wrapper transposes otherwise).
+// Follows the scan order and tie rule of SURVEY.md Appendix B: columns are scanned in the order of
+// the `remaining` list (initialised in reverse, swap-removed); among equal shortest path costs the
+// first scanned column wins unless a later scanned one is unassigned, in which case the last
+// unassigned one wins.
+constexpr int LSAP_THREADS = 256;
+
+struct Best {
+    double val;
+    int first;      // first scan position attaining val
+    int lastfree;   // last scan position attaining val whose column is unassigned (-1: none)
+};
+
+__device__ __forceinline__ Best best_merge(const Best &x, const Best &y)   // x covers earlier positions than y
+{
+    if (x.val < y.val) return x;
+    if (y.val < x.val) return y;
+    Best r;
+    r.val = x.val;
+    r.first = x.first < 0 ? y.first : x.first;
+    r.lastfree = y.lastfree >= 0 ? y.lastfree : x.lastfree;
+    return r;
+}
+
+__global__ void __launch_bounds__(LSAP_THREADS)
+k_lsap(const float *__restrict__ cost32, const double *__restrict__ cost64, int nr, int nc, int transposed,
+       double *__restrict__ work, int *__restrict__ iwork, int64_t *__restrict__ col4row_out, int *__restrict__ status)
+{
+    // cost(i, j): element of the nr x nc problem; if transposed the stored matrix is nc x nr
+    double *u = work, *v = u + nr, *spc = v + nc;
+    int *path = iwork, *row4col = path + nc, *col4row = row4col + nc, *remaining = col4row + nr;
+    int *SR = remaining + nc, *SC = SR + nr;
+    __shared__ Best s_best[LSAP_THREADS];
+    __shared__ int s_i, s_sink, s_nrem, s_fail;
+    __shared__ double s_minval;
+    const int tid = threadIdx.x;
+
+    for (int k = tid; k < nr; k += LSAP_THREADS) { u[k] = 0.0; col4row[k] = -1; }
+    for (int k = tid; k < nc; k += LSAP_THREADS) { v[k] = 0.0; row4col[k] = -1; }
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
+
+    for (int cur = 0; cur < nr; ++cur) {
+        for (int k = tid; k < nc; k += LSAP_THREADS) { remaining[k] = nc - k - 1; spc[k] = INFINITY; path[k] = -1; SC[k] = 0; }
+        for (int k = tid; k < nr; k += LSAP_THREADS) SR[k] = 0;
+        if (tid == 0) { s_i = cur; s_sink = -1; s_nrem = nc; s_minval = 0.0; }
+        __syncthreads();
+        while (s_sink == -1) {
+            const int i = s_i, nrem = s_nrem;
+            const double minval = s_minval, ui = u[i];
+            if (tid == 0) SR[i] = 1;
+            Best mine;
+            mine.val = INFINITY; mine.first = -1; mine.lastfree = -1;
+            // each thread scans a contiguous slice of the scan order
+            const int per = (nrem + LSAP_THREADS - 1) / LSAP_THREADS;
+            const int lo = tid * per, hi = min(nrem, lo + per);
+            for (int it = lo; it < hi; ++it) {
+                const int j = remaining[it];
+                const double c = cost64 ? (transposed ? cost64[(size_t)j * nr + i] : cost64[(size_t)i * nc + j])
+                                        : (double)(transposed ? cost32[(size_t)j * nr + i] : cost32[(size_t)i * nc + j]);
+                const double r = minval + c - ui - v[j];
+                if (r < spc[j]) { path[j] = i; spc[j] = r; }
+                Best b;
+                b.val = spc[j]; b.first = it; b.lastfree = row4col[j] == -1 ? it : -1;
+                mine = best_merge(mine, b);
+            }
+            s_best[tid] = mine;
+            __syncthreads();
+            for (int step = 1; step < LSAP_THREADS; step <<= 1) {      // ordered tree: left covers earlier positions
+                if ((tid & (2 * step - 1)) == 0 && tid + step < LSAP_THREADS) s_best[tid] = best_merge(s_best[tid], s_best[tid + step]);
+                __syncthreads();
+            }
+            if (tid == 0) {
+                const Best b = s_best[0];
+                if (b.first < 0 || b.val == INFINITY) {
+                    s_fail = 1;
+                    s_sink = -2;
+                } else {
+                    const int index = b.lastfree > b.first ? b.lastfree : b.first;
+                    const int j = remaining[index];
+                    s_minval = b.val;
+                    if (row4col[j] == -1) s_sink = j; else s_i = row4col[j];
+                    SC[j] = 1;
+                    remaining[index] = remaining[nrem - 1];
+                    s_nrem = nrem - 1;
+                }
+            }
+            __syncthreads();
+        }
+        if (s_fail) break;
+        const double minval = s_minval;
+        const int sink = s_sink;
+        __syncthreads();
+        for (int k = tid; k < nr; k += LSAP_THREADS)
+            if (k == cur) u[k] += minval;
+            else if (SR[k]) u[k] += minval - spc[col4row[k]];
+        for (int k = tid; k < nc; k += LSAP_THREADS)
+            if (SC[k]) v[k] -= minval - spc[k];
+        __syncthreads();
+        if (tid == 0) {
+            int j = sink;
+            for (;;) {
+                const int i = path[j];
+                row4col[j] = i;
+                const int t = col4row[i];
+                col4row[i] = j;
+                j = t;
+                if (i == cur) break;
+            }
+        }
+        __syncthreads();
+    }
+    for (int k = tid; k < nr; k += LSAP_THREADS) col4row_out[k] = col4row[k];
+    if (tid == 0) *status = s_fail;
+}
+
+}  // namespace
+
+size_t mbk_class_presence_workspace_bytes(int S0, int S1, int S2, int pad)
+{
+    if (pad <= 0) return 256;
+    return 2 * mb_align_up((size_t)S0 * S1 * S2 * sizeof(float)) + 256;
+}
+
+int mbk_class_presence(cudaStream_t stream, const float *map, int S0, int S1, int S2, int F, int c, int pad, float thr,
+                       uint8_t *image, void *workspace, size_t workspace_bytes)
+{
+    const size_t cols = (size_t)S0 * S1;
+    const unsigned blocks = (unsigned)((cols * 32 + 255) / 256);
+    if (pad <= 0) {
+        k_presence_nopad<<<blocks, 256, 0, stream>>>(map, S0, S1, S2, F, c, thr, image);
+        MB_LAUNCHED();
+        return MB_OK;
+    }
+    MB_REQUIRE(workspace && workspace_bytes >= mbk_class_presence_workspace_bytes(S0, S1, S2, pad),
+               "class presence workspace too small");
+    MbArena arena(workspace, workspace_bytes);
+    const size_t total = cols * S2;
+    float *t0 = arena.take<float>(total), *t1 = arena.take<float>(total);
+    k_boxsum_z<<<(unsigned)cols, 128, (size_t)S2 * sizeof(float), stream>>>(map, S0, S1, S2, F, c, pad, t0);
+    MB_LAUNCHED();
+    const unsigned eb = (unsigned)((total + 255) / 256);
+    k_boxsum_axis<<<eb, 256, 0, stream>>>(t0, total, S1, (size_t)S2, pad, t1);              // along x
+    MB_LAUNCHED();
+    k_boxsum_axis<<<eb, 256, 0, stream>>>(t1, total, S0, (size_t)S1 * S2, pad, t0);         // along y
+    MB_LAUNCHED();
+    const int k = 2 * pad + 1;
+    k_presence_from_sums<<<blocks, 256, 0, stream>>>(t0, S0, S1, S2, (float)(k * k * k), thr, image);
+    MB_LAUNCHED();
+    return MB_OK;
+}
+
+int mbk_instance_pool(cudaStream_t stream, const int *boxes, int nboxes, const float *sem, int S0, int S1, int S2, int F,
+                      int c, const float *feat, int FF, const float *mx, const float *my, const float *mz, float *out)
+{
+    if (nboxes <= 0) return MB_OK;
+    const size_t smem = (size_t)(POOL_THREADS / 32) * (feat ? FF : 0) * sizeof(float);
+    MB_REQUIRE(smem <= 40000, "instance feature size %d too large", FF);
+    k_instance_pool<<<nboxes, POOL_THREADS, smem, stream>>>(boxes, sem, S0, S1, S2, F, c, feat, feat ? FF : 0, mx, my, mz, out);
+    MB_LAUNCHED();
+    return MB_OK;
+}
+
+int mbk_pairwise_l2(cudaStream_t stream, const float *a, int n, const float *b, int m, int d, float *out)
+{
+    if (n <= 0 || m <= 0) return MB_OK;
+    const size_t threads = (size_t)n * m * 32;
+    k_pairwise_l2<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, n, b, m, d, out);
+    MB_LAUNCHED();
+    return MB_OK;
+}
+
+size_t mbk_lsap_workspace_bytes(int n, int m)
+{
+    const size_t nr = n < m ? n : m, nc = n < m ? m : n;
+    return mb_align_up((nr + 2 * nc) * sizeof(double)) + mb_align_up((4 * nc + 3 * nr) * sizeof(int)) +
+           mb_align_up(nr * sizeof(int64_t)) + 1024;
+}
+
+// cost is n x m (float32 or float64, exactly one non-null); writes min(n, m) pairs sorted by row
+int mbk_lsap(cudaStream_t stream, const float *cost32, const double *cost64, int n, int m, int64_t *rows, int64_t *cols,
+             int *status, void *workspace, size_t workspace_bytes);
+
+namespace {
+__global__ void k_lsap_finish(const int64_t *__restrict__ col4row, int nr, int nc, int transposed, int64_t *rows,
+                              int64_t *cols, int *scratch)
+{
+    // not transposed: pairs (i, col4row[i]).  transposed: the problem's rows are the matrix's columns:
+    // pairs (row = col4row[j], col = j), to be listed by increasing row.
+    if (!transposed) {
+        for (int i = threadIdx.x; i < nr; i += blockDim.x) { rows[i] = i; cols[i] = col4row[i]; }
+        return;
+    }
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) scratch[i] = -1;
+    __syncthreads();
+    for (int j = threadIdx.x; j < nr; j += blockDim.x) scratch[col4row[j]] = j;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int k = 0;
+        for (int i = 0; i < nc; ++i)
+            if (scratch[i] >= 0) { rows[k] = i; cols[k] = scratch[i]; ++k; }
+    }
+}
+}  // namespace
+
+int mbk_lsap(cudaStream_t stream, const float *cost32, const double *cost64, int n, int m, int64_t *rows, int64_t *cols,
+             int *status, void *workspace, size_t workspace_bytes)
+{
+    if (n <= 0 || m <= 0) return MB_OK;
+    MB_REQUIRE(workspace && workspace_bytes >= mbk_lsap_workspace_bytes(n, m), "lsap workspace too small");
+    const int transposed = m < n ? 1 : 0;
+    const int nr = transposed ? m : n, nc = transposed ? n : m;
+    MbArena arena(workspace, workspace_bytes);
+    double *work = arena.take<double>((size_t)nr + 2 * nc);
+    int *iwork = arena.take<int>((size_t)4 * nc + 3 * nr);
+    int64_t *col4row = arena.take<int64_t>((size_t)nr);
+    k_lsap<<<1, LSAP_THREADS, 0, stream>>>(cost32, cost64, nr, nc, transposed, work, iwork, col4row, status);
+    MB_LAUNCHED();
+    k_lsap_finish<<<1, 256, 0, stream>>>(col4row, nr, nc, transposed, rows, cols, iwork);
+    MB_LAUNCHED();
+    return MB_OK;
+}

@@ -57,3 +57,14 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
                      const float *bins_x, int nx, const float *bins_y, int ny, const float *bins_z, int nz,
                      float *map, float *affine_a, float alpha, float min_d, float max_d, void *workspace,
                      size_t workspace_bytes);
+
+// instances.cu: instance extraction (find) and matching
+size_t mbk_class_presence_workspace_bytes(int S0, int S1, int S2, int pad);
+int mbk_class_presence(cudaStream_t stream, const float *map, int S0, int S1, int S2, int F, int c, int pad, float thr,
+                       uint8_t *image, void *workspace, size_t workspace_bytes);
+int mbk_instance_pool(cudaStream_t stream, const int *boxes, int nboxes, const float *sem, int S0, int S1, int S2, int F,
+                      int c, const float *feat, int FF, const float *mx, const float *my, const float *mz, float *out);
+int mbk_pairwise_l2(cudaStream_t stream, const float *a, int n, const float *b, int m, int d, float *out);
+size_t mbk_lsap_workspace_bytes(int n, int m);
+int mbk_lsap(cudaStream_t stream, const float *cost32, const double *cost64, int n, int m, int64_t *rows, int64_t *cols,
+             int *status, void *workspace, size_t workspace_bytes);
