@@ -1,6 +1,132 @@
-"""Instance extraction for SemanticProjectionLayer.find (filled in with the K3 kernels)."""
+"""Instance extraction for SemanticProjectionLayer.find and the matching primitives of
+predict_scene_differences, on the kernels of libmassb200 (no CPU path for the tensor work).
+
+Reference: /root/reference/mass/nn/applications/semantic_projection_layer.py:257-362 (find),
+/root/reference/mass/utils/experimentation.py:261-287 (cost matrices + assignment).
+
+Contour extraction stays on the host with OpenCV exactly as in the reference
+(cv2.findContours / cv2.boundingRect, semantic_projection_layer.py:323-328): OpenCV decides the
+number and ORDER of the instances, so using it keeps instance indices identical by construction.
+"""
+import ctypes
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from mass_b200 import _lib
+
+Instances = namedtuple("Instances", "boxes confidences coordinates sizes features")
+
+_ws = _lib.Workspace()
+
+
+def class_presence(layer, semantic_category, contour_padding, contour_threshold):
+    """uint8 [S0, S1] CUDA image: any over z of (box mean of data[..., c]) > threshold
+    (semantic_projection_layer.py:309-317)."""
+    data = layer.data
+    device = _lib.require_cuda(data.device)
+    S0, S1, S2, F = data.shape
+    if not 0 <= int(semantic_category) < F:
+        raise IndexError("semantic_category %d is outside [0, %d)" % (semantic_category, F))
+    L = _lib.lib()
+    image = torch.empty(S0, S1, dtype=torch.uint8, device=device)
+    ws = _ws.get(L.mb_class_presence_workspace_bytes(S0, S1, S2, int(contour_padding)), device)
+    _lib.check(L.mb_class_presence(_lib.stream_ptr(device), _lib.ptr(data), S0, S1, S2, F, int(semantic_category),
+                                   int(contour_padding), float(contour_threshold), _lib.ptr(image), _lib.ptr(ws),
+                                   ws.numel()))
+    return image
+
+
+def contour_boxes(threshold_image):
+    """Host step of find(): OpenCV contours -> bounding boxes (x, y, w, h), OpenCV's order."""
+    import cv2
+    contours = cv2.findContours(np.ascontiguousarray(threshold_image), cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)[0]
+    return [tuple(int(v) for v in cv2.boundingRect(c)) for c in contours]
+
+
+def pool_boxes(layer, semantic_category, boxes, feature_map=None):
+    """[n, 5 + FF] CUDA rows {confidence, x, y, z, size, feature...} for bounding boxes over the
+    full map depth (semantic_projection_layer.py:329-357)."""
+    data = layer.data
+    device = _lib.require_cuda(data.device)
+    S0, S1, S2, F = data.shape
+    feat, FF = None, 0
+    if feature_map is not None:
+        feat = feature_map.data
+        if not feat.is_cuda:
+            raise RuntimeError("the instance feature map must live on the GPU (it is %s); the reference keeps "
+                               "it on the host only because 13.5 GiB did not fit its GPU" % feat.device)
+        if feat.device != device or tuple(feat.shape[:3]) != (S0, S1, S2) or feat.dtype != torch.float32:
+            raise ValueError("feature map must be float32 [%d, %d, %d, FF] on %s" % (S0, S1, S2, device))
+        FF = int(feat.shape[3])
+    n = len(boxes)
+    out = torch.empty(n, 5 + FF, dtype=torch.float32, device=device)
+    if n == 0:
+        return out
+    mx, my, mz = layer.cell_centres()
+    boxes_d = torch.tensor(boxes, dtype=torch.int32).reshape(n, 4).to(device)
+    _lib.check(_lib.lib().mb_instance_pool(
+        _lib.stream_ptr(device), _lib.ptr(boxes_d), n, _lib.ptr(data), S0, S1, S2, F, int(semantic_category),
+        _lib.ptr(feat), FF, _lib.ptr(mx.contiguous()), _lib.ptr(my.contiguous()), _lib.ptr(mz.contiguous()),
+        _lib.ptr(out)))
+    return out
 
 
 def find_instances(layer, semantic_category, confidence_threshold, contour_padding, contour_threshold,
                    feature_map):
-    raise NotImplementedError("find(): instance pooling kernels not built yet")
+    image = class_presence(layer, semantic_category, contour_padding, contour_threshold)
+    boxes = contour_boxes(image.cpu().numpy())
+    rows = pool_boxes(layer, semantic_category, boxes, feature_map)
+    keep = (rows[:, 0] > confidence_threshold).cpu().numpy() if len(boxes) else np.zeros(0, bool)
+    kept = [i for i in range(len(boxes)) if keep[i]]
+    return Instances(
+        boxes=[boxes[i] for i in kept],
+        confidences=[rows[i, 0] for i in kept],
+        coordinates=[rows[i, 1:4] for i in kept],
+        sizes=[rows[i, 4] for i in kept],
+        features=[rows[i, 5:] for i in kept] if feature_map is not None else None)
+
+
+def pairwise_l2(a, b):
+    """[n, m] distances ||a_i - b_j||_2 from direct differences
+    (torch.linalg.norm(a.unsqueeze(1) - b.unsqueeze(0), dim=2), experimentation.py:261-265)."""
+    device = _lib.require_cuda(a.device)
+    a = a.to(torch.float32).contiguous()
+    b = b.to(device=device, dtype=torch.float32).contiguous()
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1]:
+        raise ValueError("pairwise_l2 needs [n, d] and [m, d], got %s and %s" % (tuple(a.shape), tuple(b.shape)))
+    out = torch.empty(a.shape[0], b.shape[0], dtype=torch.float32, device=device)
+    _lib.check(_lib.lib().mb_pairwise_l2(_lib.stream_ptr(device), _lib.ptr(a), a.shape[0], _lib.ptr(b), b.shape[0],
+                                         a.shape[1], _lib.ptr(out)))
+    return out
+
+
+def linear_sum_assignment(cost):
+    """scipy.optimize.linear_sum_assignment on a CUDA cost matrix (float32 or float64): returns
+    (rows, cols) int64 numpy arrays, rows ascending, same tie behaviour as scipy (one CTA runs the
+    shortest-augmenting-path solver with float64 duals)."""
+    device = _lib.require_cuda(cost.device)
+    if cost.dim() != 2:
+        raise ValueError("expected a matrix (2-D array), got a %d array" % cost.dim())
+    if cost.dtype not in (torch.float32, torch.float64):
+        cost = cost.to(torch.float64)
+    cost = cost.contiguous()
+    n, m = cost.shape
+    k = min(n, m)
+    if k == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    if bool(torch.isnan(cost).any() | (cost == -float("inf")).any()):     # scipy rejects NaN and -inf
+        raise ValueError("matrix contains invalid numeric entries")
+    L = _lib.lib()
+    pairs = torch.empty(2, k, dtype=torch.int64, device=device)
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+    ws = _ws.get(L.mb_lsap_workspace_bytes(n, m), device)
+    c32 = cost if cost.dtype == torch.float32 else None
+    c64 = cost if cost.dtype == torch.float64 else None
+    _lib.check(L.mb_lsap(_lib.stream_ptr(device), _lib.ptr(c32), _lib.ptr(c64), n, m, _lib.ptr(pairs[0]),
+                         _lib.ptr(pairs[1]), _lib.ptr(status), _lib.ptr(ws), ws.numel()))
+    host = pairs.cpu().numpy()
+    if int(status.item()) != 0:
+        raise ValueError("cost matrix is infeasible")
+    return host[0].copy(), host[1].copy()
