@@ -89,7 +89,11 @@ int mb_update_feature_map(void *stream, const int64_t *ind0, const int64_t *ind1
  *             (mass/nn/applications/semantic_projection_layer.py:203-214); else NULL
  *   pose      [T][12]
  *   bins_x/y/z edge tables with nx/ny/nz entries (map is [ny-1][nx-1][nz-1][F]) */
-size_t mb_layer_update_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int mode);
+size_t mb_layer_update_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int F, int mode);
+/* smallest workspace with which T frames still go through as ONE chunk (MB_MODE_FAST: the feature pass may
+ * then take several rounds; 0 if T frames can never form one chunk).  With less, mb_layer_update splits the
+ * call into chunks of fewer frames; with less than the T = 1 size it fails. */
+size_t mb_layer_update_min_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int F, int mode);
 int mb_layer_update(void *stream, const float *rays, const float *depth, const float *features,
                     const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw,
                     int F, const float *bins_x, int nx, const float *bins_y, int ny,

@@ -51,7 +51,8 @@ _SIGNATURES = {
     "mb_update_feature_map_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "mb_update_feature_map": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _i32,
                                      _i32, _f32, _i32, _vp, _sz]),
-    "mb_layer_update_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "mb_layer_update_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "mb_layer_update_min_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "mb_layer_update_status": (_i32, [_vp, _vp, _vp]),
     "mb_class_presence_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "mb_class_presence": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _sz]),

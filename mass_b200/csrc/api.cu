@@ -178,11 +178,11 @@ MB_API int mb_layer_update_status(void *stream_, const void *workspace, uint32_t
 // ---- a6..a9 ---------------------------------------------------------------------------------
 // frames the batched path fuses per internal chunk when the caller sizes the workspace with
 // mb_layer_update_workspace_bytes (a larger workspace is used if given)
-static const int MB_DEFAULT_CHUNK_FRAMES = 128;
+static const int MB_DEFAULT_CHUNK_FRAMES = 512;
 
-MB_API size_t mb_layer_update_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int mode)
+MB_API size_t mb_layer_update_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int F, int mode)
 {
-    if (H <= 0 || W <= 0 || T <= 0 || nx < 2 || ny < 2 || nz < 2) return 256;
+    if (H <= 0 || W <= 0 || T <= 0 || F <= 0 || nx < 2 || ny < 2 || nz < 2) return 256;
     const uint32_t npix = (uint32_t)H * (uint32_t)W;
     if (mode == MB_MODE_EXACT) return splat_workspace_bytes(npix);
     int limit = MB_DEFAULT_CHUNK_FRAMES;
@@ -191,8 +191,17 @@ MB_API size_t mb_layer_update_workspace_bytes(int H, int W, int nx, int ny, int 
         if (v >= 1 && v <= 4096) limit = v;
     }
     int chunk = T < limit ? T : limit;
-    while (chunk > 1 && (uint64_t)chunk * npix * 8 >= 0xffffffffull) chunk /= 2;
-    return mbk_batch_workspace_bytes(npix, nx, ny, nz, chunk);
+    while (chunk > 1 && (uint64_t)chunk * npix >= 0x7fffffffull) chunk /= 2;
+    return mbk_batch_workspace_bytes(npix, nx, ny, nz, chunk, F);
+}
+
+MB_API size_t mb_layer_update_min_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int F, int mode)
+{
+    if (H <= 0 || W <= 0 || T <= 0 || F <= 0 || nx < 2 || ny < 2 || nz < 2) return 256;
+    const uint32_t npix = (uint32_t)H * (uint32_t)W;
+    if (mode == MB_MODE_EXACT) return splat_workspace_bytes(npix);
+    if ((uint64_t)T * npix >= 0x7fffffffull) return 0;          // never fits one chunk
+    return mbk_batch_min_workspace_bytes(npix, nx, ny, nz, T, F);
 }
 
 MB_API int mb_layer_update(void *stream_, const float *rays, const float *depth, const float *features,
@@ -220,10 +229,10 @@ MB_API int mb_layer_update(void *stream_, const float *rays, const float *depth,
     const uint32_t npix = (uint32_t)H * (uint32_t)W;
     const size_t feat_stride = (size_t)fh * fw * F;
     if (mode == MB_MODE_FAST) {
-        // batched brick pipeline, as many frames per chunk as the workspace holds
-        const int chunk = workspace ? mbk_batch_frames_that_fit(npix, nx, ny, nz, workspace_bytes, T) : 0;
+        // batched cell pipeline, as many frames per chunk as the workspace holds
+        const int chunk = workspace ? mbk_batch_frames_that_fit(npix, nx, ny, nz, F, workspace_bytes, T) : 0;
         MB_REQUIRE(chunk >= 1, "mb_layer_update: workspace too small (%zu < %zu)", workspace_bytes,
-                   mbk_batch_workspace_bytes(npix, nx, ny, nz, 1));
+                   mbk_batch_workspace_bytes(npix, nx, ny, nz, 1, F));
         for (int t = 0; t < T; t += chunk) {
             const int n = T - t < chunk ? T - t : chunk;
             int rc = mbk_batch_update(stream, rays, depth + (size_t)t * npix,

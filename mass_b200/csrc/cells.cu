@@ -1,0 +1,886 @@
+// Batched mapping pipeline (sm_100a): T frames fused per call, in frame order, without float atomics.
+//
+// The per-frame update of a voxel is affine in the old row:
+//     new = a_t * old + (alpha / W_t) * sum_i w_i^2 f_i,   a_t = 1 - alpha * S2_t / W_t,
+//     W_t = sum_i w_i, S2_t = sum_i w_i^2 over the contributions i of frame t to that voxel.
+// Composing the T frames of a call gives, per voxel,
+//     new = (prod_t a_t) * old + sum_i [ w_i^2 * (alpha / W_t(i)) * prod_{s > t(i)} a_s ] * f_i
+// i.e. a scalar pass that needs the frame order (W, S2, a, suffix products: no feature data) and a
+// feature pass that is a plain weighted sum of feature rows -- order-free, so it can be arranged
+// for the memory system instead of for the frame order.
+//
+// The 8 contributions of a pixel go to the 2x2x2 voxels above its lower-corner "cell"
+// (/root/reference/mass/utils/projection.py:280-323).  Pixels are therefore sorted by cell, not
+// contributions by voxel: one feature-row load feeds 8 accumulators.
+//
+//   K1  k_cell_voxelise   pixel -> record {cell key, 3 in-voxel ratios}, key array for the sort
+//   --  stable radix sort of (cell key, pixel id): inside a cell the pixels stay in (frame, pixel) order
+//   K2  k_cell_flags      head flags of cells, (cell, frame) segments and accumulate runs + counts
+//   --  three exclusive scans (ranks)
+//   K3  k_cell_emit       unique cell list, segment list, touched-voxel bitmap
+//   K4  k_vox_count/emit  ordered list of touched voxels
+//   K5  k_seg_sums        per segment and slot: W, S2                                  (scalars)
+//   K6  k_voxel_scalars   per touched voxel: backward merge of its <= 8 cells' segment lists ->
+//                         coefficient g = (alpha / W_t) * prod_{s>t} a_s per (segment, slot), A = prod a
+//   K7  k_cell_accumulate per run of same-cell pixels: 8 rows P_k = sum_i w_ik^2 g_k f_i   (the hot loop)
+//   K8  k_voxel_apply     per touched voxel: map = A * map + sum over its cells' runs of P
+//
+// Every sum runs in an order fixed by the sorted list, so results are bit-reproducible run to run.
+// Weights follow the reference's fp32 operation order; occupancy is bit-exact and values differ from
+// the reference CPU path by fp32 re-association only (<= 1e-5 relative).
+#include "common.cuh"
+#include "kernels.cuh"
+#include "geometry.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int CH = 256;                  // sorted positions per accumulate task; runs never cross a task
+constexpr int ACC_THREADS = 256;
+
+// Cells live on the map grid extended by one at the low end of each axis: a pixel in voxel 0 with
+// ratio < 0.5 has its lower corner at -1 (the reference clamps that neighbour onto voxel 0).
+struct CellGrid {
+    int S0, S1, S2;          // map dims (y flipped, x, z)
+    int E0, E1, E2;          // S + 1 cell coordinates per axis: e = corner + 1 in [0, S]
+    uint32_t invalid;        // key of invalid pixels = E0*E1*E2 (sorts last)
+};
+
+__host__ __device__ inline CellGrid make_cells(int S0, int S1, int S2)
+{
+    CellGrid g;
+    g.S0 = S0; g.S1 = S1; g.S2 = S2;
+    g.E0 = S0 + 1; g.E1 = S1 + 1; g.E2 = S2 + 1;
+    g.invalid = (uint32_t)g.E0 * (uint32_t)g.E1 * (uint32_t)g.E2;
+    return g;
+}
+
+__device__ __forceinline__ uint32_t cell_key(const CellGrid &g, int e0, int e1, int e2)
+{
+    return ((uint32_t)e0 * (uint32_t)g.E1 + (uint32_t)e1) * (uint32_t)g.E2 + (uint32_t)e2;
+}
+
+// the 8 splat weights of a pixel, slot k = (d0 << 2) | (d1 << 1) | d2 (projection.py:300-323)
+__device__ __forceinline__ void splat_weights(const uint4 &rec, float (&w)[8])
+{
+    const float q[3] = { __uint_as_float(rec.y), __uint_as_float(rec.z), __uint_as_float(rec.w) };
+    float wl[3], wu[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const bool low = q[a] < 0.5f;
+        wl[a] = low ? __fsub_rn(0.5f, q[a]) : __fsub_rn(1.5f, q[a]);
+        wu[a] = low ? __fadd_rn(q[a], 0.5f) : __fsub_rn(q[a], 0.5f);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        w[k] = __fadd_rn(1e-9f, __fmul_rn(__fmul_rn((k & 4) ? wu[0] : wl[0], (k & 2) ? wu[1] : wl[1]),
+                                          (k & 1) ? wu[2] : wl[2]));
+}
+
+// which slots of the cell at extended coordinate e = v + a (a in {0,1} per axis) land on voxel v:
+// per axis, slot bit d lands on clamp(e - 1 + d, 0, S - 1)
+__device__ __forceinline__ uint32_t axis_slots(int v, int a, int S)
+{
+    // a == 0: corner v-1: d=1 -> v always; d=0 -> clamp(v-1) == v only for v == 0
+    // a == 1: corner v:   d=0 -> v always; d=1 -> clamp(v+1) == v only for v == S-1
+    return a == 0 ? (2u | (v == 0 ? 1u : 0u)) : (1u | (v == S - 1 ? 2u : 0u));
+}
+
+__device__ __forceinline__ uint32_t slot_mask(int v0, int v1, int v2, int src, const CellGrid &g)
+{
+    const uint32_t m0 = axis_slots(v0, (src >> 2) & 1, g.S0), m1 = axis_slots(v1, (src >> 1) & 1, g.S1),
+                   m2 = axis_slots(v2, src & 1, g.S2);
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (((m0 >> ((k >> 2) & 1)) & 1u) && ((m1 >> ((k >> 1) & 1)) & 1u) && ((m2 >> (k & 1)) & 1u)) m |= 1u << k;
+    return m;
+}
+
+// index of `key` in the ascending unique-cell list, or -1
+__device__ __forceinline__ int find_cell(const uint32_t *__restrict__ ucell, uint32_t ncells, uint32_t key)
+{
+    uint32_t lo = 0, hi = ncells;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(ucell + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return (lo < ncells && __ldg(ucell + lo) == key) ? (int)lo : -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: grid = (pixel blocks, frames)
+__global__ void __launch_bounds__(256)
+k_cell_voxelise(const float *__restrict__ rays, const float *__restrict__ depth, const float *__restrict__ pose,
+                uint32_t npix, const float *__restrict__ bins_x, int nx, const float *__restrict__ bins_y, int ny,
+                const float *__restrict__ bins_z, int nz, CellGrid g, float min_d, float max_d,
+                uint4 *__restrict__ rec, uint32_t *__restrict__ keys, uint32_t *__restrict__ counters)
+{
+    __shared__ float P[12];
+    const uint32_t t = blockIdx.y;
+    if (threadIdx.x < 12) P[threadIdx.x] = pose[(size_t)t * 12 + threadIdx.x];
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < MB_NUM_COUNTERS) counters[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const size_t pid = (size_t)t * npix + p;
+    float r0, r1, r2;
+    orient(P, rays[3 * (size_t)p], rays[3 * (size_t)p + 1], rays[3 * (size_t)p + 2], r0, r1, r2);
+    const BinResult b = bin_point(bins_x, nx, bins_y, ny, bins_z, nz, P[9], P[10], P[11], r0, r1, r2,
+                                  depth[pid], min_d, max_d);
+    uint4 out = make_uint4(g.invalid, 0u, 0u, 0u);
+    if (b.ok) {
+        // map axes are (y flipped, x, z) = input axes (1, 0, 2): base_projection_layer.py:339
+        const float q0 = b.q1, q1 = b.q0, q2 = b.q2;
+        const int e0 = q0 < 0.5f ? b.i1 : b.i1 + 1;       // lower corner + 1
+        const int e1 = q1 < 0.5f ? b.i0 : b.i0 + 1;
+        const int e2 = q2 < 0.5f ? b.i2 : b.i2 + 1;
+        out = make_uint4(cell_key(g, e0, e1, e2), __float_as_uint(q0), __float_as_uint(q1), __float_as_uint(q2));
+    }
+    rec[pid] = out;
+    keys[pid] = out.x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: one thread per sorted position.  cell head: first pixel of a cell; segment head: first pixel
+// of a (cell, frame); run head: cell head or start of an accumulate task.
+__global__ void __launch_bounds__(256)
+k_cell_flags(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ spid, uint32_t n, uint32_t npix,
+             uint32_t invalid, uint32_t *__restrict__ cmask, uint32_t *__restrict__ smask, uint32_t *__restrict__ ccnt,
+             uint32_t *__restrict__ scnt, uint32_t *__restrict__ rcnt, uint32_t *__restrict__ counters)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool chead = false, shead = false, rhead = false;
+    if (i < n) {
+        const uint32_t k = skey[i];
+        if (k < invalid) {
+            const uint32_t kp = i ? skey[i - 1] : 0xffffffffu;
+            chead = i == 0 || kp != k;
+            shead = chead || spid[i - 1] / npix != spid[i] / npix;
+            rhead = chead || (i % CH) == 0;
+            if (i + 1 == n || skey[i + 1] >= invalid) counters[MB_CNT_NVALID] = i + 1;
+        }
+    }
+    const uint32_t cm = __ballot_sync(FULL, chead), sm = __ballot_sync(FULL, shead), rm = __ballot_sync(FULL, rhead);
+    if ((threadIdx.x & 31) == 0 && (i >> 5) <= (n >> 5)) {
+        cmask[i >> 5] = cm;
+        smask[i >> 5] = sm;
+        ccnt[i >> 5] = __popc(cm);
+        scnt[i >> 5] = __popc(sm);
+        rcnt[i >> 5] = __popc(rm);
+    }
+}
+
+// K3: unique cells, segments, touched-voxel bitmap.  coff/soff/roff = exclusive scans of the counts.
+__global__ void __launch_bounds__(256)
+k_cell_emit(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ spid, uint32_t n, uint32_t npix,
+            CellGrid g, const uint32_t *__restrict__ cmask, const uint32_t *__restrict__ smask,
+            const uint32_t *__restrict__ coff, const uint32_t *__restrict__ soff, const uint32_t *__restrict__ roff,
+            uint32_t *__restrict__ ucell, uint32_t *__restrict__ cstart, uint32_t *__restrict__ cseg,
+            uint32_t *__restrict__ crun, uint32_t *__restrict__ seg_start, uint32_t *__restrict__ seg_frame,
+            uint32_t *__restrict__ bitmap, uint32_t *__restrict__ counters)
+{
+    const uint32_t nvalid = counters[MB_CNT_NVALID];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const uint32_t w = i >> 5, lt = (1u << lane) - 1u;
+    const uint32_t cm = cmask[w], sm = smask[w];
+    const uint32_t crank = coff[w] + __popc(cm & lt), srank = soff[w] + __popc(sm & lt);
+    if (i < nvalid) {
+        if ((sm >> lane) & 1u) {
+            seg_start[srank] = i;
+            seg_frame[srank] = spid[i] / npix;
+        }
+        if ((cm >> lane) & 1u) {
+            const uint32_t key = skey[i];
+            // run rank: run heads before i = cell heads + task starts that are not cell heads; i is a
+            // cell head here, so its rank is the scan value of its word plus the heads before it in the
+            // word -- recomputed from the definition to avoid storing a third mask
+            uint32_t rr = roff[w];
+            {
+                const uint32_t wbase = w << 5;
+                uint32_t rm = cm;
+                if ((wbase % CH) == 0) rm |= 1u;           // CH is a multiple of 32: only bit 0 can be a task start
+                rr += __popc(rm & lt);
+            }
+            ucell[crank] = key;
+            cstart[crank] = i;
+            cseg[crank] = srank;
+            crun[crank] = rr;
+            const int e2 = (int)(key % (uint32_t)g.E2);
+            const uint32_t t = key / (uint32_t)g.E2;
+            const int e1 = (int)(t % (uint32_t)g.E1), e0 = (int)(t / (uint32_t)g.E1);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int v0 = min(max(e0 - 1 + ((k >> 2) & 1), 0), g.S0 - 1);
+                const int v1 = min(max(e1 - 1 + ((k >> 1) & 1), 0), g.S1 - 1);
+                const int v2 = min(max(e2 - 1 + (k & 1), 0), g.S2 - 1);
+                const uint32_t v = ((uint32_t)v0 * (uint32_t)g.S1 + (uint32_t)v1) * (uint32_t)g.S2 + (uint32_t)v2;
+                atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+            }
+        }
+    }
+    if (nvalid > 0 && i == nvalid - 1) {
+        // totals and sentinels
+        const uint32_t lemask = lane == 31 ? 0xffffffffu : ((2u << lane) - 1u);
+        const uint32_t nc = coff[w] + __popc(cm & lemask), ns = soff[w] + __popc(sm & lemask);
+        uint32_t rm = cm;
+        if (((w << 5) % CH) == 0) rm |= 1u;
+        const uint32_t nr = roff[w] + __popc(rm & lemask);
+        counters[MB_CNT_CELLS] = nc;
+        counters[MB_CNT_SEGS] = ns;
+        counters[MB_CNT_RUNS] = nr;
+        cstart[nc] = nvalid;
+        cseg[nc] = ns;
+        crun[nc] = nr;
+        seg_start[ns] = nvalid;
+    }
+}
+
+// K4: ordered list of touched voxels from the bitmap
+__global__ void __launch_bounds__(256)
+k_vox_count(const uint32_t *__restrict__ bitmap, uint32_t nwords, uint32_t *__restrict__ vcnt)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nwords) vcnt[i] = __popc(bitmap[i]);
+}
+
+__global__ void __launch_bounds__(256)
+k_vox_emit(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ voff, uint32_t nwords,
+           uint32_t *__restrict__ vlist, uint32_t *__restrict__ counters)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    uint32_t m = bitmap[i];
+    uint32_t o = voff[i];
+    if (i == nwords - 1) counters[MB_CNT_VOX] = o + __popc(m);
+    while (m) {
+        const int b = __ffs(m) - 1;
+        vlist[o++] = (i << 5) + (uint32_t)b;
+        m &= m - 1;
+    }
+}
+
+// K5: per (cell, frame) segment and slot: W = sum w, S2 = sum w^2, in pixel order
+__global__ void __launch_bounds__(256)
+k_seg_sums(const uint32_t *__restrict__ spid, const uint4 *__restrict__ rec, const uint32_t *__restrict__ seg_start,
+           float2 *__restrict__ segws, const uint32_t *__restrict__ counters)
+{
+    const uint32_t nsegs = counters[MB_CNT_SEGS];
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nsegs; s += gridDim.x * blockDim.x) {
+        const uint32_t beg = seg_start[s], end = seg_start[s + 1];
+        float W[8], S2[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { W[k] = 0.f; S2[k] = 0.f; }
+        for (uint32_t i = beg; i < end; ++i) {
+            const uint4 r = __ldg(rec + spid[i]);
+            float w[8];
+            splat_weights(r, w);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { W[k] += w[k]; S2[k] = fmaf(w[k], w[k], S2[k]); }
+        }
+        float4 *o = (float4 *)(segws + (size_t)s * 8);
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) o[k >> 1] = make_float4(W[k], S2[k], W[k + 1], S2[k + 1]);
+    }
+}
+
+// K6: one thread per touched voxel.  Its contributions come from the <= 8 cells at extended
+// coordinates v + {0,1}^3; each cell's segments are sorted by frame.  Walk all lists backwards
+// (latest frame first) so that the suffix product of a over later frames is at hand.
+__global__ void __launch_bounds__(128)
+k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__ ucell, const uint32_t *__restrict__ cseg,
+                const uint32_t *__restrict__ seg_frame, const float2 *__restrict__ segws, CellGrid g, float alpha,
+                float *__restrict__ gcoef, float *__restrict__ vA, const uint32_t *__restrict__ counters)
+{
+    const uint32_t nvox = counters[MB_CNT_VOX], ncells = counters[MB_CNT_CELLS];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nvox; j += gridDim.x * blockDim.x) {
+        const uint32_t v = vlist[j];
+        const int v2 = (int)(v % (uint32_t)g.S2);
+        const uint32_t t01 = v / (uint32_t)g.S2;
+        const int v1 = (int)(t01 % (uint32_t)g.S1), v0 = (int)(t01 / (uint32_t)g.S1);
+        int ptr[8], lo[8];
+        uint32_t mask[8], fr[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int u = find_cell(ucell, ncells, cell_key(g, v0 + ((s >> 2) & 1), v1 + ((s >> 1) & 1), v2 + (s & 1)));
+            mask[s] = slot_mask(v0, v1, v2, s, g);
+            if (u >= 0) { lo[s] = (int)cseg[u]; ptr[s] = (int)cseg[u + 1] - 1; }
+            else { lo[s] = 0; ptr[s] = -1; }
+            fr[s] = ptr[s] >= lo[s] ? seg_frame[ptr[s]] : 0u;
+        }
+        float suffix = 1.0f;
+        for (;;) {
+            bool any = false;
+            uint32_t t = 0;
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                if (ptr[s] >= lo[s]) { t = any ? max(t, fr[s]) : fr[s]; any = true; }
+            if (!any) break;
+            float W = 0.f, S2 = 0.f;
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                if (ptr[s] >= lo[s] && fr[s] == t) {
+                    const float2 *ws = segws + (size_t)ptr[s] * 8;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if ((mask[s] >> k) & 1u) { const float2 x = ws[k]; W += x.x; S2 += x.y; }
+                }
+            const float r = alpha / W;
+            const float a = 1.0f - r * S2;
+            const float gv = suffix * r;
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                if (ptr[s] >= lo[s] && fr[s] == t) {
+                    float *go = gcoef + (size_t)ptr[s] * 8;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if ((mask[s] >> k) & 1u) go[k] = gv;
+                    --ptr[s];
+                    if (ptr[s] >= lo[s]) fr[s] = seg_frame[ptr[s]];
+                }
+            suffix *= a;
+        }
+        vA[j] = suffix;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: the hot loop.  One warp per task of CH sorted pixels; lanes = channels (VEC floats per lane and
+// iteration, IT iterations).  Per batch of 32 pixels the lanes first act as pixels: record + segment
+// coefficient -> 8 splat coefficients per pixel, staged in shared memory; then the warp walks the 32
+// pixels: one feature row load + 8 coefficient broadcasts + 8 FMAs per lane-vector.  A run of
+// same-cell pixels accumulates in registers and is flushed as 8 rows of P.
+struct AccArgs {
+    const uint32_t *skey, *spid;
+    const uint4 *rec;
+    const uint32_t *smask, *soff, *roff;
+    const float *gcoef;
+    const uint32_t *counters;
+    MbFeatIndex fi;             // np = pixels per frame
+    uint32_t fhw;               // feature rows per frame
+    const float *features;      // [T][fhw][F] or null
+    const int64_t *class_ids;   // [T][np] or null (one-hot features)
+    int F;
+    float *P;                   // [run][8][F]
+    uint32_t run_base, run_cap; // runs of this round: [run_base, run_base + run_cap)
+};
+
+template <int VEC>
+__device__ __forceinline__ void row_load(float (&dst)[VEC], const float *p)
+{
+    if (VEC == 1) dst[0] = __ldg(p);
+    if (VEC == 2) { const float2 v = __ldg((const float2 *)p); dst[0] = v.x; dst[VEC > 1 ? 1 : 0] = v.y; }
+    if (VEC == 4) {
+        const float4 v = __ldg((const float4 *)p);
+        dst[0] = v.x; dst[VEC > 1 ? 1 : 0] = v.y; dst[VEC > 2 ? 2 : 0] = v.z; dst[VEC > 2 ? 3 : 0] = v.w;
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void row_store(float *p, const float (&src)[VEC])
+{
+    if (VEC == 1) *p = src[0];
+    if (VEC == 2) *(float2 *)p = make_float2(src[0], src[VEC > 1 ? 1 : 0]);
+    if (VEC == 4) *(float4 *)p = make_float4(src[0], src[VEC > 1 ? 1 : 0], src[VEC > 2 ? 2 : 0], src[VEC > 2 ? 3 : 0]);
+}
+
+template <int VEC, int IT, bool ONEHOT, int U>
+__global__ void __launch_bounds__(ACC_THREADS)
+k_cell_accumulate(const AccArgs A)
+{
+    constexpr int NW = ACC_THREADS / 32;
+    __shared__ __align__(16) float s_coef[NW][32][8];
+    __shared__ uint32_t s_src[NW][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nvalid = A.counters[MB_CNT_NVALID], nruns = A.counters[MB_CNT_RUNS];
+    if (A.run_base >= nruns) return;
+    const uint32_t run_end = A.run_base + A.run_cap;
+    const int F = A.F;
+    const int ch0 = (int)blockIdx.y * (32 * VEC * IT) + lane * VEC;     // first channel of this lane
+    const uint32_t ntasks = (nvalid + CH - 1) / CH;
+    const uint32_t np = A.fi.np;
+    const uint32_t lemask = lane == 31 ? 0xffffffffu : ((2u << lane) - 1u);
+
+    for (uint32_t task = blockIdx.x * NW + warp; task < ntasks; task += gridDim.x * NW) {
+        const uint32_t base = task * CH, end = min(base + (uint32_t)CH, nvalid);
+        uint32_t e = A.roff[base >> 5];                                  // rank of the task's first run
+        {
+            const uint32_t e_after = end == nvalid ? nruns : A.roff[end >> 5];
+            if (e_after <= A.run_base || e >= run_end) continue;         // no run of this round in the task
+        }
+        float acc[8][IT][VEC];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int it = 0; it < IT; ++it)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) acc[k][it][j] = 0.f;
+        uint32_t lastkey = 0xffffffffu;                                   // != any valid key: forces a head at `base`
+
+        auto flush = [&]() {
+            if (e >= A.run_base && e < run_end) {
+                float *prow = A.P + (size_t)(e - A.run_base) * 8 * F;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                    for (int it = 0; it < IT; ++it) {
+                        const int ch = ch0 + it * 32 * VEC;
+                        if (ch < F) row_store<VEC>(prow + (size_t)k * F + ch, acc[k][it]);
+                    }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int it = 0; it < IT; ++it)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) acc[k][it][j] = 0.f;
+            ++e;
+        };
+
+        for (uint32_t b0 = base; b0 < end; b0 += 32) {
+            // ---- lanes = pixels: coefficients of the batch ------------------------------------------------
+            const uint32_t i = b0 + lane;
+            const bool ok = i < end;
+            const uint32_t key = ok ? A.skey[i] : 0xfffffffeu;
+            uint32_t prevkey = __shfl_up_sync(FULL, key, 1);
+            if (lane == 0) prevkey = lastkey;
+            lastkey = __shfl_sync(FULL, key, 31);
+            const uint32_t hm = __ballot_sync(FULL, ok && key != prevkey);
+            {
+                float c[8];
+                uint32_t src = 0;
+                if (ok) {
+                    const uint32_t pid = A.spid[i];
+                    const uint32_t w = i >> 5;
+                    const uint32_t s = A.soff[w] + __popc(A.smask[w] & lemask) - 1u;
+                    const uint4 r = __ldg(A.rec + pid);
+                    const float4 g0 = __ldg((const float4 *)(A.gcoef + (size_t)s * 8));
+                    const float4 g1 = __ldg((const float4 *)(A.gcoef + (size_t)s * 8 + 4));
+                    splat_weights(r, c);
+                    c[0] = c[0] * c[0] * g0.x; c[1] = c[1] * c[1] * g0.y; c[2] = c[2] * c[2] * g0.z; c[3] = c[3] * c[3] * g0.w;
+                    c[4] = c[4] * c[4] * g1.x; c[5] = c[5] * c[5] * g1.y; c[6] = c[6] * c[6] * g1.z; c[7] = c[7] * c[7] * g1.w;
+                    if (ONEHOT) {
+                        src = (uint32_t)A.class_ids[pid];
+                    } else {
+                        const uint32_t frame = pid / np, p = pid - frame * np;
+                        if (A.fi.kx == 1 && A.fi.ky == 1) {
+                            src = frame * A.fhw + p;
+                        } else {
+                            const uint32_t y = p / A.fi.W, x = p - y * A.fi.W;
+                            src = frame * A.fhw + (y / A.fi.ky) * A.fi.fw + x / A.fi.kx;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) c[k] = 0.f;
+                }
+                __syncwarp();
+                *(float4 *)&s_coef[warp][lane][0] = make_float4(c[0], c[1], c[2], c[3]);
+                *(float4 *)&s_coef[warp][lane][4] = make_float4(c[4], c[5], c[6], c[7]);
+                s_src[warp][lane] = src;
+                __syncwarp();
+            }
+
+            // ---- lanes = channels: walk the batch ---------------------------------------------------------
+            const int nb = (int)min(32u, end - b0);
+            int jj = 0;
+            while (jj < nb) {
+                if (((hm >> jj) & 1u) && !(b0 == base && jj == 0)) flush();
+                const uint32_t rest = jj < 31 ? (hm >> (jj + 1)) : 0u;
+                int jend = rest ? jj + __ffs(rest) : nb;            // next head (exclusive end of this stretch)
+                if (jend > nb) jend = nb;
+                for (; jj + U <= jend; jj += U) {
+                    float f[U][IT][VEC];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const uint32_t src = s_src[warp][jj + u];
+#pragma unroll
+                        for (int it = 0; it < IT; ++it) {
+                            const int ch = ch0 + it * 32 * VEC;
+                            if (ONEHOT) {
+#pragma unroll
+                                for (int j = 0; j < VEC; ++j) f[u][it][j] = (uint32_t)(ch + j) == src ? 1.0f : 0.0f;
+                            } else if (ch < F) {
+                                row_load<VEC>(f[u][it], A.features + (size_t)src * F + ch);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < VEC; ++j) f[u][it][j] = 0.f;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const float4 c0 = *(const float4 *)&s_coef[warp][jj + u][0];
+                        const float4 c1 = *(const float4 *)&s_coef[warp][jj + u][4];
+                        const float c[8] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w };
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+#pragma unroll
+                            for (int it = 0; it < IT; ++it)
+#pragma unroll
+                                for (int j = 0; j < VEC; ++j) acc[k][it][j] = fmaf(c[k], f[u][it][j], acc[k][it][j]);
+                    }
+                }
+                for (; jj < jend; ++jj) {
+                    float f[IT][VEC];
+                    const uint32_t src = s_src[warp][jj];
+#pragma unroll
+                    for (int it = 0; it < IT; ++it) {
+                        const int ch = ch0 + it * 32 * VEC;
+                        if (ONEHOT) {
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) f[it][j] = (uint32_t)(ch + j) == src ? 1.0f : 0.0f;
+                        } else if (ch < F) {
+                            row_load<VEC>(f[it], A.features + (size_t)src * F + ch);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) f[it][j] = 0.f;
+                        }
+                    }
+                    const float4 c0 = *(const float4 *)&s_coef[warp][jj][0];
+                    const float4 c1 = *(const float4 *)&s_coef[warp][jj][4];
+                    const float c[8] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w };
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+#pragma unroll
+                        for (int it = 0; it < IT; ++it)
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) acc[k][it][j] = fmaf(c[k], f[it][j], acc[k][it][j]);
+                }
+            }
+        }
+        flush();
+    }
+}
+
+// K8: one warp per touched voxel: map = A * map + sum of the P rows of its cells' runs (round 0), or
+// map += sum (later rounds, when the runs did not fit one P buffer).
+struct ApplyArgs {
+    const uint32_t *vlist, *ucell, *crun;
+    const float *vA, *P;
+    const uint32_t *counters;
+    CellGrid g;
+    int F;
+    float *map, *affine_a;
+    uint32_t run_base, run_cap;
+};
+
+template <int VEC, int IT>
+__global__ void __launch_bounds__(256)
+k_voxel_apply(const ApplyArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t nvox = A.counters[MB_CNT_VOX], ncells = A.counters[MB_CNT_CELLS], nruns = A.counters[MB_CNT_RUNS];
+    if (A.run_base >= nruns && A.run_base > 0) return;
+    const uint32_t run_end = A.run_base + A.run_cap;
+    const int F = A.F;
+    const int ch0 = (int)blockIdx.y * (32 * VEC * IT) + lane * VEC;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j = wid; j < nvox; j += nw) {
+        const uint32_t v = A.vlist[j];
+        const int v2 = (int)(v % (uint32_t)A.g.S2);
+        const uint32_t t01 = v / (uint32_t)A.g.S2;
+        const int v1 = (int)(t01 % (uint32_t)A.g.S1), v0 = (int)(t01 / (uint32_t)A.g.S1);
+        uint32_t lo = 0, hi = 0;
+        if (lane < 8) {
+            const int u = find_cell(A.ucell, ncells, cell_key(A.g, v0 + ((lane >> 2) & 1), v1 + ((lane >> 1) & 1), v2 + (lane & 1)));
+            if (u >= 0) {
+                lo = max(A.crun[u], A.run_base);
+                hi = min(A.crun[u + 1], run_end);
+            }
+        }
+        float acc[IT][VEC];
+#pragma unroll
+        for (int it = 0; it < IT; ++it)
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) acc[it][q] = 0.f;
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const uint32_t slo = __shfl_sync(FULL, lo, s), shi = __shfl_sync(FULL, hi, s);
+            if (slo >= shi) continue;
+            any = true;
+            const uint32_t m = slot_mask(v0, v1, v2, s, A.g);
+            for (uint32_t e = slo; e < shi; ++e) {
+                const float *prow = A.P + (size_t)(e - A.run_base) * 8 * F;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if ((m >> k) & 1u) {
+#pragma unroll
+                        for (int it = 0; it < IT; ++it) {
+                            const int ch = ch0 + it * 32 * VEC;
+                            if (ch < F) {
+                                float x[VEC];
+                                row_load<VEC>(x, prow + (size_t)k * F + ch);
+#pragma unroll
+                                for (int q = 0; q < VEC; ++q) acc[it][q] += x[q];
+                            }
+                        }
+                    }
+            }
+        }
+        if (A.run_base > 0 && !any) continue;
+        const float a = A.run_base == 0 ? A.vA[j] : 1.0f;
+        float *grow = A.map + (size_t)v * F;
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int ch = ch0 + it * 32 * VEC;
+            if (ch < F) {
+                float old[VEC];
+                if (VEC == 1) old[0] = grow[ch];
+                if (VEC == 2) { const float2 o = *(const float2 *)(grow + ch); old[0] = o.x; old[VEC > 1 ? 1 : 0] = o.y; }
+                if (VEC == 4) { const float4 o = *(const float4 *)(grow + ch); old[0] = o.x; old[VEC > 1 ? 1 : 0] = o.y; old[VEC > 2 ? 2 : 0] = o.z; old[VEC > 2 ? 3 : 0] = o.w; }
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) old[q] = fmaf(a, old[q], acc[it][q]);
+                row_store<VEC>(grow + ch, old);
+            }
+        }
+        if (A.affine_a != nullptr && A.run_base == 0 && blockIdx.y == 0 && lane == 0) A.affine_a[v] = A.affine_a[v] * a;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct CellBuffers {
+    uint32_t *counters;
+    uint4 *rec;
+    uint32_t *keys_a, *keys_b, *pids_a, *pids_b;
+    uint32_t *cmask, *smask, *ccnt, *scnt, *rcnt, *coff, *soff, *roff;
+    uint32_t *ucell, *cstart, *cseg, *crun, *seg_start, *seg_frame;
+    float2 *segws;
+    float *gcoef;
+    uint32_t *bitmap, *vcnt, *voff, *vlist;
+    float *vA;
+    char *scan_ws, *sort_ws;
+    size_t scan_bytes, sort_bytes;
+    float *P;
+    size_t P_floats;
+};
+
+// carves everything but P; returns the bytes used
+size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const CellGrid &g)
+{
+    MbArena a(ws, bytes);
+    const size_t words = (size_t)n / 32 + 2;
+    const size_t V = (size_t)g.S0 * g.S1 * g.S2, vwords = V / 32 + 1;
+    const size_t ncap = (size_t)n < (size_t)g.invalid ? (size_t)n : (size_t)g.invalid;   // unique cells
+    const size_t vcap = V < 8 * ncap ? V : 8 * ncap;                                       // touched voxels
+    b.counters = a.take<uint32_t>(MB_NUM_COUNTERS);       // first: mb_layer_update_status reads them at offset 0
+    b.rec = a.take<uint4>(n);
+    b.keys_a = a.take<uint32_t>(n); b.keys_b = a.take<uint32_t>(n);
+    b.pids_a = a.take<uint32_t>(n); b.pids_b = a.take<uint32_t>(n);
+    b.cmask = a.take<uint32_t>(words); b.smask = a.take<uint32_t>(words);
+    b.ccnt = a.take<uint32_t>(words); b.scnt = a.take<uint32_t>(words); b.rcnt = a.take<uint32_t>(words);
+    b.coff = a.take<uint32_t>(words); b.soff = a.take<uint32_t>(words); b.roff = a.take<uint32_t>(words);
+    b.ucell = a.take<uint32_t>(ncap + 1); b.cstart = a.take<uint32_t>(ncap + 1);
+    b.cseg = a.take<uint32_t>(ncap + 1); b.crun = a.take<uint32_t>(ncap + 1);
+    b.seg_start = a.take<uint32_t>((size_t)n + 1); b.seg_frame = a.take<uint32_t>((size_t)n + 1);
+    b.segws = a.take<float2>((size_t)n * 8);
+    b.gcoef = a.take<float>((size_t)n * 8);
+    b.bitmap = a.take<uint32_t>(vwords); b.vcnt = a.take<uint32_t>(vwords); b.voff = a.take<uint32_t>(vwords);
+    b.vlist = a.take<uint32_t>(vcap + 1);
+    b.vA = a.take<float>(vcap + 1);
+    const size_t scan_n = words > vwords ? words : vwords;
+    b.scan_bytes = mb_scan_workspace_bytes((uint32_t)scan_n);
+    b.scan_ws = a.take<char>(b.scan_bytes);
+    b.sort_bytes = mb_sort_workspace_bytes(n);
+    b.sort_ws = a.take<char>(b.sort_bytes);
+    b.P = a.take<float>(0);
+    const size_t used = mb_align_up(a.used);
+    b.P_floats = bytes > used ? (bytes - used) / sizeof(float) : 0;
+    return used;
+}
+
+// most runs a call can produce: every cell starts one, every task start may split one
+size_t worst_runs(uint32_t n, const CellGrid &g)
+{
+    const size_t ncap = (size_t)n < (size_t)g.invalid ? (size_t)n : (size_t)g.invalid;
+    return ncap + ((size_t)n + CH - 1) / CH;
+}
+
+void pick_vec(const float *features, const float *map, const float *P, int F, int &vec, int &it)
+{
+    const uintptr_t al = (features ? (uintptr_t)features : 0) | (uintptr_t)map | (uintptr_t)P;
+    vec = 1;
+    if (F % 4 == 0 && al % 16 == 0) vec = 4;
+    else if (F % 2 == 0 && al % 8 == 0) vec = 2;
+    it = F > 32 * vec ? 2 : 1;
+}
+
+template <int VEC, int IT, bool ONEHOT, int U>
+int launch_accumulate(cudaStream_t stream, const AccArgs &A)
+{
+    auto kern = k_cell_accumulate<VEC, IT, ONEHOT, U>;
+    int per_sm = 1;
+    MB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ACC_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    const int cblocks = (A.F + 32 * VEC * IT - 1) / (32 * VEC * IT);
+    dim3 grid(MB_NUM_SMS * per_sm, cblocks);
+    kern<<<grid, ACC_THREADS, 0, stream>>>(A);
+    MB_LAUNCHED();
+    return MB_OK;
+}
+
+int dispatch_accumulate(cudaStream_t stream, const AccArgs &A, int vec, int it)
+{
+    const bool oh = A.class_ids != nullptr;
+#define MB_ACC(V, I, UU)                                                              \
+    if (vec == V && it == I)                                                          \
+        return oh ? launch_accumulate<V, I, true, UU>(stream, A) : launch_accumulate<V, I, false, UU>(stream, A)
+    MB_ACC(1, 1, 8); MB_ACC(1, 2, 4); MB_ACC(2, 1, 8); MB_ACC(2, 2, 4); MB_ACC(4, 1, 4); MB_ACC(4, 2, 2);
+#undef MB_ACC
+    mb_set_error("internal: no accumulate kernel for vec %d it %d", vec, it);
+    return MB_ERR_ARG;
+}
+
+template <int VEC, int IT>
+int launch_apply(cudaStream_t stream, const ApplyArgs &A)
+{
+    const int cblocks = (A.F + 32 * VEC * IT - 1) / (32 * VEC * IT);
+    dim3 grid(MB_NUM_SMS * 8, cblocks);
+    k_voxel_apply<VEC, IT><<<grid, 256, 0, stream>>>(A);
+    MB_LAUNCHED();
+    return MB_OK;
+}
+
+int dispatch_apply(cudaStream_t stream, const ApplyArgs &A, int vec, int it)
+{
+#define MB_APP(V, I) if (vec == V && it == I) return launch_apply<V, I>(stream, A)
+    MB_APP(1, 1); MB_APP(1, 2); MB_APP(2, 1); MB_APP(2, 2); MB_APP(4, 1); MB_APP(4, 2);
+#undef MB_APP
+    mb_set_error("internal: no apply kernel for vec %d it %d", vec, it);
+    return MB_ERR_ARG;
+}
+
+}  // namespace
+
+// bytes per P run (8 rows of F floats)
+static size_t run_bytes(int F) { return (size_t)8 * F * sizeof(float); }
+
+// P budget asked for by default: room for min(worst case, one run per 16 pixels), at least 64 MB
+static size_t default_P_bytes(uint32_t n, const CellGrid &g, int F)
+{
+    const size_t worst = worst_runs(n, g) * run_bytes(F);
+    size_t want = ((size_t)n / 16 + 1024) * run_bytes(F);
+    if (want < ((size_t)64 << 20)) want = (size_t)64 << 20;
+    return want < worst ? want : worst;
+}
+
+size_t mbk_batch_workspace_bytes(uint32_t npix, int nx, int ny, int nz, int T, int F)
+{
+    const CellGrid g = make_cells(ny - 1, nx - 1, nz - 1);
+    CellBuffers b;
+    const uint32_t n = (uint32_t)T * npix;
+    return carve_cells(b, nullptr, 0, n, g) + default_P_bytes(n, g, F) + 512;
+}
+
+// smallest workspace that takes T frames in one chunk: the run buffer then holds 1/64 of the worst-case
+// runs (never less than two tasks' worth), i.e. the feature pass may take up to 64 rounds
+size_t mbk_batch_min_workspace_bytes(uint32_t npix, int nx, int ny, int nz, int T, int F)
+{
+    const CellGrid g = make_cells(ny - 1, nx - 1, nz - 1);
+    CellBuffers b;
+    const uint32_t n = (uint32_t)T * npix;
+    const size_t wr = worst_runs(n, g);
+    size_t minruns = wr / 64 + 2 * CH;
+    if (minruns > wr) minruns = wr;
+    return carve_cells(b, nullptr, 0, n, g) + minruns * run_bytes(F) + 512;
+}
+
+// frames per internal chunk for a given workspace; 0 if even one frame does not fit
+int mbk_batch_frames_that_fit(uint32_t npix, int nx, int ny, int nz, int F, size_t workspace_bytes, int T)
+{
+    auto fits = [&](int t) {
+        if ((uint64_t)t * npix >= 0x7fffffffull) return false;
+        return mbk_batch_min_workspace_bytes(npix, nx, ny, nz, t, F) <= workspace_bytes;
+    };
+    if (fits(T)) return T;
+    int best = 0;
+    for (int t = 1; t <= T; t = t < 8 ? t + 1 : t * 2) {
+        if (fits(t)) best = t; else break;
+    }
+    return best;
+}
+
+// One chunk of T frames.
+int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth, const float *features,
+                     const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw, int F,
+                     const float *bins_x, int nx, const float *bins_y, int ny, const float *bins_z, int nz,
+                     float *map, float *affine_a, float alpha, float min_d, float max_d, void *workspace,
+                     size_t workspace_bytes)
+{
+    const uint32_t npix = (uint32_t)H * (uint32_t)W;
+    MB_REQUIRE((uint64_t)T * npix < 0x7fffffffull, "too many pixels per chunk");
+    const uint32_t n = (uint32_t)T * npix;
+    const CellGrid g = make_cells(ny - 1, nx - 1, nz - 1);
+    MB_REQUIRE((uint64_t)g.E0 * g.E1 * g.E2 < 0xfffffff0ull, "map too large for 32-bit cell keys");
+    MB_REQUIRE(class_ids != nullptr || (uint64_t)T * fh * fw < 0xffffffffull, "too many feature rows per chunk");
+    CellBuffers b;
+    MB_REQUIRE(carve_cells(b, workspace, workspace_bytes, n, g) + 512 <= workspace_bytes, "batch workspace too small");
+    const size_t V = (size_t)g.S0 * g.S1 * g.S2;
+    const uint32_t words = n / 32 + 1, vwords = (uint32_t)(V / 32 + 1);
+    int vec, it;
+    pick_vec(features, map, b.P, F, vec, it);
+    const size_t run_cap_sz = b.P_floats / ((size_t)8 * F);
+    const size_t wruns = worst_runs(n, g);
+    MB_REQUIRE(run_cap_sz >= (wruns < 2 * CH ? wruns : 2 * CH), "batch workspace too small for the run buffer");
+    const uint32_t run_cap = (uint32_t)(run_cap_sz < 0x7fffffffull ? run_cap_sz : 0x7fffffffull);
+    const int rounds = (int)((wruns + run_cap - 1) / run_cap);
+    MB_REQUIRE(rounds <= 4096, "batch workspace far too small for the run buffer");
+
+    // K1 + sort
+    dim3 grid((npix + 255) / 256, (unsigned)T);
+    k_cell_voxelise<<<grid, 256, 0, stream>>>(rays, depth, pose, npix, bins_x, nx, bins_y, ny, bins_z, nz, g, min_d,
+                                              max_d, b.rec, b.keys_a, b.counters);
+    MB_LAUNCHED();
+    int bits = 1;
+    while (bits < 32 && (((uint64_t)1) << bits) <= (uint64_t)g.invalid) ++bits;
+    uint32_t *skey, *spid;
+    int rc = mb_sort_pairs(stream, b.keys_a, b.pids_a, b.keys_b, b.pids_b, n, nullptr, bits, true, b.sort_ws,
+                           b.sort_bytes, &skey, &spid);
+    if (rc) return rc;
+
+    // K2 + ranks
+    MB_CHECK_CUDA(cudaMemsetAsync(b.bitmap, 0, (size_t)vwords * sizeof(uint32_t), stream));
+    const unsigned nblk = (unsigned)(((size_t)words * 32 + 255) / 256);
+    k_cell_flags<<<nblk, 256, 0, stream>>>(skey, spid, n, npix, g.invalid, b.cmask, b.smask, b.ccnt, b.scnt, b.rcnt,
+                                           b.counters);
+    MB_LAUNCHED();
+    if ((rc = mb_exclusive_scan_u32(stream, b.ccnt, b.coff, words, b.scan_ws, b.scan_bytes))) return rc;
+    if ((rc = mb_exclusive_scan_u32(stream, b.scnt, b.soff, words, b.scan_ws, b.scan_bytes))) return rc;
+    if ((rc = mb_exclusive_scan_u32(stream, b.rcnt, b.roff, words, b.scan_ws, b.scan_bytes))) return rc;
+    // K3
+    k_cell_emit<<<(n + 255) / 256, 256, 0, stream>>>(skey, spid, n, npix, g, b.cmask, b.smask, b.coff, b.soff, b.roff,
+                                                     b.ucell, b.cstart, b.cseg, b.crun, b.seg_start, b.seg_frame,
+                                                     b.bitmap, b.counters);
+    MB_LAUNCHED();
+    // K4
+    k_vox_count<<<(vwords + 255) / 256, 256, 0, stream>>>(b.bitmap, vwords, b.vcnt);
+    MB_LAUNCHED();
+    if ((rc = mb_exclusive_scan_u32(stream, b.vcnt, b.voff, vwords, b.scan_ws, b.scan_bytes))) return rc;
+    k_vox_emit<<<(vwords + 255) / 256, 256, 0, stream>>>(b.bitmap, b.voff, vwords, b.vlist, b.counters);
+    MB_LAUNCHED();
+    // K5, K6
+    k_seg_sums<<<MB_NUM_SMS * 8, 256, 0, stream>>>(spid, b.rec, b.seg_start, b.segws, b.counters);
+    MB_LAUNCHED();
+    k_voxel_scalars<<<MB_NUM_SMS * 8, 128, 0, stream>>>(b.vlist, b.ucell, b.cseg, b.seg_frame, b.segws, g, alpha,
+                                                        b.gcoef, b.vA, b.counters);
+    MB_LAUNCHED();
+    // K7, K8 (one round unless the runs outgrow the P buffer)
+    AccArgs A;
+    A.skey = skey; A.spid = spid; A.rec = b.rec; A.smask = b.smask; A.soff = b.soff; A.roff = b.roff;
+    A.gcoef = b.gcoef; A.counters = b.counters;
+    A.fi = MbFeatIndex{ npix, (uint32_t)W, (uint32_t)(H / fh), (uint32_t)(W / fw), (uint32_t)fw };
+    A.fhw = (uint32_t)fh * (uint32_t)fw;
+    A.features = features; A.class_ids = class_ids; A.F = F; A.P = b.P; A.run_cap = run_cap;
+    ApplyArgs Y;
+    Y.vlist = b.vlist; Y.ucell = b.ucell; Y.crun = b.crun; Y.vA = b.vA; Y.P = b.P; Y.counters = b.counters;
+    Y.g = g; Y.F = F; Y.map = map; Y.affine_a = affine_a; Y.run_cap = run_cap;
+    for (int r = 0; r < rounds; ++r) {
+        A.run_base = Y.run_base = (uint32_t)r * run_cap;
+        if ((rc = dispatch_accumulate(stream, A, vec, it))) return rc;
+        if ((rc = dispatch_apply(stream, Y, vec, it))) return rc;
+    }
+    return MB_OK;
+}

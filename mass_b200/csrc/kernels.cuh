@@ -2,16 +2,15 @@
 #pragma once
 #include "common.cuh"
 
-// device counters zeroed by K1 at the start of every frame
-constexpr int MB_CNT_HEADS = 0;      // number of voxel segments (= voxels touched by the frame)
-constexpr int MB_CNT_ENTRIES = 1;    // batched path: (brick, pixel) entries emitted
-constexpr int MB_CNT_BRICKS = 2;     // batched path: bricks touched
-constexpr int MB_CNT_TICKET = 3;     // batched path: next brick / group to hand to a CTA
-constexpr int MB_CNT_GROUPS = 4;     // batched path: (brick, frame) groups
-constexpr int MB_CNT_ERROR = 5;      // batched path: sticky error bits (1: an ordering wait timed out)
-constexpr int MB_CNT_BUCKET = 8;     // [32] bricks per log2(entries) bucket
-constexpr int MB_CNT_FILL = 40;      // [32] placement cursors of the buckets
-constexpr int MB_NUM_COUNTERS = 72;
+// device counters at the start of the workspace, zeroed by K1 of every call
+constexpr int MB_CNT_HEADS = 0;      // per-frame path: number of voxel segments (= voxels touched by the frame)
+constexpr int MB_CNT_NVALID = 1;     // batched path: valid pixels (sorted positions before the invalid tail)
+constexpr int MB_CNT_CELLS = 2;      // batched path: distinct cells
+constexpr int MB_CNT_SEGS = 3;       // batched path: (cell, frame) segments
+constexpr int MB_CNT_RUNS = 4;       // batched path: accumulate runs
+constexpr int MB_CNT_ERROR = 5;      // sticky error bits (read by mb_layer_update_status)
+constexpr int MB_CNT_VOX = 6;        // batched path: touched voxels
+constexpr int MB_NUM_COUNTERS = 16;
 
 // How a contribution's point id maps to its feature row.
 //   dense:   row = point id (upsample == 0), or the nearest-upsampled source pixel
@@ -49,9 +48,10 @@ int mbk_voxel_reduce(cudaStream_t stream, const uint32_t *keys, const uint32_t *
                      const MbFeatIndex &fi, const float *features, const int64_t *class_ids, int F,
                      float *map, const MbGrid &g, float alpha, int mode);
 
-// batch.cu: batched brick pipeline (affine form of the update; see the file header)
-int mbk_batch_frames_that_fit(uint32_t npix, int nx, int ny, int nz, size_t workspace_bytes, int T);
-size_t mbk_batch_workspace_bytes(uint32_t npix, int nx, int ny, int nz, int T);
+// cells.cu: batched cell-sorted pipeline (affine form of the update; see the file header)
+int mbk_batch_frames_that_fit(uint32_t npix, int nx, int ny, int nz, int F, size_t workspace_bytes, int T);
+size_t mbk_batch_workspace_bytes(uint32_t npix, int nx, int ny, int nz, int T, int F);
+size_t mbk_batch_min_workspace_bytes(uint32_t npix, int nx, int ny, int nz, int T, int F);
 int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth, const float *features,
                      const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw, int F,
                      const float *bins_x, int nx, const float *bins_y, int ny, const float *bins_z, int nz,

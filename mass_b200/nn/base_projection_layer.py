@@ -63,6 +63,7 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         self.register_buffer('bins_y', _edges(origin_y, map_height, grid_resolution))
         self.register_buffer('bins_z', _edges(origin_z, map_depth, grid_resolution))
         self._ws = _lib.Workspace()
+        self.workspace_limit = None      # optional cap (bytes) on the device scratch buffer of update()
 
     # -- state ---------------------------------------------------------------------------------
     def reset(self, origin_y: float = 0.0, origin_x: float = 0.0, origin_z: float = 0.0):
@@ -107,7 +108,12 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         L = _lib.lib()
         nx, ny, nz = self.bins_x.numel(), self.bins_y.numel(), self.bins_z.numel()
         mode = _lib.MODE_EXACT if self.exact else _lib.MODE_FAST
-        ws = self._ws.get(L.mb_layer_update_workspace_bytes(H, W, nx, ny, nz, T, mode), device)
+        want = L.mb_layer_update_workspace_bytes(H, W, nx, ny, nz, T, F, mode)
+        if self.workspace_limit is not None:
+            # a smaller scratch buffer makes the library split the call (fewer frames per chunk, more
+            # rounds of the feature pass); below the one-frame minimum the call fails
+            want = min(want, int(self.workspace_limit))
+        ws = self._ws.get(want, device)
         _lib.check(L.mb_layer_update(
             _lib.stream_ptr(device), _lib.ptr(self.rays), _lib.ptr(depth), _lib.ptr(features),
             _lib.ptr(class_ids), _lib.ptr(pose), T, H, W, fh, fw, F, _lib.ptr(self.bins_x), nx,
