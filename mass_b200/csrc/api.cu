@@ -188,7 +188,7 @@ MB_API size_t mb_layer_update_workspace_bytes(int H, int W, int nx, int ny, int 
     int limit = MB_DEFAULT_CHUNK_FRAMES;
     if (const char *e = getenv("MASSB200_CHUNK_FRAMES")) {      // tuning aid
         const int v = atoi(e);
-        if (v >= 1 && v <= 4096) limit = v;
+        if (v >= 1 && v <= MB_MAX_CHUNK_FRAMES) limit = v;
     }
     int chunk = T < limit ? T : limit;
     while (chunk > 1 && (uint64_t)chunk * npix >= 0x7fffffffull) chunk /= 2;
@@ -200,7 +200,7 @@ MB_API size_t mb_layer_update_min_workspace_bytes(int H, int W, int nx, int ny, 
     if (H <= 0 || W <= 0 || T <= 0 || F <= 0 || nx < 2 || ny < 2 || nz < 2) return 256;
     const uint32_t npix = (uint32_t)H * (uint32_t)W;
     if (mode == MB_MODE_EXACT) return splat_workspace_bytes(npix);
-    if ((uint64_t)T * npix >= 0x7fffffffull) return 0;          // never fits one chunk
+    if ((uint64_t)T * npix >= 0x7fffffffull || T > MB_MAX_CHUNK_FRAMES) return 0;          // never fits one chunk
     return mbk_batch_min_workspace_bytes(npix, nx, ny, nz, T, F);
 }
 

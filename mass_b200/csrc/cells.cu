@@ -286,63 +286,87 @@ k_seg_sums(const uint32_t *__restrict__ spid, const uint4 *__restrict__ rec, con
     }
 }
 
-// K6: one thread per touched voxel.  Its contributions come from the <= 8 cells at extended
-// coordinates v + {0,1}^3; each cell's segments are sorted by frame.  Walk all lists backwards
-// (latest frame first) so that the suffix product of a over later frames is at hand.
-__global__ void __launch_bounds__(128)
+// K6: one warp per touched voxel.  Its contributions come from the <= 8 cells at extended coordinates
+// v + {0,1}^3; each cell's segments are sorted by frame, one segment per frame.  The warp adds the W / S2
+// sums of all sources into a per-frame table in shared memory (sources one after the other, so the
+// order of the adds is fixed), turns every touched frame into a = 1 - alpha*S2/W and r = alpha/W, and runs
+// a backward product scan over the frames: g(t) = r(t) * prod_{s>t} a(s) is the coefficient of every
+// contribution of frame t to this voxel, A = prod a multiplies the old row.
+__global__ void __launch_bounds__(256)
 k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__ ucell, const uint32_t *__restrict__ cseg,
-                const uint32_t *__restrict__ seg_frame, const float2 *__restrict__ segws, CellGrid g, float alpha,
-                float *__restrict__ gcoef, float *__restrict__ vA, const uint32_t *__restrict__ counters)
+                const uint32_t *__restrict__ seg_frame, const float2 *__restrict__ segws, CellGrid g, float alpha, int T,
+                float *__restrict__ gcoef, float *__restrict__ vA, int *__restrict__ vsrc,
+                const uint32_t *__restrict__ counters)
 {
+    extern __shared__ float s_tab[];                  // [warps][2][Tp]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Tp = (T + 31) & ~31;
+    float *tW = s_tab + (size_t)warp * 2 * Tp, *tS = tW + Tp;
     const uint32_t nvox = counters[MB_CNT_VOX], ncells = counters[MB_CNT_CELLS];
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nvox; j += gridDim.x * blockDim.x) {
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j = wid; j < nvox; j += nw) {
         const uint32_t v = vlist[j];
         const int v2 = (int)(v % (uint32_t)g.S2);
         const uint32_t t01 = v / (uint32_t)g.S2;
         const int v1 = (int)(t01 % (uint32_t)g.S1), v0 = (int)(t01 / (uint32_t)g.S1);
-        int ptr[8], lo[8];
-        uint32_t mask[8], fr[8];
+        uint32_t lo = 0, hi = 0;
+        if (lane < 8) {
+            const int u = find_cell(ucell, ncells, cell_key(g, v0 + ((lane >> 2) & 1), v1 + ((lane >> 1) & 1), v2 + (lane & 1)));
+            if (u >= 0) { lo = cseg[u]; hi = cseg[u + 1]; }
+            vsrc[(size_t)j * 8 + lane] = u;
+        }
+        for (int f = lane; f < Tp; f += 32) { tW[f] = 0.f; tS[f] = 0.f; }
+        __syncwarp();
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
-            const int u = find_cell(ucell, ncells, cell_key(g, v0 + ((s >> 2) & 1), v1 + ((s >> 1) & 1), v2 + (s & 1)));
-            mask[s] = slot_mask(v0, v1, v2, s, g);
-            if (u >= 0) { lo[s] = (int)cseg[u]; ptr[s] = (int)cseg[u + 1] - 1; }
-            else { lo[s] = 0; ptr[s] = -1; }
-            fr[s] = ptr[s] >= lo[s] ? seg_frame[ptr[s]] : 0u;
+            const uint32_t slo = __shfl_sync(FULL, lo, s), shi = __shfl_sync(FULL, hi, s);
+            if (slo >= shi) continue;
+            const uint32_t m = slot_mask(v0, v1, v2, s, g);
+            for (uint32_t q = slo + lane; q < shi; q += 32) {
+                const uint32_t f = seg_frame[q];
+                const float2 *ws = segws + (size_t)q * 8;
+                float W = 0.f, S2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if ((m >> k) & 1u) { const float2 x = ws[k]; W += x.x; S2 += x.y; }
+                tW[f] += W;                            // one segment per frame and source: no two lanes share f
+                tS[f] += S2;
+            }
+            __syncwarp();
         }
-        float suffix = 1.0f;
-        for (;;) {
-            bool any = false;
-            uint32_t t = 0;
+        // backward product scan, 32 frames per step
+        float carry = 1.0f;
+        for (int base = Tp - 32; base >= 0; base -= 32) {
+            const float W = tW[base + lane], S2 = tS[base + lane];
+            float r = 0.f, a = 1.0f;
+            if (W > 0.f) { r = alpha / W; a = 1.0f - r * S2; }
+            float inc = a;                             // inclusive product over lanes >= lane
 #pragma unroll
-            for (int s = 0; s < 8; ++s)
-                if (ptr[s] >= lo[s]) { t = any ? max(t, fr[s]) : fr[s]; any = true; }
-            if (!any) break;
-            float W = 0.f, S2 = 0.f;
-#pragma unroll
-            for (int s = 0; s < 8; ++s)
-                if (ptr[s] >= lo[s] && fr[s] == t) {
-                    const float2 *ws = segws + (size_t)ptr[s] * 8;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if ((mask[s] >> k) & 1u) { const float2 x = ws[k]; W += x.x; S2 += x.y; }
-                }
-            const float r = alpha / W;
-            const float a = 1.0f - r * S2;
-            const float gv = suffix * r;
-#pragma unroll
-            for (int s = 0; s < 8; ++s)
-                if (ptr[s] >= lo[s] && fr[s] == t) {
-                    float *go = gcoef + (size_t)ptr[s] * 8;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if ((mask[s] >> k) & 1u) go[k] = gv;
-                    --ptr[s];
-                    if (ptr[s] >= lo[s]) fr[s] = seg_frame[ptr[s]];
-                }
-            suffix *= a;
+            for (int d = 1; d < 32; d <<= 1) {
+                const float o = __shfl_down_sync(FULL, inc, d);
+                if (lane + d < 32) inc *= o;
+            }
+            float exc = __shfl_down_sync(FULL, inc, 1);  // product over lanes > lane
+            if (lane == 31) exc = 1.0f;
+            tW[base + lane] = r * exc * carry;
+            carry *= __shfl_sync(FULL, inc, 0);
         }
-        vA[j] = suffix;
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const uint32_t slo = __shfl_sync(FULL, lo, s), shi = __shfl_sync(FULL, hi, s);
+            if (slo >= shi) continue;
+            const uint32_t m = slot_mask(v0, v1, v2, s, g);
+            for (uint32_t q = slo + lane; q < shi; q += 32) {
+                const float gv = tW[seg_frame[q]];
+                float *go = gcoef + (size_t)q * 8;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if ((m >> k) & 1u) go[k] = gv;
+            }
+        }
+        if (lane == 0) vA[j] = carry;
+        __syncwarp();
     }
 }
 
@@ -558,7 +582,8 @@ k_cell_accumulate(const AccArgs A)
 // K8: one warp per touched voxel: map = A * map + sum of the P rows of its cells' runs (round 0), or
 // map += sum (later rounds, when the runs did not fit one P buffer).
 struct ApplyArgs {
-    const uint32_t *vlist, *ucell, *crun;
+    const uint32_t *vlist, *crun;
+    const int *vsrc;            // [voxel][8] unique-cell index of each source cell, or -1 (from K6)
     const float *vA, *P;
     const uint32_t *counters;
     CellGrid g;
@@ -572,7 +597,7 @@ __global__ void __launch_bounds__(256)
 k_voxel_apply(const ApplyArgs A)
 {
     const int lane = threadIdx.x & 31;
-    const uint32_t nvox = A.counters[MB_CNT_VOX], ncells = A.counters[MB_CNT_CELLS], nruns = A.counters[MB_CNT_RUNS];
+    const uint32_t nvox = A.counters[MB_CNT_VOX], nruns = A.counters[MB_CNT_RUNS];
     if (A.run_base >= nruns && A.run_base > 0) return;
     const uint32_t run_end = A.run_base + A.run_cap;
     const int F = A.F;
@@ -585,7 +610,7 @@ k_voxel_apply(const ApplyArgs A)
         const int v1 = (int)(t01 % (uint32_t)A.g.S1), v0 = (int)(t01 / (uint32_t)A.g.S1);
         uint32_t lo = 0, hi = 0;
         if (lane < 8) {
-            const int u = find_cell(A.ucell, ncells, cell_key(A.g, v0 + ((lane >> 2) & 1), v1 + ((lane >> 1) & 1), v2 + (lane & 1)));
+            const int u = A.vsrc[(size_t)j * 8 + lane];
             if (u >= 0) {
                 lo = max(A.crun[u], A.run_base);
                 hi = min(A.crun[u + 1], run_end);
@@ -652,6 +677,7 @@ struct CellBuffers {
     float *gcoef;
     uint32_t *bitmap, *vcnt, *voff, *vlist;
     float *vA;
+    int *vsrc;
     char *scan_ws, *sort_ws;
     size_t scan_bytes, sort_bytes;
     float *P;
@@ -681,6 +707,7 @@ size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const Cel
     b.bitmap = a.take<uint32_t>(vwords); b.vcnt = a.take<uint32_t>(vwords); b.voff = a.take<uint32_t>(vwords);
     b.vlist = a.take<uint32_t>(vcap + 1);
     b.vA = a.take<float>(vcap + 1);
+    b.vsrc = a.take<int>((vcap + 1) * 8);
     const size_t scan_n = words > vwords ? words : vwords;
     b.scan_bytes = mb_scan_workspace_bytes((uint32_t)scan_n);
     b.scan_ws = a.take<char>(b.scan_bytes);
@@ -792,7 +819,7 @@ size_t mbk_batch_min_workspace_bytes(uint32_t npix, int nx, int ny, int nz, int 
 int mbk_batch_frames_that_fit(uint32_t npix, int nx, int ny, int nz, int F, size_t workspace_bytes, int T)
 {
     auto fits = [&](int t) {
-        if ((uint64_t)t * npix >= 0x7fffffffull) return false;
+        if ((uint64_t)t * npix >= 0x7fffffffull || t > MB_MAX_CHUNK_FRAMES) return false;
         return mbk_batch_min_workspace_bytes(npix, nx, ny, nz, t, F) <= workspace_bytes;
     };
     if (fits(T)) return T;
@@ -812,6 +839,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
 {
     const uint32_t npix = (uint32_t)H * (uint32_t)W;
     MB_REQUIRE((uint64_t)T * npix < 0x7fffffffull, "too many pixels per chunk");
+    MB_REQUIRE(T <= MB_MAX_CHUNK_FRAMES, "too many frames per chunk");
     const uint32_t n = (uint32_t)T * npix;
     const CellGrid g = make_cells(ny - 1, nx - 1, nz - 1);
     MB_REQUIRE((uint64_t)g.E0 * g.E1 * g.E2 < 0xfffffff0ull, "map too large for 32-bit cell keys");
@@ -864,9 +892,16 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     // K5, K6
     k_seg_sums<<<MB_NUM_SMS * 8, 256, 0, stream>>>(spid, b.rec, b.seg_start, b.segws, b.counters);
     MB_LAUNCHED();
-    k_voxel_scalars<<<MB_NUM_SMS * 8, 128, 0, stream>>>(b.vlist, b.ucell, b.cseg, b.seg_frame, b.segws, g, alpha,
-                                                        b.gcoef, b.vA, b.counters);
-    MB_LAUNCHED();
+    {
+        const size_t smem = (size_t)8 * 2 * ((T + 31) & ~31) * sizeof(float);
+        MB_CHECK_CUDA(cudaFuncSetAttribute(k_voxel_scalars, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        MB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_voxel_scalars, 256, smem));
+        if (per_sm < 1) per_sm = 1;
+        k_voxel_scalars<<<MB_NUM_SMS * per_sm, 256, smem, stream>>>(b.vlist, b.ucell, b.cseg, b.seg_frame, b.segws, g,
+                                                                    alpha, T, b.gcoef, b.vA, b.vsrc, b.counters);
+        MB_LAUNCHED();
+    }
     // K7, K8 (one round unless the runs outgrow the P buffer)
     AccArgs A;
     A.skey = skey; A.spid = spid; A.rec = b.rec; A.smask = b.smask; A.soff = b.soff; A.roff = b.roff;
@@ -875,7 +910,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     A.fhw = (uint32_t)fh * (uint32_t)fw;
     A.features = features; A.class_ids = class_ids; A.F = F; A.P = b.P; A.run_cap = run_cap;
     ApplyArgs Y;
-    Y.vlist = b.vlist; Y.ucell = b.ucell; Y.crun = b.crun; Y.vA = b.vA; Y.P = b.P; Y.counters = b.counters;
+    Y.vlist = b.vlist; Y.vsrc = b.vsrc; Y.crun = b.crun; Y.vA = b.vA; Y.P = b.P; Y.counters = b.counters;
     Y.g = g; Y.F = F; Y.map = map; Y.affine_a = affine_a; Y.run_cap = run_cap;
     for (int r = 0; r < rounds; ++r) {
         A.run_base = Y.run_base = (uint32_t)r * run_cap;

@@ -11,6 +11,7 @@ constexpr int MB_CNT_RUNS = 4;       // batched path: accumulate runs
 constexpr int MB_CNT_ERROR = 5;      // sticky error bits (read by mb_layer_update_status)
 constexpr int MB_CNT_VOX = 6;        // batched path: touched voxels
 constexpr int MB_NUM_COUNTERS = 16;
+constexpr int MB_MAX_CHUNK_FRAMES = 1024;   // frames fused per batched chunk (per-voxel frame table in shared memory)
 
 // How a contribution's point id maps to its feature row.
 //   dense:   row = point id (upsample == 0), or the nearest-upsampled source pixel
