@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(256)
 k_cell_voxelise(const float *__restrict__ rays, const float *__restrict__ depth, const float *__restrict__ pose,
                 uint32_t npix, const float *__restrict__ bins_x, int nx, const float *__restrict__ bins_y, int ny,
                 const float *__restrict__ bins_z, int nz, CellGrid g, float min_d, float max_d,
-                uint4 *__restrict__ rec, uint32_t *__restrict__ keys, uint32_t *__restrict__ counters)
+                uint4 *__restrict__ rec, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, int pbits,
+                uint32_t *__restrict__ counters)
 {
     __shared__ float P[12];
     const uint32_t t = blockIdx.y;
@@ -139,13 +140,14 @@ k_cell_voxelise(const float *__restrict__ rays, const float *__restrict__ depth,
     }
     rec[pid] = out;
     keys[pid] = out.x;
+    vals[pid] = (t << pbits) | p;          // sort value: frame and pixel, no division needed downstream
 }
 
 // ---------------------------------------------------------------------------------------------
 // K2: one thread per sorted position.  cell head: first pixel of a cell; segment head: first pixel
 // of a (cell, frame); run head: cell head or start of an accumulate task.
 __global__ void __launch_bounds__(256)
-k_cell_flags(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ spid, uint32_t n, uint32_t npix,
+k_cell_flags(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sval, uint32_t n, int pbits,
              uint32_t invalid, uint32_t *__restrict__ cmask, uint32_t *__restrict__ smask, uint32_t *__restrict__ ccnt,
              uint32_t *__restrict__ scnt, uint32_t *__restrict__ rcnt, uint32_t *__restrict__ counters)
 {
@@ -156,7 +158,7 @@ k_cell_flags(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ spi
         if (k < invalid) {
             const uint32_t kp = i ? skey[i - 1] : 0xffffffffu;
             chead = i == 0 || kp != k;
-            shead = chead || spid[i - 1] / npix != spid[i] / npix;
+            shead = chead || (sval[i - 1] >> pbits) != (sval[i] >> pbits);
             rhead = chead || (i % CH) == 0;
             if (i + 1 == n || skey[i + 1] >= invalid) counters[MB_CNT_NVALID] = i + 1;
         }
@@ -173,7 +175,7 @@ k_cell_flags(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ spi
 
 // K3: unique cells, segments, touched-voxel bitmap.  coff/soff/roff = exclusive scans of the counts.
 __global__ void __launch_bounds__(256)
-k_cell_emit(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ spid, uint32_t n, uint32_t npix,
+k_cell_emit(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sval, uint32_t n, int pbits,
             CellGrid g, const uint32_t *__restrict__ cmask, const uint32_t *__restrict__ smask,
             const uint32_t *__restrict__ coff, const uint32_t *__restrict__ soff, const uint32_t *__restrict__ roff,
             uint32_t *__restrict__ ucell, uint32_t *__restrict__ cstart, uint32_t *__restrict__ cseg,
@@ -190,7 +192,7 @@ k_cell_emit(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ spid
     if (i < nvalid) {
         if ((sm >> lane) & 1u) {
             seg_start[srank] = i;
-            seg_frame[srank] = spid[i] / npix;
+            seg_frame[srank] = sval[i] >> pbits;
         }
         if ((cm >> lane) & 1u) {
             const uint32_t key = skey[i];
@@ -262,23 +264,35 @@ k_vox_emit(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ vof
     }
 }
 
-// K5: per (cell, frame) segment and slot: W = sum w, S2 = sum w^2, in pixel order
+// K5: per (cell, frame) segment and slot: W = sum w, S2 = sum w^2, in pixel order.  One thread per
+// segment; four records are requested before the first is used (segments average ~6 pixels).
 __global__ void __launch_bounds__(256)
-k_seg_sums(const uint32_t *__restrict__ spid, const uint4 *__restrict__ rec, const uint32_t *__restrict__ seg_start,
-           float2 *__restrict__ segws, const uint32_t *__restrict__ counters)
+k_seg_sums(const uint32_t *__restrict__ sval, const uint4 *__restrict__ rec, const uint32_t *__restrict__ seg_start,
+           uint32_t npix, int pbits, float2 *__restrict__ segws, const uint32_t *__restrict__ counters)
 {
     const uint32_t nsegs = counters[MB_CNT_SEGS];
+    const uint32_t pmask = (1u << pbits) - 1u;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nsegs; s += gridDim.x * blockDim.x) {
         const uint32_t beg = seg_start[s], end = seg_start[s + 1];
         float W[8], S2[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { W[k] = 0.f; S2[k] = 0.f; }
-        for (uint32_t i = beg; i < end; ++i) {
-            const uint4 r = __ldg(rec + spid[i]);
-            float w[8];
-            splat_weights(r, w);
+        for (uint32_t i = beg; i < end; i += 4) {
+            uint4 r[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { W[k] += w[k]; S2[k] = fmaf(w[k], w[k], S2[k]); }
+            for (int u = 0; u < 4; ++u)
+                if (i + u < end) {
+                    const uint32_t sv = sval[i + u];
+                    r[u] = __ldg(rec + (size_t)(sv >> pbits) * npix + (sv & pmask));
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i + u < end) {
+                    float w[8];
+                    splat_weights(r[u], w);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { W[k] += w[k]; S2[k] = fmaf(w[k], w[k], S2[k]); }
+                }
         }
         float4 *o = (float4 *)(segws + (size_t)s * 8);
 #pragma unroll
@@ -304,6 +318,8 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__
     float *tW = s_tab + (size_t)warp * 2 * Tp, *tS = tW + Tp;
     const uint32_t nvox = counters[MB_CNT_VOX], ncells = counters[MB_CNT_CELLS];
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int f = lane; f < Tp; f += 32) { tW[f] = 0.f; tS[f] = 0.f; }
+    __syncwarp();
     for (uint32_t j = wid; j < nvox; j += nw) {
         const uint32_t v = vlist[j];
         const int v2 = (int)(v % (uint32_t)g.S2);
@@ -315,8 +331,8 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__
             if (u >= 0) { lo = cseg[u]; hi = cseg[u + 1]; }
             vsrc[(size_t)j * 8 + lane] = u;
         }
-        for (int f = lane; f < Tp; f += 32) { tW[f] = 0.f; tS[f] = 0.f; }
-        __syncwarp();
+        // the tables are all zero here (zeroed once per warp, and again row by row after use)
+        uint32_t rows = 0;                             // 32-frame rows with at least one touched frame
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
             const uint32_t slo = __shfl_sync(FULL, lo, s), shi = __shfl_sync(FULL, hi, s);
@@ -331,12 +347,17 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__
                     if ((m >> k) & 1u) { const float2 x = ws[k]; W += x.x; S2 += x.y; }
                 tW[f] += W;                            // one segment per frame and source: no two lanes share f
                 tS[f] += S2;
+                rows |= 1u << (f >> 5);
             }
             __syncwarp();
         }
-        // backward product scan, 32 frames per step
+        rows = __reduce_or_sync(FULL, rows);
+        // backward product scan over the touched rows (an untouched row has a = 1 everywhere)
         float carry = 1.0f;
-        for (int base = Tp - 32; base >= 0; base -= 32) {
+        for (uint32_t rm = rows; rm;) {
+            const int row = 31 - __clz(rm);
+            rm &= ~(1u << row);
+            const int base = row << 5;
             const float W = tW[base + lane], S2 = tS[base + lane];
             float r = 0.f, a = 1.0f;
             if (W > 0.f) { r = alpha / W; a = 1.0f - r * S2; }
@@ -349,6 +370,7 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__
             float exc = __shfl_down_sync(FULL, inc, 1);  // product over lanes > lane
             if (lane == 31) exc = 1.0f;
             tW[base + lane] = r * exc * carry;
+            tS[base + lane] = 0.f;
             carry *= __shfl_sync(FULL, inc, 0);
         }
         __syncwarp();
@@ -365,6 +387,8 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__
                     if ((m >> k) & 1u) go[k] = gv;
             }
         }
+        __syncwarp();
+        for (uint32_t rm = rows; rm; rm &= rm - 1) tW[((__ffs(rm) - 1) << 5) + lane] = 0.f;
         if (lane == 0) vA[j] = carry;
         __syncwarp();
     }
@@ -377,7 +401,8 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__
 // pixels: one feature row load + 8 coefficient broadcasts + 8 FMAs per lane-vector.  A run of
 // same-cell pixels accumulates in registers and is flushed as 8 rows of P.
 struct AccArgs {
-    const uint32_t *skey, *spid;
+    const uint32_t *skey, *sval;
+    int pbits;
     const uint4 *rec;
     const uint32_t *smask, *soff, *roff;
     const float *gcoef;
@@ -476,7 +501,9 @@ k_cell_accumulate(const AccArgs A)
                 float c[8];
                 uint32_t src = 0;
                 if (ok) {
-                    const uint32_t pid = A.spid[i];
+                    const uint32_t sv = A.sval[i];
+                    const uint32_t frame = sv >> A.pbits, p = sv & ((1u << A.pbits) - 1u);
+                    const size_t pid = (size_t)frame * np + p;
                     const uint32_t w = i >> 5;
                     const uint32_t s = A.soff[w] + __popc(A.smask[w] & lemask) - 1u;
                     const uint4 r = __ldg(A.rec + pid);
@@ -488,7 +515,6 @@ k_cell_accumulate(const AccArgs A)
                     if (ONEHOT) {
                         src = (uint32_t)A.class_ids[pid];
                     } else {
-                        const uint32_t frame = pid / np, p = pid - frame * np;
                         if (A.fi.kx == 1 && A.fi.ky == 1) {
                             src = frame * A.fhw + p;
                         } else {
@@ -622,28 +648,45 @@ k_voxel_apply(const ApplyArgs A)
 #pragma unroll
             for (int q = 0; q < VEC; ++q) acc[it][q] = 0.f;
         bool any = false;
+        // away from the map border source s contributes exactly its slot 7 - s (the opposite corner)
+        const bool interior = v0 > 0 && v0 < A.g.S0 - 1 && v1 > 0 && v1 < A.g.S1 - 1 && v2 > 0 && v2 < A.g.S2 - 1;
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
             const uint32_t slo = __shfl_sync(FULL, lo, s), shi = __shfl_sync(FULL, hi, s);
             if (slo >= shi) continue;
             any = true;
+            if (interior) {
+                for (uint32_t e = slo; e < shi; ++e) {
+                    const float *prow = A.P + ((size_t)(e - A.run_base) * 8 + (7 - s)) * F;
+#pragma unroll
+                    for (int it = 0; it < IT; ++it) {
+                        const int ch = ch0 + it * 32 * VEC;
+                        if (ch < F) {
+                            float x[VEC];
+                            row_load<VEC>(x, prow + ch);
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) acc[it][q] += x[q];
+                        }
+                    }
+                }
+                continue;
+            }
             const uint32_t m = slot_mask(v0, v1, v2, s, A.g);
             for (uint32_t e = slo; e < shi; ++e) {
                 const float *prow = A.P + (size_t)(e - A.run_base) * 8 * F;
+                for (uint32_t mm = m; mm; mm &= mm - 1) {
+                    const int k = __ffs(mm) - 1;
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if ((m >> k) & 1u) {
+                    for (int it = 0; it < IT; ++it) {
+                        const int ch = ch0 + it * 32 * VEC;
+                        if (ch < F) {
+                            float x[VEC];
+                            row_load<VEC>(x, prow + (size_t)k * F + ch);
 #pragma unroll
-                        for (int it = 0; it < IT; ++it) {
-                            const int ch = ch0 + it * 32 * VEC;
-                            if (ch < F) {
-                                float x[VEC];
-                                row_load<VEC>(x, prow + (size_t)k * F + ch);
-#pragma unroll
-                                for (int q = 0; q < VEC; ++q) acc[it][q] += x[q];
-                            }
+                            for (int q = 0; q < VEC; ++q) acc[it][q] += x[q];
                         }
                     }
+                }
             }
         }
         if (A.run_base > 0 && !any) continue;
@@ -785,11 +828,11 @@ int dispatch_apply(cudaStream_t stream, const ApplyArgs &A, int vec, int it)
 // bytes per P run (8 rows of F floats)
 static size_t run_bytes(int F) { return (size_t)8 * F * sizeof(float); }
 
-// P budget asked for by default: room for min(worst case, one run per 16 pixels), at least 64 MB
+// P budget asked for by default: room for min(worst case, one run per 8 pixels), at least 64 MB
 static size_t default_P_bytes(uint32_t n, const CellGrid &g, int F)
 {
     const size_t worst = worst_runs(n, g) * run_bytes(F);
-    size_t want = ((size_t)n / 16 + 1024) * run_bytes(F);
+    size_t want = ((size_t)n / 8 + 1024) * run_bytes(F);
     if (want < ((size_t)64 << 20)) want = (size_t)64 << 20;
     return want < worst ? want : worst;
 }
@@ -859,27 +902,30 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
 
     // K1 + sort
     dim3 grid((npix + 255) / 256, (unsigned)T);
+    int pbits = 1;
+    while ((1u << pbits) < npix) ++pbits;
+    MB_REQUIRE(((uint64_t)(T - 1) << pbits) < 0xffffffffull, "frame too large for the packed (frame, pixel) sort value");
     k_cell_voxelise<<<grid, 256, 0, stream>>>(rays, depth, pose, npix, bins_x, nx, bins_y, ny, bins_z, nz, g, min_d,
-                                              max_d, b.rec, b.keys_a, b.counters);
+                                              max_d, b.rec, b.keys_a, b.pids_a, pbits, b.counters);
     MB_LAUNCHED();
     int bits = 1;
     while (bits < 32 && (((uint64_t)1) << bits) <= (uint64_t)g.invalid) ++bits;
-    uint32_t *skey, *spid;
-    int rc = mb_sort_pairs(stream, b.keys_a, b.pids_a, b.keys_b, b.pids_b, n, nullptr, bits, true, b.sort_ws,
-                           b.sort_bytes, &skey, &spid);
+    uint32_t *skey, *sval;
+    int rc = mb_sort_pairs(stream, b.keys_a, b.pids_a, b.keys_b, b.pids_b, n, nullptr, bits, false, b.sort_ws,
+                           b.sort_bytes, &skey, &sval);
     if (rc) return rc;
 
     // K2 + ranks
     MB_CHECK_CUDA(cudaMemsetAsync(b.bitmap, 0, (size_t)vwords * sizeof(uint32_t), stream));
     const unsigned nblk = (unsigned)(((size_t)words * 32 + 255) / 256);
-    k_cell_flags<<<nblk, 256, 0, stream>>>(skey, spid, n, npix, g.invalid, b.cmask, b.smask, b.ccnt, b.scnt, b.rcnt,
+    k_cell_flags<<<nblk, 256, 0, stream>>>(skey, sval, n, pbits, g.invalid, b.cmask, b.smask, b.ccnt, b.scnt, b.rcnt,
                                            b.counters);
     MB_LAUNCHED();
     if ((rc = mb_exclusive_scan_u32(stream, b.ccnt, b.coff, words, b.scan_ws, b.scan_bytes))) return rc;
     if ((rc = mb_exclusive_scan_u32(stream, b.scnt, b.soff, words, b.scan_ws, b.scan_bytes))) return rc;
     if ((rc = mb_exclusive_scan_u32(stream, b.rcnt, b.roff, words, b.scan_ws, b.scan_bytes))) return rc;
     // K3
-    k_cell_emit<<<(n + 255) / 256, 256, 0, stream>>>(skey, spid, n, npix, g, b.cmask, b.smask, b.coff, b.soff, b.roff,
+    k_cell_emit<<<(n + 255) / 256, 256, 0, stream>>>(skey, sval, n, pbits, g, b.cmask, b.smask, b.coff, b.soff, b.roff,
                                                      b.ucell, b.cstart, b.cseg, b.crun, b.seg_start, b.seg_frame,
                                                      b.bitmap, b.counters);
     MB_LAUNCHED();
@@ -890,7 +936,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     k_vox_emit<<<(vwords + 255) / 256, 256, 0, stream>>>(b.bitmap, b.voff, vwords, b.vlist, b.counters);
     MB_LAUNCHED();
     // K5, K6
-    k_seg_sums<<<MB_NUM_SMS * 8, 256, 0, stream>>>(spid, b.rec, b.seg_start, b.segws, b.counters);
+    k_seg_sums<<<MB_NUM_SMS * 8, 256, 0, stream>>>(sval, b.rec, b.seg_start, npix, pbits, b.segws, b.counters);
     MB_LAUNCHED();
     {
         const size_t smem = (size_t)8 * 2 * ((T + 31) & ~31) * sizeof(float);
@@ -904,7 +950,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     }
     // K7, K8 (one round unless the runs outgrow the P buffer)
     AccArgs A;
-    A.skey = skey; A.spid = spid; A.rec = b.rec; A.smask = b.smask; A.soff = b.soff; A.roff = b.roff;
+    A.skey = skey; A.sval = sval; A.pbits = pbits; A.rec = b.rec; A.smask = b.smask; A.soff = b.soff; A.roff = b.roff;
     A.gcoef = b.gcoef; A.counters = b.counters;
     A.fi = MbFeatIndex{ npix, (uint32_t)W, (uint32_t)(H / fh), (uint32_t)(W / fw), (uint32_t)fw };
     A.fhw = (uint32_t)fh * (uint32_t)fw;
