@@ -20,7 +20,8 @@
 //   K3  k_cell_emit       unique cell list, segment list, touched-voxel bitmap
 //   K4  k_vox_count/emit  ordered list of touched voxels
 //   K5  k_seg_sums        per segment and slot: W, S2                                  (scalars)
-//   K6  k_voxel_scalars   per touched voxel: backward merge of its <= 8 cells' segment lists ->
+//   K6a k_voxel_sources   per touched voxel: segment and run ranges of its <= 8 source cells
+//   K6  k_voxel_scalars   per touched voxel: per-frame W, S2 over its sources, backward product scan ->
 //                         coefficient g = (alpha / W_t) * prod_{s>t} a_s per (segment, slot), A = prod a
 //   K7  k_cell_accumulate per run of same-cell pixels: 8 rows P_k = sum_i w_ik^2 g_k f_i   (the hot loop)
 //   K8  k_voxel_apply     per touched voxel: map = A * map + sum over its cells' runs of P
@@ -117,9 +118,16 @@ k_cell_voxelise(const float *__restrict__ rays, const float *__restrict__ depth,
                 uint4 *__restrict__ rec, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, int pbits,
                 uint32_t *__restrict__ counters)
 {
-    __shared__ float P[12];
+    __shared__ float P[12], spacing[6];
     const uint32_t t = blockIdx.y;
     if (threadIdx.x < 12) P[threadIdx.x] = pose[(size_t)t * 12 + threadIdx.x];
+    if (threadIdx.x >= 32 && threadIdx.x < 35) {
+        const int a = threadIdx.x - 32;
+        const float *bb = a == 0 ? bins_x : a == 1 ? bins_y : bins_z;
+        const int nb = a == 0 ? nx : a == 1 ? ny : nz;
+        spacing[2 * a] = __ldg(bb);
+        spacing[2 * a + 1] = bins_scale(bb, nb);
+    }
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < MB_NUM_COUNTERS) counters[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -127,8 +135,8 @@ k_cell_voxelise(const float *__restrict__ rays, const float *__restrict__ depth,
     const size_t pid = (size_t)t * npix + p;
     float r0, r1, r2;
     orient(P, rays[3 * (size_t)p], rays[3 * (size_t)p + 1], rays[3 * (size_t)p + 2], r0, r1, r2);
-    const BinResult b = bin_point(bins_x, nx, bins_y, ny, bins_z, nz, P[9], P[10], P[11], r0, r1, r2,
-                                  depth[pid], min_d, max_d);
+    const BinResult b = bin_point_fast(bins_x, nx, bins_y, ny, bins_z, nz, spacing, P[9], P[10], P[11], r0, r1, r2,
+                                       depth[pid], min_d, max_d);
     uint4 out = make_uint4(g.invalid, 0u, 0u, 0u);
     if (b.ok) {
         // map axes are (y flipped, x, z) = input axes (1, 0, 2): base_projection_layer.py:339
@@ -180,7 +188,7 @@ k_cell_emit(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sval
             const uint32_t *__restrict__ coff, const uint32_t *__restrict__ soff, const uint32_t *__restrict__ roff,
             uint32_t *__restrict__ ucell, uint32_t *__restrict__ cstart, uint32_t *__restrict__ cseg,
             uint32_t *__restrict__ crun, uint32_t *__restrict__ seg_start, uint32_t *__restrict__ seg_frame,
-            uint32_t *__restrict__ bitmap, uint32_t *__restrict__ counters)
+            uint32_t *__restrict__ bitmap, int *__restrict__ ctab, uint32_t *__restrict__ counters)
 {
     const uint32_t nvalid = counters[MB_CNT_NVALID];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -207,6 +215,7 @@ k_cell_emit(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sval
                 rr += __popc(rm & lt);
             }
             ucell[crank] = key;
+            if (ctab != nullptr) ctab[key] = (int)crank;
             cstart[crank] = i;
             cseg[crank] = srank;
             crun[crank] = rr;
@@ -268,7 +277,7 @@ k_vox_emit(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ vof
 // segment; four records are requested before the first is used (segments average ~6 pixels).
 __global__ void __launch_bounds__(256)
 k_seg_sums(const uint32_t *__restrict__ sval, const uint4 *__restrict__ rec, const uint32_t *__restrict__ seg_start,
-           uint32_t npix, int pbits, float2 *__restrict__ segws, const uint32_t *__restrict__ counters)
+           uint32_t npix, int pbits, float2 *__restrict__ segws, size_t cap, const uint32_t *__restrict__ counters)
 {
     const uint32_t nsegs = counters[MB_CNT_SEGS];
     const uint32_t pmask = (1u << pbits) - 1u;
@@ -294,62 +303,122 @@ k_seg_sums(const uint32_t *__restrict__ sval, const uint4 *__restrict__ rec, con
                     for (int k = 0; k < 8; ++k) { W[k] += w[k]; S2[k] = fmaf(w[k], w[k], S2[k]); }
                 }
         }
-        float4 *o = (float4 *)(segws + (size_t)s * 8);
 #pragma unroll
-        for (int k = 0; k < 8; k += 2) o[k >> 1] = make_float4(W[k], S2[k], W[k + 1], S2[k + 1]);
+        for (int k = 0; k < 8; ++k) segws[(size_t)k * cap + s] = make_float2(W[k], S2[k]);    // slot-major
     }
 }
 
-// K6: one warp per touched voxel.  Its contributions come from the <= 8 cells at extended coordinates
-// v + {0,1}^3; each cell's segments are sorted by frame, one segment per frame.  The warp adds the W / S2
-// sums of all sources into a per-frame table in shared memory (sources one after the other, so the
-// order of the adds is fixed), turns every touched frame into a = 1 - alpha*S2/W and r = alpha/W, and runs
-// a backward product scan over the frames: g(t) = r(t) * prod_{s>t} a(s) is the coefficient of every
-// contribution of frame t to this voxel, A = prod a multiplies the old row.
+// K6a: one thread per (touched voxel, source cell): the <= 8 cells at extended coordinates v + {0,1}^3
+// contribute to voxel v.  Looks each one up and records its segment range (for K6) and run range (for K8).
 __global__ void __launch_bounds__(256)
-k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__ ucell, const uint32_t *__restrict__ cseg,
-                const uint32_t *__restrict__ seg_frame, const float2 *__restrict__ segws, CellGrid g, float alpha, int T,
-                float *__restrict__ gcoef, float *__restrict__ vA, int *__restrict__ vsrc,
-                const uint32_t *__restrict__ counters)
+k_voxel_sources(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__ ucell, const int *__restrict__ ctab,
+                const uint32_t *__restrict__ cseg, const uint32_t *__restrict__ crun, CellGrid g,
+                uint2 *__restrict__ vseg, uint2 *__restrict__ vrun, const uint32_t *__restrict__ counters)
+{
+    const uint32_t nvox = counters[MB_CNT_VOX], ncells = counters[MB_CNT_CELLS];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvox * 8u; i += gridDim.x * blockDim.x) {
+        const uint32_t v = vlist[i >> 3];
+        const int s = (int)(i & 7u);
+        const int v2 = (int)(v % (uint32_t)g.S2);
+        const uint32_t t01 = v / (uint32_t)g.S2;
+        const int v1 = (int)(t01 % (uint32_t)g.S1), v0 = (int)(t01 / (uint32_t)g.S1);
+        const uint32_t key = cell_key(g, v0 + ((s >> 2) & 1), v1 + ((s >> 1) & 1), v2 + (s & 1));
+        const int u = ctab != nullptr ? ctab[key] : find_cell(ucell, ncells, key);
+        uint2 sr = make_uint2(0u, 0u), rr = make_uint2(0u, 0u);
+        if (u >= 0) {
+            sr = make_uint2(cseg[u], cseg[u + 1]);
+            rr = make_uint2(crun[u], crun[u + 1]);
+        }
+        vseg[i] = sr;
+        vrun[i] = rr;
+    }
+}
+
+// K6: one warp per touched voxel.  Each source cell's segments are sorted by frame, one segment per
+// frame.  The warp adds the W / S2 sums of all sources into a per-frame table in shared memory (sources
+// one after the other, so the order of the adds is fixed), turns every touched frame into
+// a = 1 - alpha*S2/W and r = alpha/W, and runs a backward product scan over the frames:
+// g(t) = r(t) * prod_{s>t} a(s) is the coefficient of every contribution of frame t to this voxel,
+// A = prod a multiplies the old row.  All list loads of a 64-segment block are issued before the first
+// is used: the kernel lives on memory-level parallelism.
+__global__ void __launch_bounds__(256)
+k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vseg, const uint32_t *__restrict__ seg_frame,
+                const float2 *__restrict__ segws, size_t cap, CellGrid g, float alpha, int T,
+                float *__restrict__ gcoef, float *__restrict__ vA, const uint32_t *__restrict__ counters)
 {
     extern __shared__ float s_tab[];                  // [warps][2][Tp]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Tp = (T + 31) & ~31;
     float *tW = s_tab + (size_t)warp * 2 * Tp, *tS = tW + Tp;
-    const uint32_t nvox = counters[MB_CNT_VOX], ncells = counters[MB_CNT_CELLS];
+    const uint32_t nvox = counters[MB_CNT_VOX];
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (int f = lane; f < Tp; f += 32) { tW[f] = 0.f; tS[f] = 0.f; }
     __syncwarp();
     for (uint32_t j = wid; j < nvox; j += nw) {
         const uint32_t v = vlist[j];
+        uint2 mine = make_uint2(0u, 0u);
+        if (lane < 8) mine = vseg[(size_t)j * 8 + lane];
         const int v2 = (int)(v % (uint32_t)g.S2);
         const uint32_t t01 = v / (uint32_t)g.S2;
         const int v1 = (int)(t01 % (uint32_t)g.S1), v0 = (int)(t01 / (uint32_t)g.S1);
-        uint32_t lo = 0, hi = 0;
-        if (lane < 8) {
-            const int u = find_cell(ucell, ncells, cell_key(g, v0 + ((lane >> 2) & 1), v1 + ((lane >> 1) & 1), v2 + (lane & 1)));
-            if (u >= 0) { lo = cseg[u]; hi = cseg[u + 1]; }
-            vsrc[(size_t)j * 8 + lane] = u;
+        // away from the map border source s contributes exactly its slot 7 - s (the opposite corner)
+        const bool interior = v0 > 0 && v0 < g.S0 - 1 && v1 > 0 && v1 < g.S1 - 1 && v2 > 0 && v2 < g.S2 - 1;
+        uint32_t slo[8], shi[8];
+        uint32_t maxlen = 0;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            slo[s] = __shfl_sync(FULL, mine.x, s);
+            shi[s] = __shfl_sync(FULL, mine.y, s);
+            maxlen = max(maxlen, shi[s] - slo[s]);
         }
         // the tables are all zero here (zeroed once per warp, and again row by row after use)
         uint32_t rows = 0;                             // 32-frame rows with at least one touched frame
+        if (interior) {
+            for (uint32_t off = 0; off < maxlen; off += 64) {
+                uint32_t f[8][2];
+                float2 x[8][2];
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            const uint32_t slo = __shfl_sync(FULL, lo, s), shi = __shfl_sync(FULL, hi, s);
-            if (slo >= shi) continue;
-            const uint32_t m = slot_mask(v0, v1, v2, s, g);
-            for (uint32_t q = slo + lane; q < shi; q += 32) {
-                const uint32_t f = seg_frame[q];
-                const float2 *ws = segws + (size_t)q * 8;
-                float W = 0.f, S2 = 0.f;
+                for (int s = 0; s < 8; ++s)
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if ((m >> k) & 1u) { const float2 x = ws[k]; W += x.x; S2 += x.y; }
-                tW[f] += W;                            // one segment per frame and source: no two lanes share f
-                tS[f] += S2;
-                rows |= 1u << (f >> 5);
+                    for (int it = 0; it < 2; ++it) {
+                        const uint32_t q = slo[s] + off + it * 32 + lane;
+                        f[s][it] = 0xffffffffu;
+                        if (q < shi[s]) {
+                            f[s][it] = __ldg(seg_frame + q);
+                            x[s][it] = __ldg(segws + (size_t)(7 - s) * cap + q);
+                        }
+                    }
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+#pragma unroll
+                    for (int it = 0; it < 2; ++it)
+                        if (f[s][it] != 0xffffffffu) {
+                            tW[f[s][it]] += x[s][it].x;    // one segment per frame and source: no two lanes share f
+                            tS[f[s][it]] += x[s][it].y;
+                            rows |= 1u << (f[s][it] >> 5);
+                        }
+                    __syncwarp();
+                }
             }
-            __syncwarp();
+        } else {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                if (slo[s] >= shi[s]) continue;
+                const uint32_t m = slot_mask(v0, v1, v2, s, g);
+                for (uint32_t q = slo[s] + lane; q < shi[s]; q += 32) {
+                    const uint32_t f = seg_frame[q];
+                    float W = 0.f, S2 = 0.f;
+                    for (uint32_t mm = m; mm; mm &= mm - 1) {
+                        const float2 x = segws[(size_t)(__ffs(mm) - 1) * cap + q];
+                        W += x.x;
+                        S2 += x.y;
+                    }
+                    tW[f] += W;
+                    tS[f] += S2;
+                    rows |= 1u << (f >> 5);
+                }
+                __syncwarp();
+            }
         }
         rows = __reduce_or_sync(FULL, rows);
         // backward product scan over the touched rows (an untouched row has a = 1 everywhere)
@@ -374,17 +443,32 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__
             carry *= __shfl_sync(FULL, inc, 0);
         }
         __syncwarp();
+        if (interior) {
+            for (uint32_t off = 0; off < maxlen; off += 64) {
+                uint32_t f[8][2];
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            const uint32_t slo = __shfl_sync(FULL, lo, s), shi = __shfl_sync(FULL, hi, s);
-            if (slo >= shi) continue;
-            const uint32_t m = slot_mask(v0, v1, v2, s, g);
-            for (uint32_t q = slo + lane; q < shi; q += 32) {
-                const float gv = tW[seg_frame[q]];
-                float *go = gcoef + (size_t)q * 8;
+                for (int s = 0; s < 8; ++s)
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if ((m >> k) & 1u) go[k] = gv;
+                    for (int it = 0; it < 2; ++it) {
+                        const uint32_t q = slo[s] + off + it * 32 + lane;
+                        f[s][it] = q < shi[s] ? __ldg(seg_frame + q) : 0xffffffffu;
+                    }
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+#pragma unroll
+                    for (int it = 0; it < 2; ++it)
+                        if (f[s][it] != 0xffffffffu)
+                            gcoef[(size_t)(7 - s) * cap + (slo[s] + off + it * 32 + lane)] = tW[f[s][it]];
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                if (slo[s] >= shi[s]) continue;
+                const uint32_t m = slot_mask(v0, v1, v2, s, g);
+                for (uint32_t q = slo[s] + lane; q < shi[s]; q += 32) {
+                    const float gv = tW[seg_frame[q]];
+                    for (uint32_t mm = m; mm; mm &= mm - 1) gcoef[(size_t)(__ffs(mm) - 1) * cap + q] = gv;
+                }
             }
         }
         __syncwarp();
@@ -405,7 +489,8 @@ struct AccArgs {
     int pbits;
     const uint4 *rec;
     const uint32_t *smask, *soff, *roff;
-    const float *gcoef;
+    const float *gcoef;         // [8 slots][cap] coefficient per (slot, segment)
+    size_t cap;
     const uint32_t *counters;
     MbFeatIndex fi;             // np = pixels per frame
     uint32_t fhw;               // feature rows per frame
@@ -507,11 +592,12 @@ k_cell_accumulate(const AccArgs A)
                     const uint32_t w = i >> 5;
                     const uint32_t s = A.soff[w] + __popc(A.smask[w] & lemask) - 1u;
                     const uint4 r = __ldg(A.rec + pid);
-                    const float4 g0 = __ldg((const float4 *)(A.gcoef + (size_t)s * 8));
-                    const float4 g1 = __ldg((const float4 *)(A.gcoef + (size_t)s * 8 + 4));
+                    float gk[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) gk[k] = __ldg(A.gcoef + (size_t)k * A.cap + s);
                     splat_weights(r, c);
-                    c[0] = c[0] * c[0] * g0.x; c[1] = c[1] * c[1] * g0.y; c[2] = c[2] * c[2] * g0.z; c[3] = c[3] * c[3] * g0.w;
-                    c[4] = c[4] * c[4] * g1.x; c[5] = c[5] * c[5] * g1.y; c[6] = c[6] * c[6] * g1.z; c[7] = c[7] * c[7] * g1.w;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) c[k] = c[k] * c[k] * gk[k];
                     if (ONEHOT) {
                         src = (uint32_t)A.class_ids[pid];
                     } else {
@@ -606,10 +692,11 @@ k_cell_accumulate(const AccArgs A)
 }
 
 // K8: one warp per touched voxel: map = A * map + sum of the P rows of its cells' runs (round 0), or
-// map += sum (later rounds, when the runs did not fit one P buffer).
+// map += sum (later rounds, when the runs did not fit one P buffer).  The old row and the first two P
+// rows of every source are requested before anything is added.
 struct ApplyArgs {
-    const uint32_t *vlist, *crun;
-    const int *vsrc;            // [voxel][8] unique-cell index of each source cell, or -1 (from K6)
+    const uint32_t *vlist;
+    const uint2 *vrun;          // [voxel][8] run range of each source cell (from K6a)
     const float *vA, *P;
     const uint32_t *counters;
     CellGrid g;
@@ -631,78 +718,112 @@ k_voxel_apply(const ApplyArgs A)
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t j = wid; j < nvox; j += nw) {
         const uint32_t v = A.vlist[j];
+        uint32_t lo = 0, hi = 0;
+        if (lane < 8) {
+            const uint2 rr = A.vrun[(size_t)j * 8 + lane];
+            lo = max(rr.x, A.run_base);
+            hi = min(rr.y, run_end);
+        }
+        const float a = A.run_base == 0 ? A.vA[j] : 1.0f;
+        float *grow = A.map + (size_t)v * F;
+        float old[IT][VEC];
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int ch = ch0 + it * 32 * VEC;
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) old[it][q] = 0.f;
+            if (ch < F) {
+                if (VEC == 1) old[it][0] = grow[ch];
+                if (VEC == 2) { const float2 o = *(const float2 *)(grow + ch); old[it][0] = o.x; old[it][VEC > 1 ? 1 : 0] = o.y; }
+                if (VEC == 4) { const float4 o = *(const float4 *)(grow + ch); old[it][0] = o.x; old[it][VEC > 1 ? 1 : 0] = o.y; old[it][VEC > 2 ? 2 : 0] = o.z; old[it][VEC > 2 ? 3 : 0] = o.w; }
+            }
+        }
         const int v2 = (int)(v % (uint32_t)A.g.S2);
         const uint32_t t01 = v / (uint32_t)A.g.S2;
         const int v1 = (int)(t01 % (uint32_t)A.g.S1), v0 = (int)(t01 / (uint32_t)A.g.S1);
-        uint32_t lo = 0, hi = 0;
-        if (lane < 8) {
-            const int u = A.vsrc[(size_t)j * 8 + lane];
-            if (u >= 0) {
-                lo = max(A.crun[u], A.run_base);
-                hi = min(A.crun[u + 1], run_end);
-            }
-        }
+        // away from the map border source s contributes exactly its slot 7 - s (the opposite corner)
+        const bool interior = v0 > 0 && v0 < A.g.S0 - 1 && v1 > 0 && v1 < A.g.S1 - 1 && v2 > 0 && v2 < A.g.S2 - 1;
         float acc[IT][VEC];
 #pragma unroll
         for (int it = 0; it < IT; ++it)
 #pragma unroll
             for (int q = 0; q < VEC; ++q) acc[it][q] = 0.f;
+        uint32_t slo[8], shi[8];
         bool any = false;
-        // away from the map border source s contributes exactly its slot 7 - s (the opposite corner)
-        const bool interior = v0 > 0 && v0 < A.g.S0 - 1 && v1 > 0 && v1 < A.g.S1 - 1 && v2 > 0 && v2 < A.g.S2 - 1;
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
-            const uint32_t slo = __shfl_sync(FULL, lo, s), shi = __shfl_sync(FULL, hi, s);
-            if (slo >= shi) continue;
-            any = true;
-            if (interior) {
-                for (uint32_t e = slo; e < shi; ++e) {
+            slo[s] = __shfl_sync(FULL, lo, s);
+            shi[s] = __shfl_sync(FULL, hi, s);
+            any = any || slo[s] < shi[s];
+        }
+        if (A.run_base > 0 && !any) continue;
+        if (interior) {
+            // first two runs of every source: 16 independent row loads
+            float x[8][2][IT][VEC];
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int it = 0; it < IT; ++it) {
+                        const int ch = ch0 + it * 32 * VEC;
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) x[s][r][it][q] = 0.f;
+                        if (slo[s] + r < shi[s] && ch < F)
+                            row_load<VEC>(x[s][r][it], A.P + ((size_t)(slo[s] + r - A.run_base) * 8 + (7 - s)) * F + ch);
+                    }
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int it = 0; it < IT; ++it)
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) acc[it][q] += x[s][r][it][q];
+                for (uint32_t e = slo[s] + 2; e < shi[s]; ++e) {
                     const float *prow = A.P + ((size_t)(e - A.run_base) * 8 + (7 - s)) * F;
 #pragma unroll
                     for (int it = 0; it < IT; ++it) {
                         const int ch = ch0 + it * 32 * VEC;
                         if (ch < F) {
-                            float x[VEC];
-                            row_load<VEC>(x, prow + ch);
+                            float y[VEC];
+                            row_load<VEC>(y, prow + ch);
 #pragma unroll
-                            for (int q = 0; q < VEC; ++q) acc[it][q] += x[q];
+                            for (int q = 0; q < VEC; ++q) acc[it][q] += y[q];
                         }
                     }
                 }
-                continue;
             }
-            const uint32_t m = slot_mask(v0, v1, v2, s, A.g);
-            for (uint32_t e = slo; e < shi; ++e) {
-                const float *prow = A.P + (size_t)(e - A.run_base) * 8 * F;
-                for (uint32_t mm = m; mm; mm &= mm - 1) {
-                    const int k = __ffs(mm) - 1;
+        } else {
 #pragma unroll
-                    for (int it = 0; it < IT; ++it) {
-                        const int ch = ch0 + it * 32 * VEC;
-                        if (ch < F) {
-                            float x[VEC];
-                            row_load<VEC>(x, prow + (size_t)k * F + ch);
+            for (int s = 0; s < 8; ++s) {
+                if (slo[s] >= shi[s]) continue;
+                const uint32_t m = slot_mask(v0, v1, v2, s, A.g);
+                for (uint32_t e = slo[s]; e < shi[s]; ++e) {
+                    const float *prow = A.P + (size_t)(e - A.run_base) * 8 * F;
+                    for (uint32_t mm = m; mm; mm &= mm - 1) {
+                        const int k = __ffs(mm) - 1;
 #pragma unroll
-                            for (int q = 0; q < VEC; ++q) acc[it][q] += x[q];
+                        for (int it = 0; it < IT; ++it) {
+                            const int ch = ch0 + it * 32 * VEC;
+                            if (ch < F) {
+                                float y[VEC];
+                                row_load<VEC>(y, prow + (size_t)k * F + ch);
+#pragma unroll
+                                for (int q = 0; q < VEC; ++q) acc[it][q] += y[q];
+                            }
                         }
                     }
                 }
             }
         }
-        if (A.run_base > 0 && !any) continue;
-        const float a = A.run_base == 0 ? A.vA[j] : 1.0f;
-        float *grow = A.map + (size_t)v * F;
 #pragma unroll
         for (int it = 0; it < IT; ++it) {
             const int ch = ch0 + it * 32 * VEC;
             if (ch < F) {
-                float old[VEC];
-                if (VEC == 1) old[0] = grow[ch];
-                if (VEC == 2) { const float2 o = *(const float2 *)(grow + ch); old[0] = o.x; old[VEC > 1 ? 1 : 0] = o.y; }
-                if (VEC == 4) { const float4 o = *(const float4 *)(grow + ch); old[0] = o.x; old[VEC > 1 ? 1 : 0] = o.y; old[VEC > 2 ? 2 : 0] = o.z; old[VEC > 2 ? 3 : 0] = o.w; }
 #pragma unroll
-                for (int q = 0; q < VEC; ++q) old[q] = fmaf(a, old[q], acc[it][q]);
-                row_store<VEC>(grow + ch, old);
+                for (int q = 0; q < VEC; ++q) old[it][q] = fmaf(a, old[it][q], acc[it][q]);
+                row_store<VEC>(grow + ch, old[it]);
             }
         }
         if (A.affine_a != nullptr && A.run_base == 0 && blockIdx.y == 0 && lane == 0) A.affine_a[v] = A.affine_a[v] * a;
@@ -720,7 +841,8 @@ struct CellBuffers {
     float *gcoef;
     uint32_t *bitmap, *vcnt, *voff, *vlist;
     float *vA;
-    int *vsrc;
+    uint2 *vseg, *vrun;
+    int *ctab;                  // dense cell key -> unique cell index (or null: binary search)
     char *scan_ws, *sort_ws;
     size_t scan_bytes, sort_bytes;
     float *P;
@@ -750,7 +872,16 @@ size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const Cel
     b.bitmap = a.take<uint32_t>(vwords); b.vcnt = a.take<uint32_t>(vwords); b.voff = a.take<uint32_t>(vwords);
     b.vlist = a.take<uint32_t>(vcap + 1);
     b.vA = a.take<float>(vcap + 1);
-    b.vsrc = a.take<int>((vcap + 1) * 8);
+    b.vseg = a.take<uint2>((vcap + 1) * 8);
+    b.vrun = a.take<uint2>((vcap + 1) * 8);
+    {
+        // dense lookup table over the extended grid when it is not out of proportion to the batch
+        size_t budget = (size_t)32 * n;
+        if (budget < ((size_t)64 << 20)) budget = (size_t)64 << 20;
+        const bool dense = (size_t)g.invalid * sizeof(int) <= budget;
+        b.ctab = dense ? a.take<int>((size_t)g.invalid) : nullptr;
+        if (!dense) b.ctab = nullptr;
+    }
     const size_t scan_n = words > vwords ? words : vwords;
     b.scan_bytes = mb_scan_workspace_bytes((uint32_t)scan_n);
     b.scan_ws = a.take<char>(b.scan_bytes);
@@ -917,6 +1048,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
 
     // K2 + ranks
     MB_CHECK_CUDA(cudaMemsetAsync(b.bitmap, 0, (size_t)vwords * sizeof(uint32_t), stream));
+    if (b.ctab) MB_CHECK_CUDA(cudaMemsetAsync(b.ctab, 0xff, (size_t)g.invalid * sizeof(int), stream));
     const unsigned nblk = (unsigned)(((size_t)words * 32 + 255) / 256);
     k_cell_flags<<<nblk, 256, 0, stream>>>(skey, sval, n, pbits, g.invalid, b.cmask, b.smask, b.ccnt, b.scnt, b.rcnt,
                                            b.counters);
@@ -927,7 +1059,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     // K3
     k_cell_emit<<<(n + 255) / 256, 256, 0, stream>>>(skey, sval, n, pbits, g, b.cmask, b.smask, b.coff, b.soff, b.roff,
                                                      b.ucell, b.cstart, b.cseg, b.crun, b.seg_start, b.seg_frame,
-                                                     b.bitmap, b.counters);
+                                                     b.bitmap, b.ctab, b.counters);
     MB_LAUNCHED();
     // K4
     k_vox_count<<<(vwords + 255) / 256, 256, 0, stream>>>(b.bitmap, vwords, b.vcnt);
@@ -936,7 +1068,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     k_vox_emit<<<(vwords + 255) / 256, 256, 0, stream>>>(b.bitmap, b.voff, vwords, b.vlist, b.counters);
     MB_LAUNCHED();
     // K5, K6
-    k_seg_sums<<<MB_NUM_SMS * 8, 256, 0, stream>>>(sval, b.rec, b.seg_start, npix, pbits, b.segws, b.counters);
+    k_seg_sums<<<MB_NUM_SMS * 8, 256, 0, stream>>>(sval, b.rec, b.seg_start, npix, pbits, b.segws, (size_t)n, b.counters);
     MB_LAUNCHED();
     {
         const size_t smem = (size_t)8 * 2 * ((T + 31) & ~31) * sizeof(float);
@@ -944,19 +1076,22 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
         int per_sm = 1;
         MB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_voxel_scalars, 256, smem));
         if (per_sm < 1) per_sm = 1;
-        k_voxel_scalars<<<MB_NUM_SMS * per_sm, 256, smem, stream>>>(b.vlist, b.ucell, b.cseg, b.seg_frame, b.segws, g,
-                                                                    alpha, T, b.gcoef, b.vA, b.vsrc, b.counters);
+        k_voxel_sources<<<MB_NUM_SMS * 8, 256, 0, stream>>>(b.vlist, b.ucell, b.ctab, b.cseg, b.crun, g, b.vseg, b.vrun,
+                                                            b.counters);
+        MB_LAUNCHED();
+        k_voxel_scalars<<<MB_NUM_SMS * per_sm, 256, smem, stream>>>(b.vlist, b.vseg, b.seg_frame, b.segws, (size_t)n, g, alpha, T,
+                                                                    b.gcoef, b.vA, b.counters);
         MB_LAUNCHED();
     }
     // K7, K8 (one round unless the runs outgrow the P buffer)
     AccArgs A;
     A.skey = skey; A.sval = sval; A.pbits = pbits; A.rec = b.rec; A.smask = b.smask; A.soff = b.soff; A.roff = b.roff;
-    A.gcoef = b.gcoef; A.counters = b.counters;
+    A.gcoef = b.gcoef; A.cap = (size_t)n; A.counters = b.counters;
     A.fi = MbFeatIndex{ npix, (uint32_t)W, (uint32_t)(H / fh), (uint32_t)(W / fw), (uint32_t)fw };
     A.fhw = (uint32_t)fh * (uint32_t)fw;
     A.features = features; A.class_ids = class_ids; A.F = F; A.P = b.P; A.run_cap = run_cap;
     ApplyArgs Y;
-    Y.vlist = b.vlist; Y.vsrc = b.vsrc; Y.crun = b.crun; Y.vA = b.vA; Y.P = b.P; Y.counters = b.counters;
+    Y.vlist = b.vlist; Y.vrun = b.vrun; Y.vA = b.vA; Y.P = b.P; Y.counters = b.counters;
     Y.g = g; Y.F = F; Y.map = map; Y.affine_a = affine_a; Y.run_cap = run_cap;
     for (int r = 0; r < rounds; ++r) {
         A.run_base = Y.run_base = (uint32_t)r * run_cap;

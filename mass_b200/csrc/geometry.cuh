@@ -66,6 +66,67 @@ __device__ __forceinline__ BinResult bin_point(const float *__restrict__ bins0, 
     return b;
 }
 
+// Same search with the table spacing precomputed by the caller (b0 = bins[0], scale = (n-1) / (bins[n-1] - b0))
+// and the two edges around the answer returned, so the ratio needs no further loads.
+struct Bucket { int i; float lo, hi; };
+
+__device__ __forceinline__ Bucket bucket_right_edges(const float *__restrict__ bins, int n, float x, float b0, float scale)
+{
+    Bucket r;
+    r.lo = r.hi = 0.f;
+    if (x != x) { r.i = n - 1; return r; }          // NaN: ATen's upper bound runs off the end
+    if (!(x >= b0)) { r.i = -1; return r; }
+    const float g = (x - b0) * scale;
+    int i = g >= (float)(n - 2) ? n - 2 : (int)g;
+    if (i < 0) i = 0;
+    float lo = __ldg(bins + i), hi = __ldg(bins + i + 1);
+    while (x >= hi) {
+        if (++i >= n - 1) { r.i = n - 1; return r; }
+        lo = hi;
+        hi = __ldg(bins + i + 1);
+    }
+    while (x < lo) {                                 // x >= bins[0], so i stays >= 0
+        --i;
+        hi = lo;
+        lo = __ldg(bins + i);
+    }
+    r.i = i; r.lo = lo; r.hi = hi;
+    return r;
+}
+
+// table spacing helpers: call once per axis (per CTA), keep in shared memory
+__device__ __forceinline__ float bins_scale(const float *__restrict__ bins, int n)
+{
+    return (float)(n - 1) / (__ldg(bins + n - 1) - __ldg(bins));
+}
+
+// bin_point with precomputed spacing: spacing = {b0_x, scale_x, b0_y, scale_y, b0_z, scale_z}
+__device__ __forceinline__ BinResult bin_point_fast(const float *__restrict__ bins0, int n0,
+                                                    const float *__restrict__ bins1, int n1,
+                                                    const float *__restrict__ bins2, int n2,
+                                                    const float *__restrict__ spacing, float o0, float o1, float o2,
+                                                    float r0, float r1, float r2, float d, float min_d, float max_d)
+{
+    BinResult b;
+    const float x0 = __fadd_rn(o0, __fmul_rn(r0, d));
+    const float x1 = __fadd_rn(o1, __fmul_rn(r1, d));
+    const float x2 = __fadd_rn(o2, __fmul_rn(r2, d));
+    const Bucket k0 = bucket_right_edges(bins0, n0, x0, spacing[0], spacing[1]);
+    const Bucket k1 = bucket_right_edges(bins1, n1, x1, spacing[2], spacing[3]);
+    const Bucket k2 = bucket_right_edges(bins2, n2, x2, spacing[4], spacing[5]);
+    b.ok = (d >= min_d) && (d <= max_d) && k0.i >= 0 && k0.i < n0 - 1 && k1.i >= 0 && k1.i < n1 - 1 &&
+           k2.i >= 0 && k2.i < n2 - 1;
+    b.i0 = k0.i; b.i1 = k1.i; b.i2 = k2.i;
+    b.q0 = b.q1 = b.q2 = 0.f;
+    if (b.ok) {
+        b.q0 = __fdiv_rn(__fsub_rn(x0, k0.lo), __fsub_rn(k0.hi, k0.lo));
+        b.q1 = __fsub_rn(1.0f, __fdiv_rn(__fsub_rn(x1, k1.lo), __fsub_rn(k1.hi, k1.lo)));
+        b.q2 = __fdiv_rn(__fsub_rn(x2, k2.lo), __fsub_rn(k2.hi, k2.lo));
+        b.i1 = n1 - 2 - k1.i;
+    }
+    return b;
+}
+
 __device__ __forceinline__ void orient(const float *__restrict__ R, float a, float b, float c, float &o0,
                                        float &o1, float &o2)
 {

@@ -4,15 +4,12 @@
 // reproduce the reference's summation order (slot-major, then pixel order:
 // /root/reference/mass/utils/projection.py:294-298, 319-323, 349-351) without float atomics.
 //
-// One pass = per-tile digit histogram -> exclusive scan over (digit, tile) -> stable scatter.
-// A tile is 2048 (8-bit digits) or 4096 (9-bit digits) elements; inside a tile each warp owns 256
-// consecutive elements and ranks them in 8 rounds of 32 with match.any, so the order
+// 8-bit digits, one sweep over the data per pass (see k_radix_onesweep below).  Inside a tile each warp
+// owns 512 consecutive elements and ranks them in 16 rounds of 32 with match.any, so the order
 // (tile, warp, round, lane) is the input order.
 #include "common.cuh"
 
 namespace {
-
-constexpr int SORT_ITEMS = 8;      // keys per thread and pass
 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
@@ -104,54 +101,104 @@ k_scan_apply(const uint32_t *in, uint32_t *out, uint32_t n, const uint32_t *__re
 }
 
 // ---------------------------------------------------------------------------------------------
-// radix pass, BITS bits per digit with one thread per digit (256 or 512 threads per CTA).
-// n_dev (optional) overrides n with a count produced on the device; the grid is sized for the
-// host-side upper bound n and tiles past the device count write empty histograms.
-template <int BITS>
-__global__ void __launch_bounds__(1 << BITS)
-k_radix_hist(const uint32_t *__restrict__ keys, uint32_t n, const uint32_t *__restrict__ n_dev, int shift,
-             uint32_t *__restrict__ tile_hist, uint32_t ntiles)
+// Radix sort, 8 bits per pass, one sweep over the data per pass ("onesweep"):
+//   k_radix_hist_all   one read of the keys -> global digit histograms of ALL passes
+//   k_radix_bases      exclusive scan of each pass's 256 counts
+//   k_radix_onesweep   per pass: a tile of 4096 pairs is ranked inside the CTA (match.any per warp round,
+//                      per-warp digit counters), the tile's position inside every digit comes from a
+//                      decoupled look-back over the preceding tiles' digit counts (tiles take their index
+//                      from a ticket, so a tile only ever waits for tiles that started before it), the
+//                      pairs are staged through shared memory in sorted order and written out coalesced.
+// Stable: the global order inside a digit is (tile, warp, round, lane) = the input order.
+constexpr int OS_ITEMS = 16;
+constexpr int OS_THREADS = 256;
+constexpr int OS_TILE = OS_THREADS * OS_ITEMS;
+constexpr uint32_t OS_FLAG_AGG = 1u << 30, OS_FLAG_PREFIX = 2u << 30, OS_VALUE_MASK = (1u << 30) - 1u;
+
+// Each thread takes 16 consecutive keys and merges runs of equal digits before touching the shared
+// histogram: neighbouring keys mostly share their digits (neighbouring pixels fall into the same cell),
+// and the lanes of a warp are 16 keys apart, so same-address conflicts are rare.
+__global__ void __launch_bounds__(256)
+k_radix_hist_all(const uint32_t *__restrict__ keys, uint32_t n, int passes, uint32_t *__restrict__ ghist)
 {
-    constexpr int R = 1 << BITS, TILE = R * SORT_ITEMS;
-    __shared__ uint32_t h[R];
-    if (n_dev) n = min(n, *n_dev);
-    h[threadIdx.x] = 0;
+    __shared__ uint32_t h[4][256];
+    for (int i = threadIdx.x; i < 4 * 256; i += 256) (&h[0][0])[i] = 0;
     __syncthreads();
-    const uint32_t base = blockIdx.x * TILE;
-    if (base < n) {
+    const uint32_t ngroups = (n + 15u) / 16u;
+    for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += gridDim.x * blockDim.x) {
+        uint32_t k[16];
+        const uint32_t base = gi * 16u;
+        if (base + 16u <= n) {
+            const uint4 *p = (const uint4 *)(keys + base);
 #pragma unroll
-        for (int i = 0; i < SORT_ITEMS; ++i) {
-            uint32_t idx = base + i * R + threadIdx.x;
-            if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & (R - 1)], 1u);
+            for (int q = 0; q < 4; ++q) {
+                const uint4 v = __ldg(p + q);
+                k[4 * q] = v.x; k[4 * q + 1] = v.y; k[4 * q + 2] = v.z; k[4 * q + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) k[q] = base + q < n ? keys[base + q] : 0xffffffffu;
+        }
+        const int cnt = (int)min(16u, n - base);
+        for (int p = 0; p < passes; ++p) {
+            uint32_t cur = (k[0] >> (8 * p)) & 255u, run = 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                if (q < cnt) {
+                    const uint32_t d = (k[q] >> (8 * p)) & 255u;
+                    if (d != cur) { atomicAdd(&h[p][cur], run); cur = d; run = 0; }
+                    ++run;
+                }
+            }
+            atomicAdd(&h[p][cur], run);
         }
     }
     __syncthreads();
-    tile_hist[threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];   // digit-major
+    for (int p = 0; p < passes; ++p) {
+        const uint32_t c = h[p][threadIdx.x];
+        if (c) atomicAdd(&ghist[p * 256 + threadIdx.x], c);
+    }
 }
 
-template <int BITS>
-__global__ void __launch_bounds__(1 << BITS)
-k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n,
-                const uint32_t *__restrict__ n_dev, int shift, const uint32_t *__restrict__ tile_offs,
-                uint32_t ntiles, int vals_iota)
+__global__ void __launch_bounds__(256)
+k_radix_bases(uint32_t *__restrict__ ghist)
 {
-    constexpr int R = 1 << BITS, WARPS = R / 32, TILE = R * SORT_ITEMS;
-    __shared__ uint32_t wcnt[WARPS][R];
-    if (n_dev) n = min(n, *n_dev);
-    if (blockIdx.x * TILE >= n) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < WARPS * R; i += R) (&wcnt[0][0])[i] = 0;
-    __syncthreads();
+    uint32_t total;
+    const uint32_t v = ghist[blockIdx.x * 256 + threadIdx.x];
+    const uint32_t e = block_exclusive_scan(v, &total);
+    ghist[blockIdx.x * 256 + threadIdx.x] = e;
+}
 
-    const uint32_t wbase = blockIdx.x * TILE + warp * (32 * SORT_ITEMS);
-    uint32_t k[SORT_ITEMS], v[SORT_ITEMS], rk[SORT_ITEMS];
+__global__ void __launch_bounds__(OS_THREADS)
+k_radix_onesweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, int shift,
+                 const uint32_t *__restrict__ gbase, uint32_t *state, uint32_t *ticket, int vals_iota)
+{
+    constexpr int R = 256, WARPS = OS_THREADS / 32;
+    __shared__ uint32_t s_key[OS_TILE], s_val[OS_TILE];
+    __shared__ uint32_t wcnt[WARPS][R];
+    __shared__ uint32_t s_dstart[R], s_gpos[R];
+    __shared__ uint32_t s_tile;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < WARPS * R; i += OS_THREADS) (&wcnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t tbase = tile * OS_TILE;
+    const uint32_t tile_n = min((uint32_t)OS_TILE, n - tbase);
+
+    const uint32_t wbase = tbase + warp * (32 * OS_ITEMS);
+    uint32_t k[OS_ITEMS], v[OS_ITEMS], rk[OS_ITEMS];
 #pragma unroll
-    for (int r = 0; r < SORT_ITEMS; ++r) {
+    for (int r = 0; r < OS_ITEMS; ++r) {
         const uint32_t idx = wbase + r * 32 + lane;
         const bool valid = idx < n;
         k[r] = valid ? keys_in[idx] : 0xffffffffu;
         v[r] = valid ? (vals_iota ? idx : vals_in[idx]) : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; ++r) {
+        const bool valid = wbase + r * 32 + lane < n;
         const uint32_t d = (k[r] >> shift) & (R - 1);
         // out-of-range lanes get a private pseudo-digit so they never join a real group
         const uint32_t m = __match_any_sync(0xffffffffu, valid ? d : (R + lane));
@@ -163,43 +210,55 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
         rk[r] = prev + rank;
     }
     __syncthreads();
-    {   // thread d: exclusive scan of digit d over the warps, seeded with this tile's global offset
-        uint32_t run = tile_offs[threadIdx.x * ntiles + blockIdx.x];
+    // thread d: digit d's count in this tile, exclusive offsets of the warps inside the digit
+    uint32_t count = 0;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            uint32_t c = wcnt[w][threadIdx.x];
-            wcnt[w][threadIdx.x] = run;
-            run += c;
+    for (int w = 0; w < WARPS; ++w) {
+        const uint32_t c = wcnt[w][tid];
+        wcnt[w][tid] = count;
+        count += c;
+    }
+    // publish the tile's digit count, then look back for the digit's count in all preceding tiles
+    uint32_t *mine = state + (size_t)tile * R + tid;
+    if (tile == 0) {
+        *(volatile uint32_t *)mine = count | OS_FLAG_PREFIX;
+    } else {
+        *(volatile uint32_t *)mine = count | OS_FLAG_AGG;
+    }
+    uint32_t total;
+    const uint32_t dstart = block_exclusive_scan(count, &total);
+    s_dstart[tid] = dstart;
+    uint32_t prefix = 0;
+    if (tile > 0) {
+        for (int t = (int)tile - 1; t >= 0; --t) {
+            const volatile uint32_t *p = state + (size_t)t * R + tid;
+            uint32_t st;
+            do { st = *p; } while ((st >> 30) == 0u);
+            prefix += st & OS_VALUE_MASK;
+            if ((st >> 30) == 2u) break;
+        }
+        *(volatile uint32_t *)mine = (prefix + count) | OS_FLAG_PREFIX;
+    }
+    s_gpos[tid] = gbase[tid] + prefix;
+    __syncthreads();
+    // stage in sorted order
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; ++r) {
+        if (wbase + r * 32 + lane < n) {
+            const uint32_t d = (k[r] >> shift) & (R - 1);
+            const uint32_t lp = s_dstart[d] + wcnt[warp][d] + rk[r];
+            s_key[lp] = k[r];
+            s_val[lp] = v[r];
         }
     }
     __syncthreads();
-#pragma unroll
-    for (int r = 0; r < SORT_ITEMS; ++r) {
-        const uint32_t idx = wbase + r * 32 + lane;
-        if (idx < n) {
-            const uint32_t d = (k[r] >> shift) & (R - 1);
-            const uint32_t pos = wcnt[warp][d] + rk[r];
-            keys_out[pos] = k[r];
-            vals_out[pos] = v[r];
-        }
+    for (uint32_t i = tid; i < tile_n; i += OS_THREADS) {
+        const uint32_t key = s_key[i];
+        const uint32_t d = (key >> shift) & (R - 1);
+        const uint32_t pos = s_gpos[d] + (i - s_dstart[d]);
+        keys_out[pos] = key;
+        vals_out[pos] = s_val[i];
     }
-}
-
-template <int BITS>
-int radix_pass(cudaStream_t stream, const uint32_t *kin, const uint32_t *vin, uint32_t *kout, uint32_t *vout,
-               uint32_t n, const uint32_t *n_dev, int shift, bool iota, uint32_t *hist, void *scan_ws,
-               size_t scan_bytes)
-{
-    constexpr int R = 1 << BITS, TILE = R * SORT_ITEMS;
-    const uint32_t ntiles = (n + TILE - 1) / TILE;
-    k_radix_hist<BITS><<<ntiles, R, 0, stream>>>(kin, n, n_dev, shift, hist, ntiles);
-    MB_LAUNCHED();
-    int rc = mb_exclusive_scan_u32(stream, hist, hist, ntiles * R, scan_ws, scan_bytes);
-    if (rc) return rc;
-    k_radix_scatter<BITS><<<ntiles, R, 0, stream>>>(kin, vin, kout, vout, n, n_dev, shift, hist, ntiles,
-                                                    iota ? 1 : 0);
-    MB_LAUNCHED();
-    return MB_OK;
 }
 
 }  // namespace
@@ -225,15 +284,11 @@ int mb_exclusive_scan_u32(cudaStream_t stream, const uint32_t *in, uint32_t *out
     return MB_OK;
 }
 
-// 9-bit digits only where they save a pass: 18-bit brick keys sort in two passes, 24-bit voxel keys
-// in three 8-bit ones
-static int digit_bits(int key_bits) { return (key_bits + 8) / 9 < (key_bits + 7) / 8 ? 9 : 8; }
-
 size_t mb_sort_workspace_bytes(uint32_t n)
 {
-    const size_t ntiles = ((size_t)n + 256 * SORT_ITEMS - 1) / (256 * SORT_ITEMS);   // the smaller tile
-    const size_t hist = mb_align_up(ntiles * 512 * sizeof(uint32_t));
-    return hist + mb_scan_workspace_bytes((uint32_t)(ntiles * 512)) + 256;
+    const size_t ntiles = ((size_t)n + OS_TILE - 1) / OS_TILE;
+    // [4 passes][256] digit histograms, 4 tickets, [4 passes][ntiles][256] look-back states
+    return mb_align_up((4 * 256 + 64) * sizeof(uint32_t)) + mb_align_up(4 * ntiles * 256 * sizeof(uint32_t)) + 256;
 }
 
 int mb_sort_pairs(cudaStream_t stream, uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b,
@@ -243,21 +298,32 @@ int mb_sort_pairs(cudaStream_t stream, uint32_t *keys_a, uint32_t *vals_a, uint3
     *keys_out = keys_a;
     *vals_out = vals_a;
     if (n == 0) return MB_OK;
+    MB_REQUIRE(n_dev == nullptr, "mb_sort_pairs: device-side counts are not supported");
+    MB_REQUIRE(n < (1u << 30), "mb_sort_pairs: too many elements");
     MB_REQUIRE(workspace_bytes >= mb_sort_workspace_bytes(n), "sort workspace too small");
+    const int passes = (key_bits + 7) / 8;
+    MB_REQUIRE(passes >= 1 && passes <= 4, "mb_sort_pairs: bad key width");
+    const size_t ntiles = ((size_t)n + OS_TILE - 1) / OS_TILE;
     MbArena arena(workspace, workspace_bytes);
-    const size_t ntiles = ((size_t)n + 256 * SORT_ITEMS - 1) / (256 * SORT_ITEMS);
-    uint32_t *hist = arena.take<uint32_t>(ntiles * 512);
-    const size_t scan_bytes = mb_scan_workspace_bytes((uint32_t)(ntiles * 512));
-    char *scan_ws = arena.take<char>(scan_bytes);
+    uint32_t *head = arena.take<uint32_t>(4 * 256 + 64);      // histograms, then the tickets
+    uint32_t *ghist = head, *tickets = head + 4 * 256;
+    uint32_t *state = arena.take<uint32_t>(4 * ntiles * 256);
+    MB_CHECK_CUDA(cudaMemsetAsync(head, 0, (4 * 256 + 64) * sizeof(uint32_t), stream));
+    MB_CHECK_CUDA(cudaMemsetAsync(state, 0, (size_t)passes * ntiles * 256 * sizeof(uint32_t), stream));
+    size_t hblocks = ((size_t)n + 256 * 16 - 1) / (256 * 16);
+    if (hblocks > (size_t)MB_NUM_SMS * 8) hblocks = (size_t)MB_NUM_SMS * 8;
+    k_radix_hist_all<<<(unsigned)hblocks, 256, 0, stream>>>(keys_a, n, passes, ghist);
+    MB_LAUNCHED();
+    k_radix_bases<<<passes, 256, 0, stream>>>(ghist);
+    MB_LAUNCHED();
 
     uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
     bool iota = vals_a_is_iota;
-    const int bits = digit_bits(key_bits);
-    const int passes = (key_bits + bits - 1) / bits;
     for (int p = 0; p < passes; ++p) {
-        int rc = bits == 9 ? radix_pass<9>(stream, kin, vin, kout, vout, n, n_dev, p * 9, iota, hist, scan_ws, scan_bytes)
-                           : radix_pass<8>(stream, kin, vin, kout, vout, n, n_dev, p * 8, iota, hist, scan_ws, scan_bytes);
-        if (rc) return rc;
+        k_radix_onesweep<<<(unsigned)ntiles, OS_THREADS, 0, stream>>>(kin, vin, kout, vout, n, 8 * p, ghist + p * 256,
+                                                                    state + (size_t)p * ntiles * 256, tickets + p,
+                                                                    iota ? 1 : 0);
+        MB_LAUNCHED();
         iota = false;
         uint32_t *t;
         t = kin; kin = kout; kout = t;
