@@ -42,6 +42,12 @@ C2_FRAMES = 500
 C2_TOUCHED_PER_FRAME = 22243.0
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_cell_accumulate launch on this workload, from the
+# committed ncu --set full capture named below (per launch, like the achieved figure)
+ACCUMULATE_DRAM_BYTES_PER_LAUNCH = 7758.4e6 + 317.8e6
+ACCUMULATE_TRAFFIC_SOURCE = "profiles/r01k_kernels.txt"
+
+
 def algorithmic_bytes_per_frame(h, w, fh, fw, F, touched):
     """depth + features as fed + one read and one write of every touched
     voxel row + pose."""
@@ -227,6 +233,15 @@ def main():
 
     for _ in range(args.warmup):
         step_device()
+    # one extra untimed step with stage events: duration of each stage of the batched pipeline
+    import ctypes
+    L.mb_profile_stages(1)
+    step_device()
+    stage_ms = (ctypes.c_float * 8)()
+    n_stage = L.mb_profile_read(stage_ms, 8)
+    L.mb_profile_stages(0)
+    stages = dict(zip(["voxelise", "sort", "index", "scalar_pass", "accumulate", "apply"],
+                      [float(stage_ms[i]) for i in range(n_stage)]))
     barrier()
     launches0 = L.mb_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -250,16 +265,30 @@ def main():
         depth_h = torch.from_numpy(walk["depth"]).pin_memory()
         probs_h = torch.empty(probs_d.shape, dtype=torch.float32, pin_memory=True)
         probs_h.copy_(probs_d)
-        chunk = 50
+        chunk = 100
+        # two device staging buffers: the copy of chunk i+1 (copy stream) overlaps the fusion of chunk i
+        copy_stream = torch.cuda.Stream(device=dev)
+        stage = [(torch.empty((chunk,) + tuple(depth_h.shape[1:]), dtype=torch.float32, device=dev),
+                  torch.empty((chunk,) + tuple(probs_h.shape[1:]), dtype=torch.float32, device=dev)) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
 
         def step_host():
-            occupied = torch.zeros((), dtype=torch.int64, device=dev)
-            for s in range(0, T, chunk):
+            main = torch.cuda.current_stream(dev)
+            for ev in free:
+                ev.record(main)
+            for i, s in enumerate(range(0, T, chunk)):
                 e = min(s + chunk, T)
+                d_buf, p_buf = stage[i % 2]
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(free[i % 2])
+                    d_buf[:e - s].copy_(depth_h[s:e], non_blocking=True)
+                    p_buf[:e - s].copy_(probs_h[s:e], non_blocking=True)
+                    ready[i % 2].record(copy_stream)
+                main.wait_event(ready[i % 2])
                 layer.update_batch(dict(position=walk["position"][s:e], yaw=walk["yaw"][s:e],
-                                        elevation=walk["elevation"][s:e],
-                                        depth=depth_h[s:e].to(dev, non_blocking=True),
-                                        features=probs_h[s:e].to(dev, non_blocking=True)))
+                                        elevation=walk["elevation"][s:e], depth=d_buf[:e - s], features=p_buf[:e - s]))
+                free[i % 2].record(main)
             occupied = (layer.data[:, :, :, 0] != 0).sum()
             return int(occupied.item())                                   # D2H read of the result
 
@@ -278,7 +307,7 @@ def main():
         e2e = {"value": world * T * n_e2e / (float(ems.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(depth_h.numel() * 4 + probs_h.numel() * 4 + T * 48),
                "d2h_bytes_per_step": 8}
-        del depth_h, probs_h
+        del depth_h, probs_h, stage
 
     if rank != 0:
         if dist is not None:
@@ -292,7 +321,15 @@ def main():
     achieved = per_gpu_fps * bpf / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "kernel": "whole step (all kernels of update_batch)",
-                "algorithmic_bytes_per_frame": bpf}
+                "algorithmic_bytes_per_frame": bpf, "stage_ms": stages}
+    if "accumulate" in stages and stages["accumulate"] > 0:
+        # the dominant kernel alone: it streams every feature row once (4*h*w*F per frame) and writes the run rows
+        acc_bytes = 4.0 * H * W * F * T
+        roofline["dominant_kernel"] = {
+            "kernel": "k_cell_accumulate", "ms": stages["accumulate"], "algorithmic_bytes": acc_bytes,
+            "achieved": acc_bytes / (stages["accumulate"] * 1e-3) / 1e9, "unit": "GB/s",
+            "frac": acc_bytes / (stages["accumulate"] * 1e-3) / 1e9 / peak,
+            "traffic": ACCUMULATE_DRAM_BYTES_PER_LAUNCH, "traffic_source": ACCUMULATE_TRAFFIC_SOURCE}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1 or (not args.no_cpu_baseline and rank == 0 and world == 1):

@@ -134,6 +134,14 @@ int mb_lsap(void *stream, const float *cost32, const double *cost64, int n, int 
  * predecessor (never expected; the map is then not trustworthy). */
 int mb_layer_update_status(void *stream, const void *workspace, uint32_t *error_bits_host);
 
+/* ---- measurement aid (bench.py) -------------------------------------------------------------------------
+ * mb_profile_stages(1) makes MB_MODE_FAST calls record CUDA events on their stream between the stages of
+ * the batched pipeline; mb_profile_read waits for the last recorded call and writes the duration in ms of
+ * {voxelise, sort, index, scalar pass, feature accumulate (round 0), apply + later rounds}; returns the
+ * number of values written (0 if nothing was recorded).  Off by default. */
+int mb_profile_stages(int enable);
+int mb_profile_read(float *ms_host, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

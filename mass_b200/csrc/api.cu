@@ -264,6 +264,15 @@ MB_API int mb_layer_update(void *stream_, const float *rays, const float *depth,
     return MB_OK;
 }
 
+// ---- measurement aid ---------------------------------------------------------------------------------
+MB_API int mb_profile_stages(int enable) { return mbk_profile_enable(enable); }
+
+MB_API int mb_profile_read(float *ms_host, int capacity)
+{
+    MB_REQUIRE(ms_host && capacity > 0, "mb_profile_read: null pointer");
+    return mbk_profile_read(ms_host, capacity);
+}
+
 // ---- a11: SemanticProjectionLayer.find -------------------------------------------------------------
 MB_API size_t mb_class_presence_workspace_bytes(int S0, int S1, int S2, int contour_padding)
 {

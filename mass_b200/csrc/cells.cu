@@ -341,7 +341,7 @@ k_voxel_sources(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__
 // g(t) = r(t) * prod_{s>t} a(s) is the coefficient of every contribution of frame t to this voxel,
 // A = prod a multiplies the old row.  All list loads of a 64-segment block are issued before the first
 // is used: the kernel lives on memory-level parallelism.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vseg, const uint32_t *__restrict__ seg_frame,
                 const float2 *__restrict__ segws, size_t cap, CellGrid g, float alpha, int T,
                 float *__restrict__ gcoef, float *__restrict__ vA, const uint32_t *__restrict__ counters)
@@ -374,29 +374,26 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vs
         // the tables are all zero here (zeroed once per warp, and again row by row after use)
         uint32_t rows = 0;                             // 32-frame rows with at least one touched frame
         if (interior) {
-            for (uint32_t off = 0; off < maxlen; off += 64) {
-                uint32_t f[8][2];
-                float2 x[8][2];
-#pragma unroll
-                for (int s = 0; s < 8; ++s)
-#pragma unroll
-                    for (int it = 0; it < 2; ++it) {
-                        const uint32_t q = slo[s] + off + it * 32 + lane;
-                        f[s][it] = 0xffffffffu;
-                        if (q < shi[s]) {
-                            f[s][it] = __ldg(seg_frame + q);
-                            x[s][it] = __ldg(segws + (size_t)(7 - s) * cap + q);
-                        }
-                    }
+            for (uint32_t off = 0; off < maxlen; off += 32) {
+                uint32_t f[8];
+                float2 x[8];
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
+                    const uint32_t q = slo[s] + off + lane;
+                    f[s] = 0xffffffffu;
+                    if (q < shi[s]) {
+                        f[s] = __ldg(seg_frame + q);
+                        x[s] = __ldg(segws + (size_t)(7 - s) * cap + q);
+                    }
+                }
 #pragma unroll
-                    for (int it = 0; it < 2; ++it)
-                        if (f[s][it] != 0xffffffffu) {
-                            tW[f[s][it]] += x[s][it].x;    // one segment per frame and source: no two lanes share f
-                            tS[f[s][it]] += x[s][it].y;
-                            rows |= 1u << (f[s][it] >> 5);
-                        }
+                for (int s = 0; s < 8; ++s) {
+                    if (slo[s] + off >= shi[s]) continue;          // warp-uniform: nothing left in this source
+                    if (f[s] != 0xffffffffu) {
+                        tW[f[s]] += x[s].x;                        // one segment per frame and source: no two lanes share f
+                        tS[f[s]] += x[s].y;
+                        rows |= 1u << (f[s] >> 5);
+                    }
                     __syncwarp();
                 }
             }
@@ -444,21 +441,16 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vs
         }
         __syncwarp();
         if (interior) {
-            for (uint32_t off = 0; off < maxlen; off += 64) {
-                uint32_t f[8][2];
+            for (uint32_t off = 0; off < maxlen; off += 32) {
+                uint32_t f[8];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const uint32_t q = slo[s] + off + lane;
+                    f[s] = q < shi[s] ? __ldg(seg_frame + q) : 0xffffffffu;
+                }
 #pragma unroll
                 for (int s = 0; s < 8; ++s)
-#pragma unroll
-                    for (int it = 0; it < 2; ++it) {
-                        const uint32_t q = slo[s] + off + it * 32 + lane;
-                        f[s][it] = q < shi[s] ? __ldg(seg_frame + q) : 0xffffffffu;
-                    }
-#pragma unroll
-                for (int s = 0; s < 8; ++s)
-#pragma unroll
-                    for (int it = 0; it < 2; ++it)
-                        if (f[s][it] != 0xffffffffu)
-                            gcoef[(size_t)(7 - s) * cap + (slo[s] + off + it * 32 + lane)] = tW[f[s][it]];
+                    if (f[s] != 0xffffffffu) gcoef[(size_t)(7 - s) * cap + (slo[s] + off + lane)] = tW[f[s]];
             }
         } else {
 #pragma unroll
@@ -956,6 +948,39 @@ int dispatch_apply(cudaStream_t stream, const ApplyArgs &A, int vec, int it)
 
 }  // namespace
 
+// ---- optional stage timing (mb_profile_stages / mb_profile_read): CUDA events between the stages of the
+// last chunk processed while profiling was enabled.  Off by default: no events are recorded.
+namespace {
+constexpr int N_STAGES = 6;      // voxelise, sort, index, scalars, accumulate, apply
+bool g_profile = false;
+cudaEvent_t g_ev[N_STAGES + 1];
+bool g_ev_ready = false, g_ev_recorded = false;
+
+int stage_mark(cudaStream_t stream, int i)
+{
+    if (!g_profile) return MB_OK;
+    if (!g_ev_ready) {
+        for (int k = 0; k <= N_STAGES; ++k) MB_CHECK_CUDA(cudaEventCreate(&g_ev[k]));
+        g_ev_ready = true;
+    }
+    MB_CHECK_CUDA(cudaEventRecord(g_ev[i], stream));
+    if (i == N_STAGES) g_ev_recorded = true;
+    return MB_OK;
+}
+}  // namespace
+
+int mbk_profile_enable(int enable) { g_profile = enable != 0; return MB_OK; }
+
+int mbk_profile_read(float *ms_host, int capacity)
+{
+    if (!g_ev_recorded) return 0;
+    if (cudaEventSynchronize(g_ev[N_STAGES]) != cudaSuccess) return 0;
+    int n = 0;
+    for (int k = 0; k < N_STAGES && k < capacity; ++k, ++n)
+        if (cudaEventElapsedTime(&ms_host[k], g_ev[k], g_ev[k + 1]) != cudaSuccess) return n;
+    return n;
+}
+
 // bytes per P run (8 rows of F floats)
 static size_t run_bytes(int F) { return (size_t)8 * F * sizeof(float); }
 
@@ -1032,6 +1057,8 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     MB_REQUIRE(rounds <= 4096, "batch workspace far too small for the run buffer");
 
     // K1 + sort
+    int rc;
+    if ((rc = stage_mark(stream, 0))) return rc;
     dim3 grid((npix + 255) / 256, (unsigned)T);
     int pbits = 1;
     while ((1u << pbits) < npix) ++pbits;
@@ -1041,12 +1068,14 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     MB_LAUNCHED();
     int bits = 1;
     while (bits < 32 && (((uint64_t)1) << bits) <= (uint64_t)g.invalid) ++bits;
+    if ((rc = stage_mark(stream, 1))) return rc;
     uint32_t *skey, *sval;
-    int rc = mb_sort_pairs(stream, b.keys_a, b.pids_a, b.keys_b, b.pids_b, n, nullptr, bits, false, b.sort_ws,
+    rc = mb_sort_pairs(stream, b.keys_a, b.pids_a, b.keys_b, b.pids_b, n, nullptr, bits, false, b.sort_ws,
                            b.sort_bytes, &skey, &sval);
     if (rc) return rc;
 
     // K2 + ranks
+    if ((rc = stage_mark(stream, 2))) return rc;
     MB_CHECK_CUDA(cudaMemsetAsync(b.bitmap, 0, (size_t)vwords * sizeof(uint32_t), stream));
     if (b.ctab) MB_CHECK_CUDA(cudaMemsetAsync(b.ctab, 0xff, (size_t)g.invalid * sizeof(int), stream));
     const unsigned nblk = (unsigned)(((size_t)words * 32 + 255) / 256);
@@ -1068,6 +1097,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     k_vox_emit<<<(vwords + 255) / 256, 256, 0, stream>>>(b.bitmap, b.voff, vwords, b.vlist, b.counters);
     MB_LAUNCHED();
     // K5, K6
+    if ((rc = stage_mark(stream, 3))) return rc;
     k_seg_sums<<<MB_NUM_SMS * 8, 256, 0, stream>>>(sval, b.rec, b.seg_start, npix, pbits, b.segws, (size_t)n, b.counters);
     MB_LAUNCHED();
     {
@@ -1095,8 +1125,10 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     Y.g = g; Y.F = F; Y.map = map; Y.affine_a = affine_a; Y.run_cap = run_cap;
     for (int r = 0; r < rounds; ++r) {
         A.run_base = Y.run_base = (uint32_t)r * run_cap;
+        if (r == 0 && (rc = stage_mark(stream, 4))) return rc;
         if ((rc = dispatch_accumulate(stream, A, vec, it))) return rc;
+        if (r == 0 && (rc = stage_mark(stream, 5))) return rc;
         if ((rc = dispatch_apply(stream, Y, vec, it))) return rc;
     }
-    return MB_OK;
+    return stage_mark(stream, 6);
 }

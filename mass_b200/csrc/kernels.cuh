@@ -59,6 +59,9 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
                      float *map, float *affine_a, float alpha, float min_d, float max_d, void *workspace,
                      size_t workspace_bytes);
 
+int mbk_profile_enable(int enable);
+int mbk_profile_read(float *ms_host, int capacity);
+
 // instances.cu: instance extraction (find) and matching
 size_t mbk_class_presence_workspace_bytes(int S0, int S1, int S2, int pad);
 int mbk_class_presence(cudaStream_t stream, const float *map, int S0, int S1, int S2, int F, int c, int pad, float thr,
