@@ -493,6 +493,28 @@ struct AccArgs {
     uint32_t run_base, run_cap; // runs of this round: [run_base, run_base + run_cap)
 };
 
+// acc += c * f on VEC floats; pairs go through the packed fp32x2 FMA of sm_100
+__device__ __forceinline__ void ffma2(float &a0, float &a1, float c, float f0, float f1)
+{
+    unsigned long long ra, rc, rf;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(rc) : "f"(c));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rf) : "f"(f0), "f"(f1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ra) : "l"(rc), "l"(rf));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ra));
+}
+
+template <int VEC>
+__device__ __forceinline__ void vec_fma(float (&acc)[VEC], float c, const float (&f)[VEC])
+{
+    if (VEC == 1) acc[0] = fmaf(c, f[0], acc[0]);
+    if (VEC == 2) ffma2(acc[0], acc[VEC > 1 ? 1 : 0], c, f[0], f[VEC > 1 ? 1 : 0]);
+    if (VEC == 4) {
+        ffma2(acc[0], acc[VEC > 1 ? 1 : 0], c, f[0], f[VEC > 1 ? 1 : 0]);
+        ffma2(acc[VEC > 2 ? 2 : 0], acc[VEC > 2 ? 3 : 0], c, f[VEC > 2 ? 2 : 0], f[VEC > 2 ? 3 : 0]);
+    }
+}
+
 template <int VEC>
 __device__ __forceinline__ void row_load(float (&dst)[VEC], const float *p)
 {
@@ -646,9 +668,7 @@ k_cell_accumulate(const AccArgs A)
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
 #pragma unroll
-                            for (int it = 0; it < IT; ++it)
-#pragma unroll
-                                for (int j = 0; j < VEC; ++j) acc[k][it][j] = fmaf(c[k], f[u][it][j], acc[k][it][j]);
+                            for (int it = 0; it < IT; ++it) vec_fma<VEC>(acc[k][it], c[k], f[u][it]);
                     }
                 }
                 for (; jj < jend; ++jj) {
@@ -673,9 +693,7 @@ k_cell_accumulate(const AccArgs A)
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
 #pragma unroll
-                        for (int it = 0; it < IT; ++it)
-#pragma unroll
-                            for (int j = 0; j < VEC; ++j) acc[k][it][j] = fmaf(c[k], f[it][j], acc[k][it][j]);
+                        for (int it = 0; it < IT; ++it) vec_fma<VEC>(acc[k][it], c[k], f[it]);
                 }
             }
         }
