@@ -101,6 +101,23 @@ int mb_layer_update(void *stream, const float *rays, const float *depth, const f
                     float min_ray_depth, float max_ray_depth, int mode, void *workspace,
                     size_t workspace_bytes);
 
+/* ---- frame-sharded scenes: ordered affine combine of partial maps (no counterpart in the reference, which is
+ * single-GPU; the per-voxel update it composes is mass/utils/projection.py:335-351) ----
+ * mb_layer_fold: like mb_layer_update in MB_MODE_FAST, but also folds the frames' per-voxel coefficients into
+ *   partial_a [S0*S1*S2]: entries equal to 2.0f mark untouched voxels on entry and stay 2.0f if the call does
+ *   not touch them; a touched voxel ends as the product of its frames' a (times its previous value unless that
+ *   was 2.0f).  With partial_b zeroed and partial_a filled with 2.0f beforehand, the T frames act on any map M
+ *   as  M[v] <- partial_a[v] * M[v] + partial_b[v]  for every touched v.
+ * mb_affine_apply_rows: map[voxel_index[i]] = a[i] * map[voxel_index[i]] + b[i] (rows of F floats, distinct
+ *   indices), the in-order application of one rank's partial. */
+int mb_layer_fold(void *stream, const float *rays, const float *depth, const float *features,
+                  const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw, int F,
+                  const float *bins_x, int nx, const float *bins_y, int ny, const float *bins_z, int nz,
+                  float *partial_b, float *partial_a, float interpolation_weight, float min_ray_depth,
+                  float max_ray_depth, void *workspace, size_t workspace_bytes);
+int mb_affine_apply_rows(void *stream, float *map, int F, const int64_t *voxel_index, const float *a,
+                         const float *b, int64_t n);
+
 /* ---- a11: SemanticProjectionLayer.find (mass/nn/applications/semantic_projection_layer.py:257-362) ----
  * Step 1, lines 309-317: image[y][x] = any over z of (box mean of map[..., category] with kernel
  * 2*contour_padding+1, zero padded, divisor k^3) > contour_threshold; uint8 [S0][S1].

@@ -53,6 +53,9 @@ _SIGNATURES = {
                                      _i32, _f32, _i32, _vp, _sz]),
     "mb_layer_update_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "mb_layer_update_min_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "mb_layer_fold": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32,
+                             _vp, _i32, _vp, _i32, _vp, _vp, _f32, _f32, _f32, _vp, _sz]),
+    "mb_affine_apply_rows": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64]),
     "mb_profile_stages": (_i32, [_i32]),
     "mb_profile_read": (_i32, [_vp, _i32]),
     "mb_layer_update_status": (_i32, [_vp, _vp, _vp]),

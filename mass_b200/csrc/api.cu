@@ -204,12 +204,12 @@ MB_API size_t mb_layer_update_min_workspace_bytes(int H, int W, int nx, int ny, 
     return mbk_batch_min_workspace_bytes(npix, nx, ny, nz, T, F);
 }
 
-MB_API int mb_layer_update(void *stream_, const float *rays, const float *depth, const float *features,
-                           const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw,
-                           int F, const float *bins_x, int nx, const float *bins_y, int ny,
-                           const float *bins_z, int nz, float *map, float interpolation_weight,
-                           float min_ray_depth, float max_ray_depth, int mode, void *workspace,
-                           size_t workspace_bytes)
+static int layer_update(void *stream_, const float *rays, const float *depth, const float *features,
+                        const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw,
+                        int F, const float *bins_x, int nx, const float *bins_y, int ny,
+                        const float *bins_z, int nz, float *map, float *affine_a, float interpolation_weight,
+                        float min_ray_depth, float max_ray_depth, int mode, void *workspace,
+                        size_t workspace_bytes)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     MB_REQUIRE(T >= 0 && H > 0 && W > 0 && F > 0, "mb_layer_update: bad sizes");
@@ -238,7 +238,7 @@ MB_API int mb_layer_update(void *stream_, const float *rays, const float *depth,
             int rc = mbk_batch_update(stream, rays, depth + (size_t)t * npix,
                                       features ? features + (size_t)t * feat_stride : nullptr,
                                       class_ids ? class_ids + (size_t)t * npix : nullptr, pose + (size_t)t * 12, n,
-                                      H, W, fh, fw, F, bins_x, nx, bins_y, ny, bins_z, nz, map, nullptr,
+                                      H, W, fh, fw, F, bins_x, nx, bins_y, ny, bins_z, nz, map, affine_a,
                                       interpolation_weight, min_ray_depth, max_ray_depth, workspace, workspace_bytes);
             if (rc) return rc;
         }
@@ -262,6 +262,40 @@ MB_API int mb_layer_update(void *stream_, const float *rays, const float *depth,
         if (rc) return rc;
     }
     return MB_OK;
+}
+
+MB_API int mb_layer_update(void *stream, const float *rays, const float *depth, const float *features,
+                           const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw,
+                           int F, const float *bins_x, int nx, const float *bins_y, int ny,
+                           const float *bins_z, int nz, float *map, float interpolation_weight,
+                           float min_ray_depth, float max_ray_depth, int mode, void *workspace,
+                           size_t workspace_bytes)
+{
+    return layer_update(stream, rays, depth, features, class_ids, pose, T, H, W, fh, fw, F, bins_x, nx, bins_y, ny,
+                        bins_z, nz, map, nullptr, interpolation_weight, min_ray_depth, max_ray_depth, mode, workspace,
+                        workspace_bytes);
+}
+
+// ---- frame-sharded scenes ---------------------------------------------------------------
+MB_API int mb_layer_fold(void *stream, const float *rays, const float *depth, const float *features,
+                         const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw, int F,
+                         const float *bins_x, int nx, const float *bins_y, int ny, const float *bins_z, int nz,
+                         float *partial_b, float *partial_a, float interpolation_weight, float min_ray_depth,
+                         float max_ray_depth, void *workspace, size_t workspace_bytes)
+{
+    MB_REQUIRE(partial_a != nullptr, "mb_layer_fold: null pointer");
+    return layer_update(stream, rays, depth, features, class_ids, pose, T, H, W, fh, fw, F, bins_x, nx, bins_y, ny,
+                        bins_z, nz, partial_b, partial_a, interpolation_weight, min_ray_depth, max_ray_depth,
+                        MB_MODE_FAST, workspace, workspace_bytes);
+}
+
+MB_API int mb_affine_apply_rows(void *stream, float *map, int F, const int64_t *voxel_index, const float *a,
+                                const float *b, int64_t n)
+{
+    MB_REQUIRE(n >= 0 && F > 0, "mb_affine_apply_rows: bad sizes");
+    if (n == 0) return MB_OK;
+    MB_REQUIRE(map && voxel_index && a && b, "mb_affine_apply_rows: null pointer");
+    return mbk_affine_apply_rows((cudaStream_t)stream, map, F, voxel_index, a, b, n);
 }
 
 // ---- measurement aid ---------------------------------------------------------------------------------

@@ -836,7 +836,27 @@ k_voxel_apply(const ApplyArgs A)
                 row_store<VEC>(grow + ch, old[it]);
             }
         }
-        if (A.affine_a != nullptr && A.run_base == 0 && blockIdx.y == 0 && lane == 0) A.affine_a[v] = A.affine_a[v] * a;
+        if (A.affine_a != nullptr && A.run_base == 0 && blockIdx.y == 0 && lane == 0) {
+            // fold output: 2.0 marks a voxel no chunk has touched yet (a product of a's never exceeds 1)
+            const float prev = A.affine_a[v];
+            A.affine_a[v] = (prev == 2.0f ? 1.0f : prev) * a;
+        }
+    }
+}
+
+// Ordered affine combine of frame-sharded partial maps: map[idx[i]] = a[i] * map[idx[i]] + b[i].
+// One warp per row, lanes stride over the channels; idx holds distinct voxels, so rows never collide.
+__global__ void __launch_bounds__(256)
+k_affine_apply_rows(float *__restrict__ map, int F, const int64_t *__restrict__ idx, const float *__restrict__ a,
+                    const float *__restrict__ b, int64_t n)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = wid; i < n; i += nw) {
+        float *row = map + (size_t)idx[i] * F;
+        const float *brow = b + (size_t)i * F;
+        const float ai = a[i];
+        for (int ch = lane; ch < F; ch += 32) row[ch] = fmaf(ai, row[ch], brow[ch]);
     }
 }
 
@@ -997,6 +1017,15 @@ int mbk_profile_read(float *ms_host, int capacity)
     for (int k = 0; k < N_STAGES && k < capacity; ++k, ++n)
         if (cudaEventElapsedTime(&ms_host[k], g_ev[k], g_ev[k + 1]) != cudaSuccess) return n;
     return n;
+}
+
+int mbk_affine_apply_rows(cudaStream_t stream, float *map, int F, const int64_t *idx, const float *a, const float *b,
+                          int64_t n)
+{
+    if (n <= 0) return MB_OK;
+    k_affine_apply_rows<<<MB_NUM_SMS * 8, 256, 0, stream>>>(map, F, idx, a, b, n);
+    MB_LAUNCHED();
+    return MB_OK;
 }
 
 // bytes per P run (8 rows of F floats)

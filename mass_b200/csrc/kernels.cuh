@@ -59,6 +59,8 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
                      float *map, float *affine_a, float alpha, float min_d, float max_d, void *workspace,
                      size_t workspace_bytes);
 
+int mbk_affine_apply_rows(cudaStream_t stream, float *map, int F, const int64_t *idx, const float *a, const float *b,
+                          int64_t n);
 int mbk_profile_enable(int enable);
 int mbk_profile_read(float *ms_host, int capacity);
 

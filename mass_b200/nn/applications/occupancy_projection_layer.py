@@ -19,7 +19,7 @@ class OccupancyProjectionLayer(BaseProjectionLayer):
                                    features=torch.ones_like(depth).reshape(
                                        self.camera_height, self.camera_width, 1)))
 
-    def update_batch(self, observations):
+    def update_batch(self, observations, fold=None):
         if isinstance(observations, (list, tuple)):
             observations = {k: torch.stack([torch.as_tensor(o[k]) for o in observations])
                             for k in ("position", "yaw", "elevation", "depth")}
@@ -28,7 +28,7 @@ class OccupancyProjectionLayer(BaseProjectionLayer):
         return super().update_batch(dict(position=observations["position"], yaw=observations["yaw"],
                                          elevation=observations["elevation"], depth=depth,
                                          features=torch.ones_like(depth).reshape(
-                                             T, self.camera_height, self.camera_width, 1)))
+                                             T, self.camera_height, self.camera_width, 1)), fold=fold)
 
     def visualize(self, obs: Dict[str, Any], depth_slice: slice = slice(4, 32)):
         """Occupied columns in black, the agent's cell in red.  The reference draws the

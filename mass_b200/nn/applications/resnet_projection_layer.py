@@ -51,7 +51,7 @@ class ResNetProjectionLayer(BaseProjectionLayer):
                                    elevation=observation["elevation"],
                                    depth=self.subsample_depth(depth, features.shape[0]), features=features))
 
-    def update_batch(self, observations):
+    def update_batch(self, observations, fold=None):
         if isinstance(observations, (list, tuple)):
             observations = {k: torch.stack([torch.as_tensor(o[k]) for o in observations])
                             for k in observations[0].keys()}
@@ -60,7 +60,7 @@ class ResNetProjectionLayer(BaseProjectionLayer):
         return super().update_batch(dict(position=observations["position"], yaw=observations["yaw"],
                                          elevation=observations["elevation"],
                                          depth=self.subsample_depth(depth, features.shape[1]),
-                                         features=features))
+                                         features=features), fold=fold)
 
     def visualize(self, obs: Dict[str, Any], depth_slice: slice = slice(4, 32)):
         """The reference returns None here (resnet_projection_layer.py:245-269)."""

@@ -54,7 +54,7 @@ class SemanticProjectionLayer(BaseProjectionLayer):
                                    elevation=observation["elevation"], depth=observation["depth"],
                                    class_ids=ids))
 
-    def update_batch(self, observations):
+    def update_batch(self, observations, fold=None):
         if isinstance(observations, (list, tuple)):
             observations = {k: torch.stack([torch.as_tensor(o[k]) for o in observations])
                             for k in observations[0].keys()}
@@ -64,7 +64,7 @@ class SemanticProjectionLayer(BaseProjectionLayer):
             raise RuntimeError("Class values must be in [0, %d)" % self.feature_size)
         return super().update_batch(dict(position=observations["position"], yaw=observations["yaw"],
                                          elevation=observations["elevation"], depth=observations["depth"],
-                                         class_ids=ids))
+                                         class_ids=ids), fold=fold)
 
     def visualize(self, obs: Dict[str, Any], depth_slice: slice = slice(0, 32)):
         """Top-down arg-max class colours, white where empty, red boxes from the last find().

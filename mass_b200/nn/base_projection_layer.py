@@ -82,8 +82,10 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         return self.get_feature_map()
 
     # -- the hot path ----------------------------------------------------------------------------
-    def _fuse(self, pose, depth, features, class_ids, T):
-        """pose [T,12] CPU f32; depth [T,H,W] ; features [T,fh,fw,F] or class_ids [T,H,W] int64."""
+    def _fuse(self, pose, depth, features, class_ids, T, fold=None):
+        """pose [T,12] CPU f32; depth [T,H,W] ; features [T,fh,fw,F] or class_ids [T,H,W] int64.
+        fold = (partial_b, partial_a): fold the frames into a partial map instead of self.data
+        (frame-sharded scenes, mass_b200/nn/sharded.py)."""
         device = _lib.require_cuda(self.data.device)
         if self.data.dtype != torch.float32 or not self.data.is_contiguous():
             raise ValueError("layer.data must be a contiguous float32 tensor")
@@ -107,13 +109,22 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
             features = features.contiguous()
         L = _lib.lib()
         nx, ny, nz = self.bins_x.numel(), self.bins_y.numel(), self.bins_z.numel()
-        mode = _lib.MODE_EXACT if self.exact else _lib.MODE_FAST
+        mode = _lib.MODE_EXACT if (self.exact and fold is None) else _lib.MODE_FAST
         want = L.mb_layer_update_workspace_bytes(H, W, nx, ny, nz, T, F, mode)
         if self.workspace_limit is not None:
             # a smaller scratch buffer makes the library split the call (fewer frames per chunk, more
             # rounds of the feature pass); below the one-frame minimum the call fails
             want = min(want, int(self.workspace_limit))
         ws = self._ws.get(want, device)
+        if fold is not None:
+            partial_b, partial_a = fold
+            _lib.check(L.mb_layer_fold(
+                _lib.stream_ptr(device), _lib.ptr(self.rays), _lib.ptr(depth), _lib.ptr(features),
+                _lib.ptr(class_ids), _lib.ptr(pose), T, H, W, fh, fw, F, _lib.ptr(self.bins_x), nx,
+                _lib.ptr(self.bins_y), ny, _lib.ptr(self.bins_z), nz, _lib.ptr(partial_b), _lib.ptr(partial_a),
+                float(self.interpolation_weight), float(self.min_ray_depth), float(self.max_ray_depth),
+                _lib.ptr(ws), ws.numel()))
+            return self
         _lib.check(L.mb_layer_update(
             _lib.stream_ptr(device), _lib.ptr(self.rays), _lib.ptr(depth), _lib.ptr(features),
             _lib.ptr(class_ids), _lib.ptr(pose), T, H, W, fh, fw, F, _lib.ptr(self.bins_x), nx,
@@ -146,7 +157,7 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
             return self._fuse(pose, observation["depth"], observation["features"], None, 1)
         return self._fuse(pose, observation["depth"], None, observation["class_ids"], 1)
 
-    def update_batch(self, observations):
+    def update_batch(self, observations, fold=None):
         """Fuse T observations in order (frames do not commute).  `observations` is a
         list of observation dicts or one dict of stacked arrays with a leading T axis."""
         if isinstance(observations, (list, tuple)):
@@ -157,8 +168,8 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
                            torch.as_tensor(observations["yaw"]).reshape(T),
                            torch.as_tensor(observations["elevation"]).reshape(T))
         if "features" in observations:
-            return self._fuse(pose, observations["depth"], observations["features"], None, T)
-        return self._fuse(pose, observations["depth"], None, observations["class_ids"], T)
+            return self._fuse(pose, observations["depth"], observations["features"], None, T, fold=fold)
+        return self._fuse(pose, observations["depth"], None, observations["class_ids"], T, fold=fold)
 
     # -- rendering + coordinate helpers (not on the hot path; plain torch) --------------------------
     def top_down(self, depth_slice: slice = slice(0, 32)):

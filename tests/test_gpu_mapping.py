@@ -417,3 +417,55 @@ def test_batched_c2_prefix_vs_oracle(dev, oracle):
     assert np.array_equal((got != 0).any(-1), (ref.data != 0).any(-1))
     idx = np.flatnonzero((ref.data != 0).any(-1).reshape(-1))
     assert_close_rel(got.reshape(-1, 54)[idx], ref.data.reshape(-1, 54)[idx])
+
+
+# ---- frame-sharded scenes -----------------------------------------------------------
+def test_fold_and_ordered_apply_equal_sequential(dev, oracle):
+    """One GPU standing in for three ranks: contiguous frame chunks folded into sparse partials from the
+    identity, then applied in chunk order, equal the sequential fusion (and the reverse order does not)."""
+    from mass_b200.nn import sharded
+    H, W, T, F = 32, 40, 9, 12
+    kw = dict(camera_height=H, camera_width=W, vertical_fov=90.0, map_height=44, map_width=50, map_depth=18,
+              feature_size=F, grid_resolution=0.12, interpolation_weight=0.5, origin_z=0.3)
+    rng = np.random.default_rng(21)
+    frames = _random_frames(rng, T, H, W, H, W, F, depth_lo=0.8, depth_hi=1.4)
+    frames["position"][:] = frames["position"][0]
+    frames["yaw"][:] = frames["yaw"][0] + rng.normal(0, 0.05, T).astype(np.float32)
+    frames["elevation"][:] = frames["elevation"][0]
+    start = (rng.random((44, 50, 18, F)) * (rng.random((44, 50, 18, 1)) < 0.5)).astype(np.float32)
+    ref = oracle.OracleLayer(**kw)
+    ref.data[...] = start
+    for t in range(T):
+        ref.update({k: v[t] for k, v in frames.items()})
+    layer = make_layer(kw, dev, exact=False)
+    layer.data.copy_(torch.from_numpy(start))
+    partial = sharded.PartialMap(layer)
+    parts = []
+    for lo, hi in ((0, 4), (4, 5), (5, 9)):
+        parts.append(sharded.fold_frames(layer, {k: v[lo:hi] for k, v in frames.items()}, partial))
+    assert torch.equal(layer.data.cpu(), torch.from_numpy(start))          # folding does not touch the map
+    assert float(partial.a.min()) == 2.0 and float(partial.b.abs().max()) == 0.0   # scratch is clean again
+    for idx, a, b in parts:
+        assert idx.dtype == torch.int64 and a.shape == idx.shape and tuple(b.shape) == (idx.numel(), F)
+        sharded.apply_partial(layer, idx, a, b)
+    got = layer.data.cpu().numpy()
+    assert np.array_equal((got != 0).any(-1), (ref.data != 0).any(-1))
+    assert_close_rel(got, ref.data)
+    wrong = make_layer(kw, dev, exact=False)
+    wrong.data.copy_(torch.from_numpy(start))
+    for idx, a, b in reversed(parts):
+        sharded.apply_partial(wrong, idx, a, b)
+    assert not np.allclose(wrong.data.cpu().numpy(), ref.data, rtol=1e-3, atol=0)
+
+
+def test_sharded_nccl_two_gpus():
+    """Real exchange over NCCL when the box has >= 2 GPUs (gpurun --gpus 2); skipped on one GPU."""
+    import subprocess, sys, os
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                           "--master-addr", "127.0.0.1", "--master-port", "29531",
+                           os.path.join(root, "tests", "dist_sharded_check.py")],
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-3000:]
