@@ -15,9 +15,9 @@
 //
 //   K1  k_cell_voxelise   pixel -> record {cell key, 3 in-voxel ratios}, key array for the sort
 //   --  stable radix sort of (cell key, pixel id): inside a cell the pixels stay in (frame, pixel) order
-//   K2  k_cell_flags      head flags of cells, (cell, frame) segments and accumulate runs + counts
-//   --  three exclusive scans (ranks)
-//   K3  k_cell_emit       unique cell list, segment list, touched-voxel bitmap
+//   K2  k_cell_index      one sweep over the sorted list: heads of cells, (cell, frame) segments and accumulate
+//                         runs, their ranks (decoupled look-back), unique cell list, segment list, dense cell
+//                         table, touched-voxel bitmap
 //   K4  k_vox_count/emit  ordered list of touched voxels
 //   K5  k_seg_sums        per segment and slot: W, S2                                  (scalars)
 //   K6a k_voxel_sources   per touched voxel: segment and run ranges of its <= 8 source cells
@@ -152,100 +152,156 @@ k_cell_voxelise(const float *__restrict__ rays, const float *__restrict__ depth,
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: one thread per sorted position.  cell head: first pixel of a cell; segment head: first pixel
-// of a (cell, frame); run head: cell head or start of an accumulate task.
-__global__ void __launch_bounds__(256)
-k_cell_flags(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sval, uint32_t n, int pbits,
-             uint32_t invalid, uint32_t *__restrict__ cmask, uint32_t *__restrict__ smask, uint32_t *__restrict__ ccnt,
-             uint32_t *__restrict__ scnt, uint32_t *__restrict__ rcnt, uint32_t *__restrict__ counters)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool chead = false, shead = false, rhead = false;
-    if (i < n) {
-        const uint32_t k = skey[i];
-        if (k < invalid) {
-            const uint32_t kp = i ? skey[i - 1] : 0xffffffffu;
-            chead = i == 0 || kp != k;
-            shead = chead || (sval[i - 1] >> pbits) != (sval[i] >> pbits);
-            rhead = chead || (i % CH) == 0;
-            if (i + 1 == n || skey[i + 1] >= invalid) counters[MB_CNT_NVALID] = i + 1;
-        }
-    }
-    const uint32_t cm = __ballot_sync(FULL, chead), sm = __ballot_sync(FULL, shead), rm = __ballot_sync(FULL, rhead);
-    if ((threadIdx.x & 31) == 0 && (i >> 5) <= (n >> 5)) {
-        cmask[i >> 5] = cm;
-        smask[i >> 5] = sm;
-        ccnt[i >> 5] = __popc(cm);
-        scnt[i >> 5] = __popc(sm);
-        rcnt[i >> 5] = __popc(rm);
-    }
-}
+// K2/K3 fused: one sweep over the sorted list finds the heads of cells, (cell, frame) segments and accumulate
+// runs, ranks them and emits the unique cell list, the segment list, the dense cell table and the
+// touched-voxel bitmap.  A tile is 2048 sorted positions (8 warps x 8 words of 32).  The three ranks of a
+// tile's first position come from a decoupled look-back over the preceding tiles' counts (tiles take
+// their index from a ticket, so a tile only ever waits for tiles that started before it).
+//   cell head: first pixel of a cell; segment head: first pixel of a (cell, frame); run head: cell head or
+//   start of an accumulate task (a multiple of CH).
+constexpr int IDX_WORDS = 8;                      // words per warp
+constexpr int IDX_TILE = 256 * IDX_WORDS;         // positions per tile
+constexpr uint32_t IDX_AGG = 1u << 30, IDX_PREFIX = 2u << 30, IDX_MASK = (1u << 30) - 1u;
 
-// K3: unique cells, segments, touched-voxel bitmap.  coff/soff/roff = exclusive scans of the counts.
+struct IndexOut {
+    uint32_t *smask, *soff, *roff;                // per word of 32 positions: segment-head mask, ranks before the word
+    uint32_t *ucell, *cstart, *cseg, *crun;       // per unique cell (+ sentinel)
+    uint32_t *seg_start, *seg_frame;              // per segment (+ sentinel)
+    uint32_t *bitmap;                             // touched voxels
+    int *ctab;                                    // dense cell key -> unique index, or null
+    uint32_t *counters;
+    uint32_t *state;                              // [tiles][3] look-back words, zeroed
+    uint32_t *ticket;                             // zeroed
+};
+
 __global__ void __launch_bounds__(256)
-k_cell_emit(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sval, uint32_t n, int pbits,
-            CellGrid g, const uint32_t *__restrict__ cmask, const uint32_t *__restrict__ smask,
-            const uint32_t *__restrict__ coff, const uint32_t *__restrict__ soff, const uint32_t *__restrict__ roff,
-            uint32_t *__restrict__ ucell, uint32_t *__restrict__ cstart, uint32_t *__restrict__ cseg,
-            uint32_t *__restrict__ crun, uint32_t *__restrict__ seg_start, uint32_t *__restrict__ seg_frame,
-            uint32_t *__restrict__ bitmap, int *__restrict__ ctab, uint32_t *__restrict__ counters)
+k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sval, uint32_t n, int pbits, CellGrid g,
+             const IndexOut O)
 {
-    const uint32_t nvalid = counters[MB_CNT_NVALID];
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    if (i >= n) return;
-    const uint32_t w = i >> 5, lt = (1u << lane) - 1u;
-    const uint32_t cm = cmask[w], sm = smask[w];
-    const uint32_t crank = coff[w] + __popc(cm & lt), srank = soff[w] + __popc(sm & lt);
-    if (i < nvalid) {
-        if ((sm >> lane) & 1u) {
-            seg_start[srank] = i;
-            seg_frame[srank] = sval[i] >> pbits;
-        }
-        if ((cm >> lane) & 1u) {
-            const uint32_t key = skey[i];
-            // run rank: run heads before i = cell heads + task starts that are not cell heads; i is a
-            // cell head here, so its rank is the scan value of its word plus the heads before it in the
-            // word -- recomputed from the definition to avoid storing a third mask
-            uint32_t rr = roff[w];
-            {
-                const uint32_t wbase = w << 5;
-                uint32_t rm = cm;
-                if ((wbase % CH) == 0) rm |= 1u;           // CH is a multiple of 32: only bit 0 can be a task start
-                rr += __popc(rm & lt);
-            }
-            ucell[crank] = key;
-            if (ctab != nullptr) ctab[key] = (int)crank;
-            cstart[crank] = i;
-            cseg[crank] = srank;
-            crun[crank] = rr;
-            const int e2 = (int)(key % (uint32_t)g.E2);
-            const uint32_t t = key / (uint32_t)g.E2;
-            const int e1 = (int)(t % (uint32_t)g.E1), e0 = (int)(t / (uint32_t)g.E1);
+    __shared__ uint32_t s_tile, s_wsum[8][3], s_base[3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(O.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t wbase = tile * IDX_TILE + warp * (32 * IDX_WORDS);
+    const uint32_t lt = (1u << lane) - 1u;
+
+    uint32_t key[IDX_WORDS], val[IDX_WORDS], cm[IDX_WORDS], sm[IDX_WORDS], rm[IDX_WORDS];
+    uint32_t pk = 0xffffffffu, pv = 0;            // element before the warp's first one
+    if (lane == 0 && wbase > 0 && wbase <= n) { pk = skey[wbase - 1]; pv = sval[wbase - 1]; }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int v0 = min(max(e0 - 1 + ((k >> 2) & 1), 0), g.S0 - 1);
-                const int v1 = min(max(e1 - 1 + ((k >> 1) & 1), 0), g.S1 - 1);
-                const int v2 = min(max(e2 - 1 + (k & 1), 0), g.S2 - 1);
-                const uint32_t v = ((uint32_t)v0 * (uint32_t)g.S1 + (uint32_t)v1) * (uint32_t)g.S2 + (uint32_t)v2;
-                atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+    for (int r = 0; r < IDX_WORDS; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        key[r] = i < n ? skey[i] : 0xffffffffu;
+        val[r] = i < n ? sval[i] : 0u;
+    }
+    uint32_t cw = 0, sw = 0, rw = 0;              // heads in this warp's 8 words
+#pragma unroll
+    for (int r = 0; r < IDX_WORDS; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        uint32_t kprev = __shfl_up_sync(FULL, key[r], 1), vprev = __shfl_up_sync(FULL, val[r], 1);
+        if (lane == 0) { kprev = pk; vprev = pv; }
+        pk = __shfl_sync(FULL, key[r], 31);       // (only lane 0's copy is used)
+        pv = __shfl_sync(FULL, val[r], 31);
+        const bool valid = key[r] < g.invalid;    // positions past n carry 0xffffffff
+        const bool chead = valid && (i == 0 || kprev != key[r]);
+        const bool shead = valid && (chead || (vprev >> pbits) != (val[r] >> pbits));
+        const bool rhead = valid && (chead || (i % CH) == 0);
+        cm[r] = __ballot_sync(FULL, chead);
+        sm[r] = __ballot_sync(FULL, shead);
+        rm[r] = __ballot_sync(FULL, rhead);
+        cw += __popc(cm[r]); sw += __popc(sm[r]); rw += __popc(rm[r]);
+    }
+    if (lane == 0) { s_wsum[warp][0] = cw; s_wsum[warp][1] = sw; s_wsum[warp][2] = rw; }
+    __syncthreads();
+    if (tid < 3) {
+        // tile total of counter `tid`, published; then the look-back for the tile's base rank
+        uint32_t total = 0;
+        for (int w = 0; w < 8; ++w) total += s_wsum[w][tid];
+        uint32_t *mine = O.state + (size_t)tile * 3 + tid;
+        *(volatile uint32_t *)mine = total | (tile == 0 ? IDX_PREFIX : IDX_AGG);
+        uint32_t prefix = 0;
+        if (tile > 0) {
+            int t = (int)tile - 1;
+            bool done = false;
+            while (!done) {
+                uint32_t st[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) st[q] = t - q >= 0 ? *(const volatile uint32_t *)(O.state + (size_t)(t - q) * 3 + tid) : IDX_PREFIX;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (done) break;
+                    if ((st[q] >> 30) == 0u) break;
+                    prefix += st[q] & IDX_MASK;
+                    --t;
+                    if ((st[q] >> 30) == 2u) done = true;
+                }
+            }
+            *(volatile uint32_t *)mine = (prefix + total) | IDX_PREFIX;
+        }
+        s_base[tid] = prefix;
+    }
+    __syncthreads();
+    uint32_t cb = s_base[0], sb = s_base[1], rb = s_base[2];      // ranks before this warp's first word
+    for (int w = 0; w < warp; ++w) { cb += s_wsum[w][0]; sb += s_wsum[w][1]; rb += s_wsum[w][2]; }
+
+#pragma unroll
+    for (int r = 0; r < IDX_WORDS; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        const uint32_t w = i >> 5;
+        if (lane == 0 && w <= (n >> 5)) { O.smask[w] = sm[r]; O.soff[w] = sb; O.roff[w] = rb; }
+        const bool valid = key[r] < g.invalid;
+        if (valid) {
+            const uint32_t crank = cb + __popc(cm[r] & lt), srank = sb + __popc(sm[r] & lt), rrank = rb + __popc(rm[r] & lt);
+            if ((sm[r] >> lane) & 1u) {
+                O.seg_start[srank] = i;
+                O.seg_frame[srank] = val[r] >> pbits;
+            }
+            if ((cm[r] >> lane) & 1u) {
+                const uint32_t k = key[r];
+                O.ucell[crank] = k;
+                if (O.ctab != nullptr) O.ctab[k] = (int)crank;
+                O.cstart[crank] = i;
+                O.cseg[crank] = srank;
+                O.crun[crank] = rrank;
+                const int e2 = (int)(k % (uint32_t)g.E2);
+                const uint32_t t = k / (uint32_t)g.E2;
+                const int e1 = (int)(t % (uint32_t)g.E1), e0 = (int)(t / (uint32_t)g.E1);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int v0 = min(max(e0 - 1 + ((q >> 2) & 1), 0), g.S0 - 1);
+                    const int v1 = min(max(e1 - 1 + ((q >> 1) & 1), 0), g.S1 - 1);
+                    const int v2 = min(max(e2 - 1 + (q & 1), 0), g.S2 - 1);
+                    const uint32_t v = ((uint32_t)v0 * (uint32_t)g.S1 + (uint32_t)v1) * (uint32_t)g.S2 + (uint32_t)v2;
+                    atomicOr(&O.bitmap[v >> 5], 1u << (v & 31));
+                }
             }
         }
-    }
-    if (nvalid > 0 && i == nvalid - 1) {
-        // totals and sentinels
-        const uint32_t lemask = lane == 31 ? 0xffffffffu : ((2u << lane) - 1u);
-        const uint32_t nc = coff[w] + __popc(cm & lemask), ns = soff[w] + __popc(sm & lemask);
-        uint32_t rm = cm;
-        if (((w << 5) % CH) == 0) rm |= 1u;
-        const uint32_t nr = roff[w] + __popc(rm & lemask);
-        counters[MB_CNT_CELLS] = nc;
-        counters[MB_CNT_SEGS] = ns;
-        counters[MB_CNT_RUNS] = nr;
-        cstart[nc] = nvalid;
-        cseg[nc] = ns;
-        crun[nc] = nr;
-        seg_start[ns] = nvalid;
+        // is position i the last valid one?  (the next key is invalid, or i is the last position)
+        {
+            uint32_t knext = __shfl_down_sync(FULL, key[r], 1);
+            const uint32_t nextfirst = __shfl_sync(FULL, key[r + 1 < IDX_WORDS ? r + 1 : r], 0);
+            bool is_last = false;
+            if (valid) {
+                if (i + 1 >= n) is_last = true;
+                else if (lane < 31) is_last = knext >= g.invalid;
+                else if (r + 1 < IDX_WORDS) is_last = nextfirst >= g.invalid;
+                else is_last = skey[i + 1] >= g.invalid;                 // next position belongs to another warp
+            }
+            if (is_last) {
+                const uint32_t le = lane == 31 ? 0xffffffffu : ((2u << lane) - 1u);
+                const uint32_t nc = cb + __popc(cm[r] & le), ns = sb + __popc(sm[r] & le), nr = rb + __popc(rm[r] & le);
+                O.counters[MB_CNT_NVALID] = i + 1;
+                O.counters[MB_CNT_CELLS] = nc;
+                O.counters[MB_CNT_SEGS] = ns;
+                O.counters[MB_CNT_RUNS] = nr;
+                O.cstart[nc] = i + 1;
+                O.cseg[nc] = ns;
+                O.crun[nc] = nr;
+                O.seg_start[ns] = i + 1;
+            }
+        }
+        cb += __popc(cm[r]); sb += __popc(sm[r]); rb += __popc(rm[r]);
     }
 }
 
@@ -535,7 +591,7 @@ __device__ __forceinline__ void row_store(float *p, const float (&src)[VEC])
 }
 
 template <int VEC, int IT, bool ONEHOT, int U>
-__global__ void __launch_bounds__(ACC_THREADS)
+__global__ void __launch_bounds__(ACC_THREADS, (VEC * IT <= 2 ? 5 : 1))
 k_cell_accumulate(const AccArgs A)
 {
     constexpr int NW = ACC_THREADS / 32;
@@ -865,7 +921,7 @@ struct CellBuffers {
     uint32_t *counters;
     uint4 *rec;
     uint32_t *keys_a, *keys_b, *pids_a, *pids_b;
-    uint32_t *cmask, *smask, *ccnt, *scnt, *rcnt, *coff, *soff, *roff;
+    uint32_t *smask, *soff, *roff, *idx_state;
     uint32_t *ucell, *cstart, *cseg, *crun, *seg_start, *seg_frame;
     float2 *segws;
     float *gcoef;
@@ -891,9 +947,8 @@ size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const Cel
     b.rec = a.take<uint4>(n);
     b.keys_a = a.take<uint32_t>(n); b.keys_b = a.take<uint32_t>(n);
     b.pids_a = a.take<uint32_t>(n); b.pids_b = a.take<uint32_t>(n);
-    b.cmask = a.take<uint32_t>(words); b.smask = a.take<uint32_t>(words);
-    b.ccnt = a.take<uint32_t>(words); b.scnt = a.take<uint32_t>(words); b.rcnt = a.take<uint32_t>(words);
-    b.coff = a.take<uint32_t>(words); b.soff = a.take<uint32_t>(words); b.roff = a.take<uint32_t>(words);
+    b.smask = a.take<uint32_t>(words); b.soff = a.take<uint32_t>(words); b.roff = a.take<uint32_t>(words);
+    b.idx_state = a.take<uint32_t>(((size_t)n + IDX_TILE - 1) / IDX_TILE * 3 + 8);
     b.ucell = a.take<uint32_t>(ncap + 1); b.cstart = a.take<uint32_t>(ncap + 1);
     b.cseg = a.take<uint32_t>(ncap + 1); b.crun = a.take<uint32_t>(ncap + 1);
     b.seg_start = a.take<uint32_t>((size_t)n + 1); b.seg_frame = a.take<uint32_t>((size_t)n + 1);
@@ -959,7 +1014,7 @@ int dispatch_accumulate(cudaStream_t stream, const AccArgs &A, int vec, int it)
 #define MB_ACC(V, I, UU)                                                              \
     if (vec == V && it == I)                                                          \
         return oh ? launch_accumulate<V, I, true, UU>(stream, A) : launch_accumulate<V, I, false, UU>(stream, A)
-    MB_ACC(1, 1, 8); MB_ACC(1, 2, 4); MB_ACC(2, 1, 8); MB_ACC(2, 2, 4); MB_ACC(4, 1, 4); MB_ACC(4, 2, 2);
+    MB_ACC(1, 1, 8); MB_ACC(1, 2, 4); MB_ACC(2, 1, 4); MB_ACC(2, 2, 4); MB_ACC(4, 1, 4); MB_ACC(4, 2, 2);
 #undef MB_ACC
     mb_set_error("internal: no accumulate kernel for vec %d it %d", vec, it);
     return MB_ERR_ARG;
@@ -1093,7 +1148,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     CellBuffers b;
     MB_REQUIRE(carve_cells(b, workspace, workspace_bytes, n, g) + 512 <= workspace_bytes, "batch workspace too small");
     const size_t V = (size_t)g.S0 * g.S1 * g.S2;
-    const uint32_t words = n / 32 + 1, vwords = (uint32_t)(V / 32 + 1);
+    const uint32_t vwords = (uint32_t)(V / 32 + 1);
     int vec, it;
     pick_vec(features, map, b.P, F, vec, it);
     const size_t run_cap_sz = b.P_floats / ((size_t)8 * F);
@@ -1125,18 +1180,17 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     if ((rc = stage_mark(stream, 2))) return rc;
     MB_CHECK_CUDA(cudaMemsetAsync(b.bitmap, 0, (size_t)vwords * sizeof(uint32_t), stream));
     if (b.ctab) MB_CHECK_CUDA(cudaMemsetAsync(b.ctab, 0xff, (size_t)g.invalid * sizeof(int), stream));
-    const unsigned nblk = (unsigned)(((size_t)words * 32 + 255) / 256);
-    k_cell_flags<<<nblk, 256, 0, stream>>>(skey, sval, n, pbits, g.invalid, b.cmask, b.smask, b.ccnt, b.scnt, b.rcnt,
-                                           b.counters);
-    MB_LAUNCHED();
-    if ((rc = mb_exclusive_scan_u32(stream, b.ccnt, b.coff, words, b.scan_ws, b.scan_bytes))) return rc;
-    if ((rc = mb_exclusive_scan_u32(stream, b.scnt, b.soff, words, b.scan_ws, b.scan_bytes))) return rc;
-    if ((rc = mb_exclusive_scan_u32(stream, b.rcnt, b.roff, words, b.scan_ws, b.scan_bytes))) return rc;
-    // K3
-    k_cell_emit<<<(n + 255) / 256, 256, 0, stream>>>(skey, sval, n, pbits, g, b.cmask, b.smask, b.coff, b.soff, b.roff,
-                                                     b.ucell, b.cstart, b.cseg, b.crun, b.seg_start, b.seg_frame,
-                                                     b.bitmap, b.ctab, b.counters);
-    MB_LAUNCHED();
+    {
+        const uint32_t itiles = (n + IDX_TILE - 1) / IDX_TILE;
+        MB_CHECK_CUDA(cudaMemsetAsync(b.idx_state, 0, ((size_t)itiles * 3 + 4) * sizeof(uint32_t), stream));
+        IndexOut O;
+        O.smask = b.smask; O.soff = b.soff; O.roff = b.roff;
+        O.ucell = b.ucell; O.cstart = b.cstart; O.cseg = b.cseg; O.crun = b.crun;
+        O.seg_start = b.seg_start; O.seg_frame = b.seg_frame; O.bitmap = b.bitmap; O.ctab = b.ctab;
+        O.counters = b.counters; O.state = b.idx_state + 4; O.ticket = b.idx_state;
+        k_cell_index<<<itiles, 256, 0, stream>>>(skey, sval, n, pbits, g, O);
+        MB_LAUNCHED();
+    }
     // K4
     k_vox_count<<<(vwords + 255) / 256, 256, 0, stream>>>(b.bitmap, vwords, b.vcnt);
     MB_LAUNCHED();

@@ -169,7 +169,7 @@ k_radix_bases(uint32_t *__restrict__ ghist)
     ghist[blockIdx.x * 256 + threadIdx.x] = e;
 }
 
-__global__ void __launch_bounds__(OS_THREADS)
+__global__ void __launch_bounds__(OS_THREADS, 4)
 k_radix_onesweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                  uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, int shift,
                  const uint32_t *__restrict__ gbase, uint32_t *state, uint32_t *ticket, int vals_iota)
@@ -188,13 +188,12 @@ k_radix_onesweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restric
     const uint32_t tile_n = min((uint32_t)OS_TILE, n - tbase);
 
     const uint32_t wbase = tbase + warp * (32 * OS_ITEMS);
-    uint32_t k[OS_ITEMS], v[OS_ITEMS], rk[OS_ITEMS];
+    uint32_t k[OS_ITEMS];
+    uint32_t rk2[OS_ITEMS / 2];                 // ranks inside (warp, digit), two 16-bit values per register
 #pragma unroll
     for (int r = 0; r < OS_ITEMS; ++r) {
         const uint32_t idx = wbase + r * 32 + lane;
-        const bool valid = idx < n;
-        k[r] = valid ? keys_in[idx] : 0xffffffffu;
-        v[r] = valid ? (vals_iota ? idx : vals_in[idx]) : 0u;
+        k[r] = idx < n ? keys_in[idx] : 0xffffffffu;
     }
 #pragma unroll
     for (int r = 0; r < OS_ITEMS; ++r) {
@@ -207,7 +206,7 @@ k_radix_onesweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restric
         __syncwarp();
         if (valid && rank == 0) wcnt[warp][d] = prev + __popc(m);
         __syncwarp();
-        rk[r] = prev + rank;
+        if (r & 1) rk2[r >> 1] |= (prev + rank) << 16; else rk2[r >> 1] = prev + rank;
     }
     __syncthreads();
     // thread d: digit d's count in this tile, exclusive offsets of the warps inside the digit
@@ -220,35 +219,42 @@ k_radix_onesweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restric
     }
     // publish the tile's digit count, then look back for the digit's count in all preceding tiles
     uint32_t *mine = state + (size_t)tile * R + tid;
-    if (tile == 0) {
-        *(volatile uint32_t *)mine = count | OS_FLAG_PREFIX;
-    } else {
-        *(volatile uint32_t *)mine = count | OS_FLAG_AGG;
-    }
+    *(volatile uint32_t *)mine = count | (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG);
     uint32_t total;
     const uint32_t dstart = block_exclusive_scan(count, &total);
     s_dstart[tid] = dstart;
     uint32_t prefix = 0;
     if (tile > 0) {
-        for (int t = (int)tile - 1; t >= 0; --t) {
-            const volatile uint32_t *p = state + (size_t)t * R + tid;
-            uint32_t st;
-            do { st = *p; } while ((st >> 30) == 0u);
-            prefix += st & OS_VALUE_MASK;
-            if ((st >> 30) == 2u) break;
+        // four predecessors per round trip; stop at the first one that already knows its prefix
+        int t = (int)tile - 1;
+        bool done = false;
+        while (!done) {
+            uint32_t st[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) st[q] = t - q >= 0 ? *(const volatile uint32_t *)(state + (size_t)(t - q) * R + tid) : OS_FLAG_PREFIX;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (done) break;
+                if ((st[q] >> 30) == 0u) break;            // not published yet: poll again from this tile
+                prefix += st[q] & OS_VALUE_MASK;
+                --t;
+                if ((st[q] >> 30) == 2u) done = true;
+            }
         }
         *(volatile uint32_t *)mine = (prefix + count) | OS_FLAG_PREFIX;
     }
     s_gpos[tid] = gbase[tid] + prefix;
     __syncthreads();
-    // stage in sorted order
+    // stage in sorted order (values are loaded only now: fewer live registers while ranking)
 #pragma unroll
     for (int r = 0; r < OS_ITEMS; ++r) {
-        if (wbase + r * 32 + lane < n) {
+        const uint32_t idx = wbase + r * 32 + lane;
+        if (idx < n) {
             const uint32_t d = (k[r] >> shift) & (R - 1);
-            const uint32_t lp = s_dstart[d] + wcnt[warp][d] + rk[r];
+            const uint32_t rank = (r & 1) ? (rk2[r >> 1] >> 16) : (rk2[r >> 1] & 0xffffu);
+            const uint32_t lp = s_dstart[d] + wcnt[warp][d] + rank;
             s_key[lp] = k[r];
-            s_val[lp] = v[r];
+            s_val[lp] = vals_iota ? idx : vals_in[idx];
         }
     }
     __syncthreads();
