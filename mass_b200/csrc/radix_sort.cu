@@ -4,7 +4,7 @@
 // reproduce the reference's summation order (slot-major, then pixel order:
 // /root/reference/mass/utils/projection.py:294-298, 319-323, 349-351) without float atomics.
 //
-// 8-bit digits, one sweep over the data per pass (see k_radix_onesweep below).  Inside a tile each warp
+// 8-bit digits, one contiguous block of the input per resident CTA (see below).  Inside a tile each warp
 // owns 512 consecutive elements and ranks them in 16 rounds of 32 with match.any, so the order
 // (tile, warp, round, lane) is the input order.
 #include "common.cuh"
@@ -101,34 +101,34 @@ k_scan_apply(const uint32_t *in, uint32_t *out, uint32_t n, const uint32_t *__re
 }
 
 // ---------------------------------------------------------------------------------------------
-// Radix sort, 8 bits per pass, one sweep over the data per pass ("onesweep"):
-//   k_radix_hist_all   one read of the keys -> global digit histograms of ALL passes
-//   k_radix_bases      exclusive scan of each pass's 256 counts
-//   k_radix_onesweep   per pass: a tile of 4096 pairs is ranked inside the CTA (match.any per warp round,
-//                      per-warp digit counters), the tile's position inside every digit comes from a
-//                      decoupled look-back over the preceding tiles' digit counts (tiles take their index
-//                      from a ticket, so a tile only ever waits for tiles that started before it), the
-//                      pairs are staged through shared memory in sorted order and written out coalesced.
-// Stable: the global order inside a digit is (tile, warp, round, lane) = the input order.
+// Radix sort, 8 bits per pass.  The input is cut into one contiguous block per resident CTA (148 SMs x 4);
+// per pass:
+//   k_radix_block_hist     each CTA counts the digits of its block (runs of equal digits are merged before
+//                          they touch the shared-memory histogram) -> table [digit][block]
+//   exclusive scan of the table (digit-major): the global position of every (digit, block)
+//   k_radix_block_scatter  each CTA walks its block tile by tile (4096 pairs): ranks the tile (match.any per
+//                          warp round, per-warp digit counters), stages the pairs through shared memory in
+//                          sorted order and writes them out coalesced, carrying the running position of
+//                          every digit in shared memory.
+// No CTA ever waits for another one.  Stable: the global order inside a digit is (block, tile, warp, round,
+// lane) = the input order.
 constexpr int OS_ITEMS = 16;
 constexpr int OS_THREADS = 256;
 constexpr int OS_TILE = OS_THREADS * OS_ITEMS;
-constexpr uint32_t OS_FLAG_AGG = 1u << 30, OS_FLAG_PREFIX = 2u << 30, OS_VALUE_MASK = (1u << 30) - 1u;
+constexpr int OS_BLOCKS = MB_NUM_SMS * 2;
 
-// Each thread takes 16 consecutive keys and merges runs of equal digits before touching the shared
-// histogram: neighbouring keys mostly share their digits (neighbouring pixels fall into the same cell),
-// and the lanes of a warp are 16 keys apart, so same-address conflicts are rare.
 __global__ void __launch_bounds__(256)
-k_radix_hist_all(const uint32_t *__restrict__ keys, uint32_t n, int passes, uint32_t *__restrict__ ghist)
+k_radix_block_hist(const uint32_t *__restrict__ keys, uint32_t n, uint32_t per_block, int shift,
+                   uint32_t *__restrict__ table)
 {
-    __shared__ uint32_t h[4][256];
-    for (int i = threadIdx.x; i < 4 * 256; i += 256) (&h[0][0])[i] = 0;
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t ngroups = (n + 15u) / 16u;
-    for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += gridDim.x * blockDim.x) {
+    const uint32_t beg = min(n, blockIdx.x * per_block), end = min(n, beg + per_block);
+    // each thread takes 16 consecutive keys (per_block and beg are multiples of 4096)
+    for (uint32_t base = beg + threadIdx.x * 16u; base < end; base += 256u * 16u) {
         uint32_t k[16];
-        const uint32_t base = gi * 16u;
-        if (base + 16u <= n) {
+        if (base + 16u <= end) {
             const uint4 *p = (const uint4 *)(keys + base);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -137,133 +137,129 @@ k_radix_hist_all(const uint32_t *__restrict__ keys, uint32_t n, int passes, uint
             }
         } else {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) k[q] = base + q < n ? keys[base + q] : 0xffffffffu;
+            for (int q = 0; q < 16; ++q) k[q] = base + q < end ? keys[base + q] : 0u;
         }
-        const int cnt = (int)min(16u, n - base);
-        for (int p = 0; p < passes; ++p) {
-            uint32_t cur = (k[0] >> (8 * p)) & 255u, run = 0;
+        const int cnt = (int)min(16u, end - base);
+        uint32_t cur = (k[0] >> shift) & 255u, run = 0;
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                if (q < cnt) {
-                    const uint32_t d = (k[q] >> (8 * p)) & 255u;
-                    if (d != cur) { atomicAdd(&h[p][cur], run); cur = d; run = 0; }
-                    ++run;
-                }
+        for (int q = 0; q < 16; ++q) {
+            if (q < cnt) {
+                const uint32_t d = (k[q] >> shift) & 255u;
+                if (d != cur) { atomicAdd(&h[cur], run); cur = d; run = 0; }
+                ++run;
             }
-            atomicAdd(&h[p][cur], run);
         }
+        atomicAdd(&h[cur], run);
     }
     __syncthreads();
-    for (int p = 0; p < passes; ++p) {
-        const uint32_t c = h[p][threadIdx.x];
-        if (c) atomicAdd(&ghist[p * 256 + threadIdx.x], c);
-    }
+    table[threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];      // digit-major
 }
 
-__global__ void __launch_bounds__(256)
-k_radix_bases(uint32_t *__restrict__ ghist)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 {
-    uint32_t total;
-    const uint32_t v = ghist[blockIdx.x * 256 + threadIdx.x];
-    const uint32_t e = block_exclusive_scan(v, &total);
-    ghist[blockIdx.x * 256 + threadIdx.x] = e;
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-__global__ void __launch_bounds__(OS_THREADS, 4)
-k_radix_onesweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, int shift,
-                 const uint32_t *__restrict__ gbase, uint32_t *state, uint32_t *ticket, int vals_iota)
+// Shared memory of k_radix_block_scatter (dynamic): two input buffers of one tile each (keys, values),
+// filled by cp.async one tile ahead of the tile being ranked, and the sorted staging area.
+struct ScatterSmem {
+    uint32_t in_key[2][OS_TILE], in_val[2][OS_TILE];
+    uint32_t s_key[OS_TILE], s_val[OS_TILE];
+    uint32_t wcnt[OS_THREADS / 32][256];
+    uint32_t s_dstart[256], s_gpos[256];
+};
+
+__global__ void __launch_bounds__(OS_THREADS, 2)
+k_radix_block_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, uint32_t per_block,
+                      int shift, const uint32_t *__restrict__ table, int vals_iota)
 {
     constexpr int R = 256, WARPS = OS_THREADS / 32;
-    __shared__ uint32_t s_key[OS_TILE], s_val[OS_TILE];
-    __shared__ uint32_t wcnt[WARPS][R];
-    __shared__ uint32_t s_dstart[R], s_gpos[R];
-    __shared__ uint32_t s_tile;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScatterSmem &S = *reinterpret_cast<ScatterSmem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < WARPS * R; i += OS_THREADS) (&wcnt[0][0])[i] = 0;
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint32_t tbase = tile * OS_TILE;
-    const uint32_t tile_n = min((uint32_t)OS_TILE, n - tbase);
+    const uint32_t beg = min(n, blockIdx.x * per_block), end = min(n, beg + per_block);
+    S.s_gpos[tid] = table[tid * gridDim.x + blockIdx.x];
 
-    const uint32_t wbase = tbase + warp * (32 * OS_ITEMS);
-    uint32_t k[OS_ITEMS];
-    uint32_t rk2[OS_ITEMS / 2];                 // ranks inside (warp, digit), two 16-bit values per register
-#pragma unroll
-    for (int r = 0; r < OS_ITEMS; ++r) {
-        const uint32_t idx = wbase + r * 32 + lane;
-        k[r] = idx < n ? keys_in[idx] : 0xffffffffu;
-    }
-#pragma unroll
-    for (int r = 0; r < OS_ITEMS; ++r) {
-        const bool valid = wbase + r * 32 + lane < n;
-        const uint32_t d = (k[r] >> shift) & (R - 1);
-        // out-of-range lanes get a private pseudo-digit so they never join a real group
-        const uint32_t m = __match_any_sync(0xffffffffu, valid ? d : (R + lane));
-        const uint32_t rank = __popc(m & ((1u << lane) - 1u));
-        const uint32_t prev = valid ? wcnt[warp][d] : 0u;
-        __syncwarp();
-        if (valid && rank == 0) wcnt[warp][d] = prev + __popc(m);
-        __syncwarp();
-        if (r & 1) rk2[r >> 1] |= (prev + rank) << 16; else rk2[r >> 1] = prev + rank;
-    }
-    __syncthreads();
-    // thread d: digit d's count in this tile, exclusive offsets of the warps inside the digit
-    uint32_t count = 0;
-#pragma unroll
-    for (int w = 0; w < WARPS; ++w) {
-        const uint32_t c = wcnt[w][tid];
-        wcnt[w][tid] = count;
-        count += c;
-    }
-    // publish the tile's digit count, then look back for the digit's count in all preceding tiles
-    uint32_t *mine = state + (size_t)tile * R + tid;
-    *(volatile uint32_t *)mine = count | (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG);
-    uint32_t total;
-    const uint32_t dstart = block_exclusive_scan(count, &total);
-    s_dstart[tid] = dstart;
-    uint32_t prefix = 0;
-    if (tile > 0) {
-        // four predecessors per round trip; stop at the first one that already knows its prefix
-        int t = (int)tile - 1;
-        bool done = false;
-        while (!done) {
-            uint32_t st[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) st[q] = t - q >= 0 ? *(const volatile uint32_t *)(state + (size_t)(t - q) * R + tid) : OS_FLAG_PREFIX;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (done) break;
-                if ((st[q] >> 30) == 0u) break;            // not published yet: poll again from this tile
-                prefix += st[q] & OS_VALUE_MASK;
-                --t;
-                if ((st[q] >> 30) == 2u) done = true;
+    // a tile is fetched in 16-byte pieces (beg is a multiple of the tile; the array tails are padded by the
+    // allocation: pieces that start before `end` are always in bounds of a 16-byte aligned buffer)
+    auto fetch = [&](uint32_t tbase, int buf) {
+        for (int c = tid; c < OS_TILE / 4; c += OS_THREADS) {
+            const uint32_t idx = tbase + 4u * c;
+            if (idx < end) {
+                cp_async16(&S.in_key[buf][4 * c], keys_in + idx);
+                if (!vals_iota) cp_async16(&S.in_val[buf][4 * c], vals_in + idx);
             }
         }
-        *(volatile uint32_t *)mine = (prefix + count) | OS_FLAG_PREFIX;
-    }
-    s_gpos[tid] = gbase[tid] + prefix;
-    __syncthreads();
-    // stage in sorted order (values are loaded only now: fewer live registers while ranking)
+        cp_async_commit();
+    };
+    if (beg < end) fetch(beg, 0);
+    int buf = 0;
+    for (uint32_t tbase = beg; tbase < end; tbase += OS_TILE, buf ^= 1) {
+        for (int i = tid; i < WARPS * R; i += OS_THREADS) (&S.wcnt[0][0])[i] = 0;
+        cp_async_wait_all();
+        __syncthreads();                          // this tile's input is in shared memory; staging area is free
+        if (tbase + OS_TILE < end) fetch(tbase + OS_TILE, buf ^ 1);      // next tile, while this one is ranked
+        const uint32_t tile_n = min((uint32_t)OS_TILE, end - tbase);
+        const uint32_t wloc = warp * (32 * OS_ITEMS);
+        uint32_t k[OS_ITEMS];
+        uint32_t rk2[OS_ITEMS / 2];             // ranks inside (warp, digit), two 16-bit values per register
 #pragma unroll
-    for (int r = 0; r < OS_ITEMS; ++r) {
-        const uint32_t idx = wbase + r * 32 + lane;
-        if (idx < n) {
-            const uint32_t d = (k[r] >> shift) & (R - 1);
-            const uint32_t rank = (r & 1) ? (rk2[r >> 1] >> 16) : (rk2[r >> 1] & 0xffffu);
-            const uint32_t lp = s_dstart[d] + wcnt[warp][d] + rank;
-            s_key[lp] = k[r];
-            s_val[lp] = vals_iota ? idx : vals_in[idx];
+        for (int r = 0; r < OS_ITEMS; ++r) {
+            const uint32_t loc = wloc + r * 32 + lane;
+            k[r] = loc < tile_n ? S.in_key[buf][loc] : 0xffffffffu;
         }
-    }
-    __syncthreads();
-    for (uint32_t i = tid; i < tile_n; i += OS_THREADS) {
-        const uint32_t key = s_key[i];
-        const uint32_t d = (key >> shift) & (R - 1);
-        const uint32_t pos = s_gpos[d] + (i - s_dstart[d]);
-        keys_out[pos] = key;
-        vals_out[pos] = s_val[i];
+#pragma unroll
+        for (int r = 0; r < OS_ITEMS; ++r) {
+            const bool valid = wloc + r * 32 + lane < tile_n;
+            const uint32_t d = (k[r] >> shift) & (R - 1);
+            // out-of-range lanes get a private pseudo-digit so they never join a real group
+            const uint32_t m = __match_any_sync(0xffffffffu, valid ? d : (R + lane));
+            const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+            const uint32_t prev = valid ? S.wcnt[warp][d] : 0u;
+            __syncwarp();
+            if (valid && rank == 0) S.wcnt[warp][d] = prev + __popc(m);
+            __syncwarp();
+            if (r & 1) rk2[r >> 1] |= (prev + rank) << 16; else rk2[r >> 1] = prev + rank;
+        }
+        __syncthreads();
+        // thread d: digit d's count in this tile, exclusive offsets of the warps inside the digit
+        uint32_t count = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t c = S.wcnt[w][tid];
+            S.wcnt[w][tid] = count;
+            count += c;
+        }
+        uint32_t total;
+        const uint32_t dstart = block_exclusive_scan(count, &total);
+        S.s_dstart[tid] = dstart;
+        __syncthreads();
+        // stage in sorted order
+#pragma unroll
+        for (int r = 0; r < OS_ITEMS; ++r) {
+            const uint32_t loc = wloc + r * 32 + lane;
+            if (loc < tile_n) {
+                const uint32_t d = (k[r] >> shift) & (R - 1);
+                const uint32_t rank = (r & 1) ? (rk2[r >> 1] >> 16) : (rk2[r >> 1] & 0xffffu);
+                const uint32_t lp = S.s_dstart[d] + S.wcnt[warp][d] + rank;
+                S.s_key[lp] = k[r];
+                S.s_val[lp] = vals_iota ? tbase + loc : S.in_val[buf][loc];
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < tile_n; i += OS_THREADS) {
+            const uint32_t key = S.s_key[i];
+            const uint32_t d = (key >> shift) & (R - 1);
+            const uint32_t pos = S.s_gpos[d] + (i - S.s_dstart[d]);
+            keys_out[pos] = key;
+            vals_out[pos] = S.s_val[i];
+        }
+        __syncthreads();
+        S.s_gpos[tid] += count;                  // running position of digit `tid` inside this block
     }
 }
 
@@ -292,9 +288,9 @@ int mb_exclusive_scan_u32(cudaStream_t stream, const uint32_t *in, uint32_t *out
 
 size_t mb_sort_workspace_bytes(uint32_t n)
 {
-    const size_t ntiles = ((size_t)n + OS_TILE - 1) / OS_TILE;
-    // [4 passes][256] digit histograms, 4 tickets, [4 passes][ntiles][256] look-back states
-    return mb_align_up((4 * 256 + 64) * sizeof(uint32_t)) + mb_align_up(4 * ntiles * 256 * sizeof(uint32_t)) + 256;
+    (void)n;
+    const size_t table = (size_t)256 * OS_BLOCKS;
+    return mb_align_up(table * sizeof(uint32_t)) + mb_scan_workspace_bytes((uint32_t)table) + 256;
 }
 
 int mb_sort_pairs(cudaStream_t stream, uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b,
@@ -305,30 +301,30 @@ int mb_sort_pairs(cudaStream_t stream, uint32_t *keys_a, uint32_t *vals_a, uint3
     *vals_out = vals_a;
     if (n == 0) return MB_OK;
     MB_REQUIRE(n_dev == nullptr, "mb_sort_pairs: device-side counts are not supported");
-    MB_REQUIRE(n < (1u << 30), "mb_sort_pairs: too many elements");
     MB_REQUIRE(workspace_bytes >= mb_sort_workspace_bytes(n), "sort workspace too small");
     const int passes = (key_bits + 7) / 8;
     MB_REQUIRE(passes >= 1 && passes <= 4, "mb_sort_pairs: bad key width");
     const size_t ntiles = ((size_t)n + OS_TILE - 1) / OS_TILE;
+    int blocks = ntiles < (size_t)OS_BLOCKS ? (int)ntiles : OS_BLOCKS;
+    const uint32_t per_block = (uint32_t)((ntiles + blocks - 1) / blocks) * OS_TILE;      // a multiple of the tile
+    blocks = (int)(((size_t)n + per_block - 1) / per_block);
+    MB_CHECK_CUDA(cudaFuncSetAttribute(k_radix_block_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ScatterSmem)));
     MbArena arena(workspace, workspace_bytes);
-    uint32_t *head = arena.take<uint32_t>(4 * 256 + 64);      // histograms, then the tickets
-    uint32_t *ghist = head, *tickets = head + 4 * 256;
-    uint32_t *state = arena.take<uint32_t>(4 * ntiles * 256);
-    MB_CHECK_CUDA(cudaMemsetAsync(head, 0, (4 * 256 + 64) * sizeof(uint32_t), stream));
-    MB_CHECK_CUDA(cudaMemsetAsync(state, 0, (size_t)passes * ntiles * 256 * sizeof(uint32_t), stream));
-    size_t hblocks = ((size_t)n + 256 * 16 - 1) / (256 * 16);
-    if (hblocks > (size_t)MB_NUM_SMS * 8) hblocks = (size_t)MB_NUM_SMS * 8;
-    k_radix_hist_all<<<(unsigned)hblocks, 256, 0, stream>>>(keys_a, n, passes, ghist);
-    MB_LAUNCHED();
-    k_radix_bases<<<passes, 256, 0, stream>>>(ghist);
-    MB_LAUNCHED();
+    const uint32_t table_n = 256u * (uint32_t)blocks;
+    uint32_t *table = arena.take<uint32_t>((size_t)256 * OS_BLOCKS);
+    const size_t scan_bytes = mb_scan_workspace_bytes(256u * OS_BLOCKS);
+    char *scan_ws = arena.take<char>(scan_bytes);
 
     uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
     bool iota = vals_a_is_iota;
     for (int p = 0; p < passes; ++p) {
-        k_radix_onesweep<<<(unsigned)ntiles, OS_THREADS, 0, stream>>>(kin, vin, kout, vout, n, 8 * p, ghist + p * 256,
-                                                                    state + (size_t)p * ntiles * 256, tickets + p,
-                                                                    iota ? 1 : 0);
+        k_radix_block_hist<<<blocks, 256, 0, stream>>>(kin, n, per_block, 8 * p, table);
+        MB_LAUNCHED();
+        int rc = mb_exclusive_scan_u32(stream, table, table, table_n, scan_ws, scan_bytes);
+        if (rc) return rc;
+        k_radix_block_scatter<<<blocks, OS_THREADS, sizeof(ScatterSmem), stream>>>(kin, vin, kout, vout, n, per_block,
+                                                                                   8 * p, table, iota ? 1 : 0);
         MB_LAUNCHED();
         iota = false;
         uint32_t *t;
