@@ -44,8 +44,8 @@ C2_TOUCHED_PER_FRAME = 22243.0
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_cell_accumulate launch on this workload, from the
 # committed ncu --set full capture named below (per launch, like the achieved figure)
-ACCUMULATE_DRAM_BYTES_PER_LAUNCH = 7758.4e6 + 317.8e6
-ACCUMULATE_TRAFFIC_SOURCE = "profiles/r01k_kernels.txt"
+ACCUMULATE_DRAM_BYTES_PER_LAUNCH = 8055.4e6 + 346.7e6
+ACCUMULATE_TRAFFIC_SOURCE = "profiles/r01p_kernels.txt"
 
 
 def algorithmic_bytes_per_frame(h, w, fh, fw, F, touched):
