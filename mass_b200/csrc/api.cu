@@ -191,8 +191,10 @@ MB_API size_t mb_layer_update_workspace_bytes(int H, int W, int nx, int ny, int 
         if (v >= 1 && v <= MB_MAX_CHUNK_FRAMES) limit = v;
     }
     int chunk = T < limit ? T : limit;
-    while (chunk > 1 && (uint64_t)chunk * npix >= 0x7fffffffull) chunk /= 2;
-    return mbk_batch_workspace_bytes(npix, nx, ny, nz, chunk, F);
+    const int most = mbk_batch_max_chunk_frames(H, W);
+    if (chunk > most) chunk = most;
+    if (chunk < 1) return 0;
+    return mbk_batch_workspace_bytes(H, W, nx, ny, nz, chunk, F);
 }
 
 MB_API size_t mb_layer_update_min_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int F, int mode)
@@ -200,8 +202,8 @@ MB_API size_t mb_layer_update_min_workspace_bytes(int H, int W, int nx, int ny, 
     if (H <= 0 || W <= 0 || T <= 0 || F <= 0 || nx < 2 || ny < 2 || nz < 2) return 256;
     const uint32_t npix = (uint32_t)H * (uint32_t)W;
     if (mode == MB_MODE_EXACT) return splat_workspace_bytes(npix);
-    if ((uint64_t)T * npix >= 0x7fffffffull || T > MB_MAX_CHUNK_FRAMES) return 0;          // never fits one chunk
-    return mbk_batch_min_workspace_bytes(npix, nx, ny, nz, T, F);
+    if (T > mbk_batch_max_chunk_frames(H, W)) return 0;          // never fits one chunk
+    return mbk_batch_min_workspace_bytes(H, W, nx, ny, nz, T, F);
 }
 
 static int layer_update(void *stream_, const float *rays, const float *depth, const float *features,
@@ -230,9 +232,9 @@ static int layer_update(void *stream_, const float *rays, const float *depth, co
     const size_t feat_stride = (size_t)fh * fw * F;
     if (mode == MB_MODE_FAST) {
         // batched cell pipeline, as many frames per chunk as the workspace holds
-        const int chunk = workspace ? mbk_batch_frames_that_fit(npix, nx, ny, nz, F, workspace_bytes, T) : 0;
+        const int chunk = workspace ? mbk_batch_frames_that_fit(H, W, nx, ny, nz, F, workspace_bytes, T) : 0;
         MB_REQUIRE(chunk >= 1, "mb_layer_update: workspace too small (%zu < %zu)", workspace_bytes,
-                   mbk_batch_workspace_bytes(npix, nx, ny, nz, 1, F));
+                   mbk_batch_workspace_bytes(H, W, nx, ny, nz, 1, F));
         for (int t = 0; t < T; t += chunk) {
             const int n = T - t < chunk ? T - t : chunk;
             int rc = mbk_batch_update(stream, rays, depth + (size_t)t * npix,

@@ -36,7 +36,6 @@
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int CH = 256;                  // sorted positions per accumulate task; runs never cross a task
 constexpr int ACC_THREADS = 256;
 
 // Cells live on the map grid extended by one at the low end of each axis: a pixel in voxel 0 with
@@ -64,7 +63,7 @@ __device__ __forceinline__ uint32_t cell_key(const CellGrid &g, int e0, int e1, 
 // the 8 splat weights of a pixel, slot k = (d0 << 2) | (d1 << 1) | d2 (projection.py:300-323)
 __device__ __forceinline__ void splat_weights(const uint4 &rec, float (&w)[8])
 {
-    const float q[3] = { __uint_as_float(rec.y), __uint_as_float(rec.z), __uint_as_float(rec.w) };
+    const float q[3] = { __uint_as_float(rec.x), __uint_as_float(rec.y), __uint_as_float(rec.z) };
     float wl[3], wu[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -110,55 +109,207 @@ __device__ __forceinline__ int find_cell(const uint32_t *__restrict__ ucell, uin
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: grid = (pixel blocks, frames)
-__global__ void __launch_bounds__(256)
-k_cell_voxelise(const float *__restrict__ rays, const float *__restrict__ depth, const float *__restrict__ pose,
-                uint32_t npix, const float *__restrict__ bins_x, int nx, const float *__restrict__ bins_y, int ny,
-                const float *__restrict__ bins_z, int nz, CellGrid g, float min_d, float max_d,
-                uint4 *__restrict__ rec, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, int pbits,
-                uint32_t *__restrict__ counters)
+// K1: one CTA per 32 x 32 pixel tile of one frame: voxelise its 1024 pixels, then group them by cell inside
+// shared memory.  Neighbouring pixels fall into the same cell (a (cell, frame) segment averages ~4 pixels),
+// so what leaves the tile is an ITEM list -- (cell key, tile, first slot, length <= 16) -- a few times
+// shorter than the pixel list; the pixel records are written in grouped order, so an item's pixels are
+// contiguous.  Grouping: the tile's distinct keys go into a 2048-slot hash table (atomicCAS), the pixels
+// are ranked inside their slot with the radix machinery (match.any per warp round, per-warp counters, fixed
+// (warp, round, lane) order), slots are laid out by a block scan.  Which slot a key gets is a race, so
+// the ORDER OF GROUPS inside a tile may differ run to run; nothing downstream depends on it (items are
+// sorted by cell key, and a cell has one group per tile).
+//   item value = tile << 14 | first slot << 4 | (length - 1);  pixel record = {ratio0, ratio1, ratio2, pixel in tile}
+constexpr int TILE_DIM = 32, TILE_PIX = TILE_DIM * TILE_DIM;
+constexpr int HASH_SLOTS = 2048;
+constexpr int ITEM_MAX = 16;                     // pixels per item
+constexpr uint32_t HASH_EMPTY = 0xffffffffu;
+constexpr int TASK_ITEMS = 64;                   // items per accumulate task; runs never cross a task
+
+struct TileGeom {
+    int H, W;                // camera
+    int tiles_x, tpf;        // tiles per image row, tiles per frame
+};
+
+__host__ __device__ inline TileGeom make_tiles(int H, int W)
 {
-    __shared__ float P[12], spacing[6];
-    const uint32_t t = blockIdx.y;
-    if (threadIdx.x < 12) P[threadIdx.x] = pose[(size_t)t * 12 + threadIdx.x];
-    if (threadIdx.x >= 32 && threadIdx.x < 35) {
-        const int a = threadIdx.x - 32;
+    TileGeom t;
+    t.H = H; t.W = W;
+    t.tiles_x = (W + TILE_DIM - 1) / TILE_DIM;
+    t.tpf = t.tiles_x * ((H + TILE_DIM - 1) / TILE_DIM);
+    return t;
+}
+
+struct TileSmem {
+    uint32_t hkey[HASH_SLOTS];
+    uint16_t hcnt[8][HASH_SLOTS];                // per warp: pixels of the slot seen so far / exclusive warp offsets
+    uint16_t gstart[HASH_SLOTS], istart[HASH_SLOTS], total[HASH_SLOTS];
+    uint32_t warp_sum[8];
+    float P[12], spacing[6];
+};
+
+__global__ void __launch_bounds__(256)
+k_tile_voxelise(const float *__restrict__ rays, const float *__restrict__ depth, const float *__restrict__ pose,
+                TileGeom tg, const float *__restrict__ bins_x, int nx, const float *__restrict__ bins_y, int ny,
+                const float *__restrict__ bins_z, int nz, CellGrid g, float min_d, float max_d,
+                uint4 *__restrict__ rec, uint32_t *__restrict__ tkey, uint32_t *__restrict__ tval,
+                uint32_t *__restrict__ tcount, uint32_t *__restrict__ counters)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem &S = *reinterpret_cast<TileSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t frame = blockIdx.y, tif = blockIdx.x;
+    const uint32_t tile = frame * (uint32_t)tg.tpf + tif;
+    const int y0 = (int)(tif / (uint32_t)tg.tiles_x) * TILE_DIM, x0 = (int)(tif % (uint32_t)tg.tiles_x) * TILE_DIM;
+    if (tid < 12) S.P[tid] = pose[(size_t)frame * 12 + tid];
+    if (tid >= 32 && tid < 35) {
+        const int a = tid - 32;
         const float *bb = a == 0 ? bins_x : a == 1 ? bins_y : bins_z;
         const int nb = a == 0 ? nx : a == 1 ? ny : nz;
-        spacing[2 * a] = __ldg(bb);
-        spacing[2 * a + 1] = bins_scale(bb, nb);
+        S.spacing[2 * a] = __ldg(bb);
+        S.spacing[2 * a + 1] = bins_scale(bb, nb);
     }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < MB_NUM_COUNTERS) counters[threadIdx.x] = 0;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid < MB_NUM_COUNTERS) counters[tid] = 0;
+    for (int i = tid; i < HASH_SLOTS; i += 256) S.hkey[i] = HASH_EMPTY;
+    for (int i = tid; i < 8 * HASH_SLOTS / 2; i += 256) ((uint32_t *)&S.hcnt[0][0])[i] = 0u;
     __syncthreads();
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npix) return;
-    const size_t pid = (size_t)t * npix + p;
-    float r0, r1, r2;
-    orient(P, rays[3 * (size_t)p], rays[3 * (size_t)p + 1], rays[3 * (size_t)p + 2], r0, r1, r2);
-    const BinResult b = bin_point_fast(bins_x, nx, bins_y, ny, bins_z, nz, spacing, P[9], P[10], P[11], r0, r1, r2,
-                                       depth[pid], min_d, max_d);
-    uint4 out = make_uint4(g.invalid, 0u, 0u, 0u);
-    if (b.ok) {
-        // map axes are (y flipped, x, z) = input axes (1, 0, 2): base_projection_layer.py:339
-        const float q0 = b.q1, q1 = b.q0, q2 = b.q2;
-        const int e0 = q0 < 0.5f ? b.i1 : b.i1 + 1;       // lower corner + 1
-        const int e1 = q1 < 0.5f ? b.i0 : b.i0 + 1;
-        const int e2 = q2 < 0.5f ? b.i2 : b.i2 + 1;
-        out = make_uint4(cell_key(g, e0, e1, e2), __float_as_uint(q0), __float_as_uint(q1), __float_as_uint(q2));
+
+    // ---- voxelise: pixel l = r * 256 + tid of the tile -------------------------------------------------
+    uint32_t key[4], slot[4], rk[4];
+    float q[4][3];
+    const size_t fbase = (size_t)frame * tg.H * tg.W;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int l = r * 256 + tid;
+        const int y = y0 + (l >> 5), x = x0 + (l & 31);
+        key[r] = HASH_EMPTY;
+        q[r][0] = q[r][1] = q[r][2] = 0.f;
+        if (y < tg.H && x < tg.W) {
+            const size_t p = (size_t)y * tg.W + x;
+            float r0, r1, r2;
+            orient(S.P, rays[3 * p], rays[3 * p + 1], rays[3 * p + 2], r0, r1, r2);
+            const BinResult b = bin_point_fast(bins_x, nx, bins_y, ny, bins_z, nz, S.spacing, S.P[9], S.P[10], S.P[11],
+                                               r0, r1, r2, depth[fbase + p], min_d, max_d);
+            if (b.ok) {
+                // map axes are (y flipped, x, z) = input axes (1, 0, 2): base_projection_layer.py:339
+                q[r][0] = b.q1; q[r][1] = b.q0; q[r][2] = b.q2;
+                const int e0 = q[r][0] < 0.5f ? b.i1 : b.i1 + 1;       // lower corner + 1
+                const int e1 = q[r][1] < 0.5f ? b.i0 : b.i0 + 1;
+                const int e2 = q[r][2] < 0.5f ? b.i2 : b.i2 + 1;
+                key[r] = cell_key(g, e0, e1, e2);
+            }
+        }
     }
-    rec[pid] = out;
-    keys[pid] = out.x;
-    vals[pid] = (t << pbits) | p;          // sort value: frame and pixel, no division needed downstream
+    // ---- distinct keys -> hash slots -----------------------------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        slot[r] = HASH_SLOTS;
+        if (key[r] != HASH_EMPTY) {
+            uint32_t h = (key[r] * 2654435761u) >> 21;
+            for (;;) {
+                const uint32_t old = atomicCAS(&S.hkey[h], HASH_EMPTY, key[r]);
+                if (old == HASH_EMPTY || old == key[r]) break;
+                h = (h + 1) & (HASH_SLOTS - 1);
+            }
+            slot[r] = h;
+        }
+    }
+    // ---- rank inside the slot: order (warp, round, lane) ---------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const bool valid = slot[r] < HASH_SLOTS;
+        const uint32_t m = __match_any_sync(FULL, valid ? slot[r] : HASH_SLOTS + lane);
+        const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+        const uint32_t prev = valid ? S.hcnt[warp][slot[r]] : 0u;
+        __syncwarp();
+        if (valid && rank == 0) S.hcnt[warp][slot[r]] = (uint16_t)(prev + __popc(m));
+        __syncwarp();
+        rk[r] = prev + rank;
+    }
+    __syncthreads();
+    // ---- lay the slots out: thread t owns slots t, t + 256, ... -------------------------------------------------
+    uint32_t mine = 0;                              // pixels | items << 16 of this thread's slots
+#pragma unroll
+    for (int j = 0; j < HASH_SLOTS / 256; ++j) {
+        const int sl = tid + 256 * j;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t c = S.hcnt[w][sl];
+            S.hcnt[w][sl] = (uint16_t)run;
+            run += c;
+        }
+        S.total[sl] = (uint16_t)run;
+        mine += run | (((run + ITEM_MAX - 1) / ITEM_MAX) << 16);
+    }
+    uint32_t inc = mine;                            // block exclusive scan of the packed pair
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) S.warp_sum[warp] = inc;
+    __syncthreads();
+    uint32_t base = inc - mine;
+    for (int w = 0; w < warp; ++w) base += S.warp_sum[w];
+    uint32_t nitems = 0;
+    for (int w = 0; w < 8; ++w) nitems += S.warp_sum[w] >> 16;
+#pragma unroll
+    for (int j = 0; j < HASH_SLOTS / 256; ++j) {
+        const int sl = tid + 256 * j;
+        const uint32_t run = S.total[sl];
+        S.gstart[sl] = (uint16_t)(base & 0xffffu);
+        S.istart[sl] = (uint16_t)(base >> 16);
+        base += run | (((run + ITEM_MAX - 1) / ITEM_MAX) << 16);
+    }
+    __syncthreads();
+    // ---- pixel records in grouped order, items ------------------------------------------------------------------
+    const size_t tbase = (size_t)tile * TILE_PIX;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (slot[r] < HASH_SLOTS) {
+            const uint32_t pos = (uint32_t)S.gstart[slot[r]] + S.hcnt[warp][slot[r]] + rk[r];
+            rec[tbase + pos] = make_uint4(__float_as_uint(q[r][0]), __float_as_uint(q[r][1]), __float_as_uint(q[r][2]),
+                                          (uint32_t)(r * 256 + tid));
+        }
+#pragma unroll
+    for (int j = 0; j < HASH_SLOTS / 256; ++j) {
+        const int sl = tid + 256 * j;
+        const uint32_t run = S.total[sl];
+        if (run) {
+            const uint32_t k = S.hkey[sl], gs = S.gstart[sl], is = S.istart[sl];
+            for (uint32_t o = 0, n = 0; o < run; o += ITEM_MAX, ++n) {
+                tkey[tbase + is + n] = k;
+                tval[tbase + is + n] = (tile << 14) | ((gs + o) << 4) | (min((uint32_t)ITEM_MAX, run - o) - 1u);
+            }
+        }
+    }
+    if (tid == 0) tcount[tile] = nitems;
+}
+
+// K1b: dense item list in tile order (toff = exclusive scan of the tile counts)
+__global__ void __launch_bounds__(256)
+k_tile_compact(const uint32_t *__restrict__ tkey, const uint32_t *__restrict__ tval, const uint32_t *__restrict__ tcount,
+               const uint32_t *__restrict__ toff, uint32_t ntiles, uint32_t *__restrict__ ikey,
+               uint32_t *__restrict__ ival, uint32_t *__restrict__ counters)
+{
+    const uint32_t tile = blockIdx.x;
+    const uint32_t cnt = tcount[tile], off = toff[tile];
+    const size_t tbase = (size_t)tile * TILE_PIX;
+    for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+        ikey[off + j] = tkey[tbase + j];
+        ival[off + j] = tval[tbase + j];
+    }
+    if (tile == ntiles - 1 && threadIdx.x == 0) counters[MB_CNT_NVALID] = off + cnt;     // number of items
 }
 
 // ---------------------------------------------------------------------------------------------
 // K2/K3 fused: one sweep over the sorted list finds the heads of cells, (cell, frame) segments and accumulate
 // runs, ranks them and emits the unique cell list, the segment list, the dense cell table and the
-// touched-voxel bitmap.  A tile is 2048 sorted positions (8 warps x 8 words of 32).  The three ranks of a
+// touched-voxel bitmap.  A tile is 2048 sorted items (8 warps x 8 words of 32).  The three ranks of a
 // tile's first position come from a decoupled look-back over the preceding tiles' counts (tiles take
 // their index from a ticket, so a tile only ever waits for tiles that started before it).
-//   cell head: first pixel of a cell; segment head: first pixel of a (cell, frame); run head: cell head or
-//   start of an accumulate task (a multiple of CH).
+//   The sorted list is the ITEM list (K1): cell head: first item of a cell; segment head: first item of a
+//   (cell, frame); run head: cell head or start of an accumulate task (a multiple of TASK_ITEMS items).
 constexpr int IDX_WORDS = 8;                      // words per warp
 constexpr int IDX_TILE = 256 * IDX_WORDS;         // positions per tile
 constexpr uint32_t IDX_AGG = 1u << 30, IDX_PREFIX = 2u << 30, IDX_MASK = (1u << 30) - 1u;
@@ -175,14 +326,16 @@ struct IndexOut {
 };
 
 __global__ void __launch_bounds__(256)
-k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sval, uint32_t n, int pbits, CellGrid g,
-             const IndexOut O)
+k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sval, const uint32_t *__restrict__ n_dev,
+             uint32_t tpf, CellGrid g, const IndexOut O)
 {
     __shared__ uint32_t s_tile, s_wsum[8][3], s_base[3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = *n_dev;                    // number of items
     if (tid == 0) s_tile = atomicAdd(O.ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
+    if ((uint64_t)tile * IDX_TILE >= n) return;   // launched for the worst case; later tiles are empty too
     const uint32_t wbase = tile * IDX_TILE + warp * (32 * IDX_WORDS);
     const uint32_t lt = (1u << lane) - 1u;
 
@@ -203,10 +356,10 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
         if (lane == 0) { kprev = pk; vprev = pv; }
         pk = __shfl_sync(FULL, key[r], 31);       // (only lane 0's copy is used)
         pv = __shfl_sync(FULL, val[r], 31);
-        const bool valid = key[r] < g.invalid;    // positions past n carry 0xffffffff
+        const bool valid = i < n;
         const bool chead = valid && (i == 0 || kprev != key[r]);
-        const bool shead = valid && (chead || (vprev >> pbits) != (val[r] >> pbits));
-        const bool rhead = valid && (chead || (i % CH) == 0);
+        const bool shead = valid && (chead || (vprev >> 14) / tpf != (val[r] >> 14) / tpf);
+        const bool rhead = valid && (chead || (i % TASK_ITEMS) == 0);
         cm[r] = __ballot_sync(FULL, chead);
         sm[r] = __ballot_sync(FULL, shead);
         rm[r] = __ballot_sync(FULL, rhead);
@@ -250,12 +403,12 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
         const uint32_t i = wbase + r * 32 + lane;
         const uint32_t w = i >> 5;
         if (lane == 0 && w <= (n >> 5)) { O.smask[w] = sm[r]; O.soff[w] = sb; O.roff[w] = rb; }
-        const bool valid = key[r] < g.invalid;
+        const bool valid = i < n;
         if (valid) {
             const uint32_t crank = cb + __popc(cm[r] & lt), srank = sb + __popc(sm[r] & lt), rrank = rb + __popc(rm[r] & lt);
             if ((sm[r] >> lane) & 1u) {
                 O.seg_start[srank] = i;
-                O.seg_frame[srank] = val[r] >> pbits;
+                O.seg_frame[srank] = (val[r] >> 14) / tpf;
             }
             if ((cm[r] >> lane) & 1u) {
                 const uint32_t k = key[r];
@@ -277,17 +430,8 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
                 }
             }
         }
-        // is position i the last valid one?  (the next key is invalid, or i is the last position)
         {
-            uint32_t knext = __shfl_down_sync(FULL, key[r], 1);
-            const uint32_t nextfirst = __shfl_sync(FULL, key[r + 1 < IDX_WORDS ? r + 1 : r], 0);
-            bool is_last = false;
-            if (valid) {
-                if (i + 1 >= n) is_last = true;
-                else if (lane < 31) is_last = knext >= g.invalid;
-                else if (r + 1 < IDX_WORDS) is_last = nextfirst >= g.invalid;
-                else is_last = skey[i + 1] >= g.invalid;                 // next position belongs to another warp
-            }
+            const bool is_last = valid && i + 1 == n;
             if (is_last) {
                 const uint32_t le = lane == 31 ? 0xffffffffu : ((2u << lane) - 1u);
                 const uint32_t nc = cb + __popc(cm[r] & le), ns = sb + __popc(sm[r] & le), nr = rb + __popc(rm[r] & le);
@@ -329,35 +473,36 @@ k_vox_emit(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ vof
     }
 }
 
-// K5: per (cell, frame) segment and slot: W = sum w, S2 = sum w^2, in pixel order.  One thread per
-// segment; four records are requested before the first is used (segments average ~6 pixels).
+// K5: per (cell, frame) segment and slot: W = sum w, S2 = sum w^2 over the pixels of the segment's items (item
+// order, pixel order inside the item).  One thread per segment; an item's records are contiguous.
 __global__ void __launch_bounds__(256)
-k_seg_sums(const uint32_t *__restrict__ sval, const uint4 *__restrict__ rec, const uint32_t *__restrict__ seg_start,
-           uint32_t npix, int pbits, float2 *__restrict__ segws, size_t cap, const uint32_t *__restrict__ counters)
+k_seg_sums(const uint32_t *__restrict__ ival, const uint4 *__restrict__ rec, const uint32_t *__restrict__ seg_start,
+           float2 *__restrict__ segws, size_t cap, const uint32_t *__restrict__ counters)
 {
     const uint32_t nsegs = counters[MB_CNT_SEGS];
-    const uint32_t pmask = (1u << pbits) - 1u;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nsegs; s += gridDim.x * blockDim.x) {
         const uint32_t beg = seg_start[s], end = seg_start[s + 1];
         float W[8], S2[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { W[k] = 0.f; S2[k] = 0.f; }
-        for (uint32_t i = beg; i < end; i += 4) {
-            uint4 r[4];
+        for (uint32_t it = beg; it < end; ++it) {
+            const uint32_t v = ival[it];
+            const uint4 *pr = rec + (size_t)(v >> 14) * TILE_PIX + ((v >> 4) & 1023u);
+            const uint32_t len = (v & 15u) + 1u;
+            for (uint32_t i = 0; i < len; i += 4) {
+                uint4 r[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i + u < end) {
-                    const uint32_t sv = sval[i + u];
-                    r[u] = __ldg(rec + (size_t)(sv >> pbits) * npix + (sv & pmask));
-                }
+                for (int u = 0; u < 4; ++u)
+                    if (i + u < len) r[u] = __ldg(pr + i + u);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i + u < end) {
-                    float w[8];
-                    splat_weights(r[u], w);
+                for (int u = 0; u < 4; ++u)
+                    if (i + u < len) {
+                        float w[8];
+                        splat_weights(r[u], w);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) { W[k] += w[k]; S2[k] = fmaf(w[k], w[k], S2[k]); }
-                }
+                        for (int k = 0; k < 8; ++k) { W[k] += w[k]; S2[k] = fmaf(w[k], w[k], S2[k]); }
+                    }
+            }
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) segws[(size_t)k * cap + s] = make_float2(W[k], S2[k]);    // slot-major
@@ -533,9 +678,9 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vs
 // pixels: one feature row load + 8 coefficient broadcasts + 8 FMAs per lane-vector.  A run of
 // same-cell pixels accumulates in registers and is flushed as 8 rows of P.
 struct AccArgs {
-    const uint32_t *skey, *sval;
-    int pbits;
-    const uint4 *rec;
+    const uint32_t *ikey, *ival;   // sorted item list
+    TileGeom tg;
+    const uint4 *rec;              // pixel records in tile-grouped order
     const uint32_t *smask, *soff, *roff;
     const float *gcoef;         // [8 slots][cap] coefficient per (slot, segment)
     size_t cap;
@@ -597,23 +742,65 @@ k_cell_accumulate(const AccArgs A)
     constexpr int NW = ACC_THREADS / 32;
     __shared__ __align__(16) float s_coef[NW][32][8];
     __shared__ uint32_t s_src[NW][32];
+    __shared__ uint32_t s_pre[NW][TASK_ITEMS + 1], s_ival[NW][TASK_ITEMS], s_seg[NW][TASK_ITEMS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nvalid = A.counters[MB_CNT_NVALID], nruns = A.counters[MB_CNT_RUNS];
+    const uint32_t nitems = A.counters[MB_CNT_NVALID], nruns = A.counters[MB_CNT_RUNS];
     if (A.run_base >= nruns) return;
     const uint32_t run_end = A.run_base + A.run_cap;
     const int F = A.F;
     const int ch0 = (int)blockIdx.y * (32 * VEC * IT) + lane * VEC;     // first channel of this lane
-    const uint32_t ntasks = (nvalid + CH - 1) / CH;
+    const uint32_t ntasks = (nitems + TASK_ITEMS - 1) / TASK_ITEMS;
     const uint32_t np = A.fi.np;
     const uint32_t lemask = lane == 31 ? 0xffffffffu : ((2u << lane) - 1u);
 
     for (uint32_t task = blockIdx.x * NW + warp; task < ntasks; task += gridDim.x * NW) {
-        const uint32_t base = task * CH, end = min(base + (uint32_t)CH, nvalid);
+        const uint32_t base = task * TASK_ITEMS, end = min(base + (uint32_t)TASK_ITEMS, nitems);
         uint32_t e = A.roff[base >> 5];                                  // rank of the task's first run
         {
-            const uint32_t e_after = end == nvalid ? nruns : A.roff[end >> 5];
+            const uint32_t e_after = end == nitems ? nruns : A.roff[end >> 5];
             if (e_after <= A.run_base || e >= run_end) continue;         // no run of this round in the task
         }
+        // ---- the task's items: pixel prefix, run heads, segment ranks (two items per lane) -----------------
+        uint32_t ihead[2];                                                // run-head masks of items 0-31, 32-63
+        uint32_t npixels;
+        {
+            uint32_t key[2], len[2];
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t i = base + 32 * h + lane;
+                key[h] = 0xfffffffeu;
+                len[h] = 0;
+                if (i < end) {
+                    const uint32_t v = A.ival[i];
+                    key[h] = A.ikey[i];
+                    len[h] = (v & 15u) + 1u;
+                    const uint32_t w = i >> 5;
+                    s_ival[warp][32 * h + lane] = v;
+                    s_seg[warp][32 * h + lane] = A.soff[w] + __popc(A.smask[w] & lemask) - 1u;
+                }
+            }
+            uint32_t carry = 0, lastkey = 0xffffffffu;                    // != any key: item 0 is a run head
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t inc = len[h];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(FULL, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                s_pre[warp][32 * h + lane] = carry + inc - len[h];
+                carry += __shfl_sync(FULL, inc, 31);
+                uint32_t prevkey = __shfl_up_sync(FULL, key[h], 1);
+                if (lane == 0) prevkey = lastkey;
+                lastkey = __shfl_sync(FULL, key[h], 31);
+                ihead[h] = __ballot_sync(FULL, len[h] != 0 && key[h] != prevkey);
+            }
+            npixels = carry;
+            if (lane == 0) s_pre[warp][TASK_ITEMS] = carry;
+            __syncwarp();
+        }
+        const int nit = (int)(end - base);
         float acc[8][IT][VEC];
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -621,7 +808,6 @@ k_cell_accumulate(const AccArgs A)
             for (int it = 0; it < IT; ++it)
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) acc[k][it][j] = 0.f;
-        uint32_t lastkey = 0xffffffffu;                                   // != any valid key: forces a head at `base`
 
         auto flush = [&]() {
             if (e >= A.run_base && e < run_end) {
@@ -643,40 +829,38 @@ k_cell_accumulate(const AccArgs A)
             ++e;
         };
 
-        for (uint32_t b0 = base; b0 < end; b0 += 32) {
+        for (uint32_t b0 = 0; b0 < npixels; b0 += 32) {
             // ---- lanes = pixels: coefficients of the batch ------------------------------------------------
-            const uint32_t i = b0 + lane;
-            const bool ok = i < end;
-            const uint32_t key = ok ? A.skey[i] : 0xfffffffeu;
-            uint32_t prevkey = __shfl_up_sync(FULL, key, 1);
-            if (lane == 0) prevkey = lastkey;
-            lastkey = __shfl_sync(FULL, key, 31);
-            const uint32_t hm = __ballot_sync(FULL, ok && key != prevkey);
+            const uint32_t qp = b0 + lane;                                // pixel of the task
+            const bool ok = qp < npixels;
+            bool phead = false;
             {
                 float c[8];
                 uint32_t src = 0;
                 if (ok) {
-                    const uint32_t sv = A.sval[i];
-                    const uint32_t frame = sv >> A.pbits, p = sv & ((1u << A.pbits) - 1u);
-                    const size_t pid = (size_t)frame * np + p;
-                    const uint32_t w = i >> 5;
-                    const uint32_t s = A.soff[w] + __popc(A.smask[w] & lemask) - 1u;
-                    const uint4 r = __ldg(A.rec + pid);
+                    int lo = 0, hi = nit;                                 // last item whose prefix is <= qp
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_pre[warp][mid] <= qp) lo = mid; else hi = mid;
+                    }
+                    const uint32_t v = s_ival[warp][lo], off = qp - s_pre[warp][lo];
+                    phead = off == 0 && ((ihead[lo >> 5] >> (lo & 31)) & 1u);
+                    const uint32_t tile = v >> 14;
+                    const uint4 r = __ldg(A.rec + (size_t)tile * TILE_PIX + ((v >> 4) & 1023u) + off);
+                    const uint32_t s = s_seg[warp][lo];
                     float gk[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) gk[k] = __ldg(A.gcoef + (size_t)k * A.cap + s);
                     splat_weights(r, c);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) c[k] = c[k] * c[k] * gk[k];
+                    const uint32_t frame = tile / (uint32_t)A.tg.tpf, tif = tile - frame * (uint32_t)A.tg.tpf;
+                    const uint32_t tyo = tif / (uint32_t)A.tg.tiles_x, txo = tif - tyo * (uint32_t)A.tg.tiles_x;
+                    const uint32_t y = tyo * TILE_DIM + (r.w >> 5), x = txo * TILE_DIM + (r.w & 31u);
                     if (ONEHOT) {
-                        src = (uint32_t)A.class_ids[pid];
+                        src = (uint32_t)A.class_ids[(size_t)frame * np + y * A.fi.W + x];
                     } else {
-                        if (A.fi.kx == 1 && A.fi.ky == 1) {
-                            src = frame * A.fhw + p;
-                        } else {
-                            const uint32_t y = p / A.fi.W, x = p - y * A.fi.W;
-                            src = frame * A.fhw + (y / A.fi.ky) * A.fi.fw + x / A.fi.kx;
-                        }
+                        src = frame * A.fhw + (y / A.fi.ky) * A.fi.fw + x / A.fi.kx;
                     }
                 } else {
 #pragma unroll
@@ -688,12 +872,13 @@ k_cell_accumulate(const AccArgs A)
                 s_src[warp][lane] = src;
                 __syncwarp();
             }
+            const uint32_t hm = __ballot_sync(FULL, phead);
 
             // ---- lanes = channels: walk the batch ---------------------------------------------------------
-            const int nb = (int)min(32u, end - b0);
+            const int nb = (int)min(32u, npixels - b0);
             int jj = 0;
             while (jj < nb) {
-                if (((hm >> jj) & 1u) && !(b0 == base && jj == 0)) flush();
+                if (((hm >> jj) & 1u) && !(b0 == 0 && jj == 0)) flush();
                 const uint32_t rest = jj < 31 ? (hm >> (jj + 1)) : 0u;
                 int jend = rest ? jj + __ffs(rest) : nb;            // next head (exclusive end of this stretch)
                 if (jend > nb) jend = nb;
@@ -921,6 +1106,7 @@ struct CellBuffers {
     uint32_t *counters;
     uint4 *rec;
     uint32_t *keys_a, *keys_b, *pids_a, *pids_b;
+    uint32_t *tcount, *toff;
     uint32_t *smask, *soff, *roff, *idx_state;
     uint32_t *ucell, *cstart, *cseg, *crun, *seg_start, *seg_frame;
     float2 *segws;
@@ -935,10 +1121,12 @@ struct CellBuffers {
     size_t P_floats;
 };
 
-// carves everything but P; returns the bytes used
+// carves everything but P; returns the bytes used.  n = padded pixel count of the chunk (tiles * 1024): the
+// capacity of every per-pixel, per-item and per-segment array.
 size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const CellGrid &g)
 {
     MbArena a(ws, bytes);
+    const size_t ntiles = (size_t)n / TILE_PIX;
     const size_t words = (size_t)n / 32 + 2;
     const size_t V = (size_t)g.S0 * g.S1 * g.S2, vwords = V / 32 + 1;
     const size_t ncap = (size_t)n < (size_t)g.invalid ? (size_t)n : (size_t)g.invalid;   // unique cells
@@ -947,6 +1135,7 @@ size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const Cel
     b.rec = a.take<uint4>(n);
     b.keys_a = a.take<uint32_t>(n); b.keys_b = a.take<uint32_t>(n);
     b.pids_a = a.take<uint32_t>(n); b.pids_b = a.take<uint32_t>(n);
+    b.tcount = a.take<uint32_t>(ntiles + 1); b.toff = a.take<uint32_t>(ntiles + 1);
     b.smask = a.take<uint32_t>(words); b.soff = a.take<uint32_t>(words); b.roff = a.take<uint32_t>(words);
     b.idx_state = a.take<uint32_t>(((size_t)n + IDX_TILE - 1) / IDX_TILE * 3 + 8);
     b.ucell = a.take<uint32_t>(ncap + 1); b.cstart = a.take<uint32_t>(ncap + 1);
@@ -967,7 +1156,7 @@ size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const Cel
         b.ctab = dense ? a.take<int>((size_t)g.invalid) : nullptr;
         if (!dense) b.ctab = nullptr;
     }
-    const size_t scan_n = words > vwords ? words : vwords;
+    const size_t scan_n = ntiles + 1 > vwords ? ntiles + 1 : vwords;
     b.scan_bytes = mb_scan_workspace_bytes((uint32_t)scan_n);
     b.scan_ws = a.take<char>(b.scan_bytes);
     b.sort_bytes = mb_sort_workspace_bytes(n);
@@ -978,11 +1167,11 @@ size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const Cel
     return used;
 }
 
-// most runs a call can produce: every cell starts one, every task start may split one
+// most runs a call can produce: every cell starts one, every task start (64 items) may split one
 size_t worst_runs(uint32_t n, const CellGrid &g)
 {
     const size_t ncap = (size_t)n < (size_t)g.invalid ? (size_t)n : (size_t)g.invalid;
-    return ncap + ((size_t)n + CH - 1) / CH;
+    return ncap + ((size_t)n + TASK_ITEMS - 1) / TASK_ITEMS;
 }
 
 void pick_vec(const float *features, const float *map, const float *P, int F, int &vec, int &it)
@@ -1095,33 +1284,51 @@ static size_t default_P_bytes(uint32_t n, const CellGrid &g, int F)
     return want < worst ? want : worst;
 }
 
-size_t mbk_batch_workspace_bytes(uint32_t npix, int nx, int ny, int nz, int T, int F)
+// padded pixel count of a chunk of T frames (tiles * 1024), 0 if the chunk is too large
+static uint64_t padded_pixels(int H, int W, int T)
+{
+    const TileGeom tg = make_tiles(H, W);
+    const uint64_t ntiles = (uint64_t)T * tg.tpf;
+    if (ntiles >= (1u << 18) || T > MB_MAX_CHUNK_FRAMES) return 0;      // tile ids are 18 bits of the item value
+    return ntiles * TILE_PIX;
+}
+
+size_t mbk_batch_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int F)
 {
     const CellGrid g = make_cells(ny - 1, nx - 1, nz - 1);
     CellBuffers b;
-    const uint32_t n = (uint32_t)T * npix;
+    const uint32_t n = (uint32_t)padded_pixels(H, W, T);
     return carve_cells(b, nullptr, 0, n, g) + default_P_bytes(n, g, F) + 512;
 }
 
 // smallest workspace that takes T frames in one chunk: the run buffer then holds 1/64 of the worst-case
-// runs (never less than two tasks' worth), i.e. the feature pass may take up to 64 rounds
-size_t mbk_batch_min_workspace_bytes(uint32_t npix, int nx, int ny, int nz, int T, int F)
+// runs (never less than a few tasks' worth), i.e. the feature pass may take up to 64 rounds
+size_t mbk_batch_min_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int F)
 {
     const CellGrid g = make_cells(ny - 1, nx - 1, nz - 1);
     CellBuffers b;
-    const uint32_t n = (uint32_t)T * npix;
+    const uint32_t n = (uint32_t)padded_pixels(H, W, T);
     const size_t wr = worst_runs(n, g);
-    size_t minruns = wr / 64 + 2 * CH;
+    size_t minruns = wr / 64 + 512;
     if (minruns > wr) minruns = wr;
     return carve_cells(b, nullptr, 0, n, g) + minruns * run_bytes(F) + 512;
 }
 
+// largest number of frames one chunk can hold at all (tile ids are 18 bits; MB_MAX_CHUNK_FRAMES frames)
+int mbk_batch_max_chunk_frames(int H, int W)
+{
+    const TileGeom tg = make_tiles(H, W);
+    int t = (int)(((1u << 18) - 1) / (uint32_t)tg.tpf);
+    if (t > MB_MAX_CHUNK_FRAMES) t = MB_MAX_CHUNK_FRAMES;
+    return t;
+}
+
 // frames per internal chunk for a given workspace; 0 if even one frame does not fit
-int mbk_batch_frames_that_fit(uint32_t npix, int nx, int ny, int nz, int F, size_t workspace_bytes, int T)
+int mbk_batch_frames_that_fit(int H, int W, int nx, int ny, int nz, int F, size_t workspace_bytes, int T)
 {
     auto fits = [&](int t) {
-        if ((uint64_t)t * npix >= 0x7fffffffull || t > MB_MAX_CHUNK_FRAMES) return false;
-        return mbk_batch_min_workspace_bytes(npix, nx, ny, nz, t, F) <= workspace_bytes;
+        if (padded_pixels(H, W, t) == 0) return false;
+        return mbk_batch_min_workspace_bytes(H, W, nx, ny, nz, t, F) <= workspace_bytes;
     };
     if (fits(T)) return T;
     int best = 0;
@@ -1139,9 +1346,10 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
                      size_t workspace_bytes)
 {
     const uint32_t npix = (uint32_t)H * (uint32_t)W;
-    MB_REQUIRE((uint64_t)T * npix < 0x7fffffffull, "too many pixels per chunk");
-    MB_REQUIRE(T <= MB_MAX_CHUNK_FRAMES, "too many frames per chunk");
-    const uint32_t n = (uint32_t)T * npix;
+    const TileGeom tg = make_tiles(H, W);
+    const uint64_t padded = padded_pixels(H, W, T);
+    MB_REQUIRE(padded != 0 && padded < 0x7fffffffull, "too many frames or pixels per chunk");
+    const uint32_t n = (uint32_t)padded, ntiles = n / TILE_PIX;
     const CellGrid g = make_cells(ny - 1, nx - 1, nz - 1);
     MB_REQUIRE((uint64_t)g.E0 * g.E1 * g.E2 < 0xfffffff0ull, "map too large for 32-bit cell keys");
     MB_REQUIRE(class_ids != nullptr || (uint64_t)T * fh * fw < 0xffffffffull, "too many feature rows per chunk");
@@ -1153,30 +1361,33 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     pick_vec(features, map, b.P, F, vec, it);
     const size_t run_cap_sz = b.P_floats / ((size_t)8 * F);
     const size_t wruns = worst_runs(n, g);
-    MB_REQUIRE(run_cap_sz >= (wruns < 2 * CH ? wruns : 2 * CH), "batch workspace too small for the run buffer");
+    MB_REQUIRE(run_cap_sz >= (wruns < 512 ? wruns : 512), "batch workspace too small for the run buffer");
     const uint32_t run_cap = (uint32_t)(run_cap_sz < 0x7fffffffull ? run_cap_sz : 0x7fffffffull);
     const int rounds = (int)((wruns + run_cap - 1) / run_cap);
     MB_REQUIRE(rounds <= 4096, "batch workspace far too small for the run buffer");
 
-    // K1 + sort
+    // K1: voxelise + group inside tiles, compact the items; then sort the items by cell
     int rc;
     if ((rc = stage_mark(stream, 0))) return rc;
-    dim3 grid((npix + 255) / 256, (unsigned)T);
-    int pbits = 1;
-    while ((1u << pbits) < npix) ++pbits;
-    MB_REQUIRE(((uint64_t)(T - 1) << pbits) < 0xffffffffull, "frame too large for the packed (frame, pixel) sort value");
-    k_cell_voxelise<<<grid, 256, 0, stream>>>(rays, depth, pose, npix, bins_x, nx, bins_y, ny, bins_z, nz, g, min_d,
-                                              max_d, b.rec, b.keys_a, b.pids_a, pbits, b.counters);
+    uint32_t *tkey = b.keys_b, *tval = b.pids_b;          // tile-local item lists live in the sort's second buffers
+    MB_CHECK_CUDA(cudaFuncSetAttribute(k_tile_voxelise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    dim3 grid((unsigned)tg.tpf, (unsigned)T);
+    k_tile_voxelise<<<grid, 256, sizeof(TileSmem), stream>>>(rays, depth, pose, tg, bins_x, nx, bins_y, ny, bins_z, nz, g,
+                                                             min_d, max_d, b.rec, tkey, tval, b.tcount, b.counters);
     MB_LAUNCHED();
+    if ((rc = mb_exclusive_scan_u32(stream, b.tcount, b.toff, ntiles, b.scan_ws, b.scan_bytes))) return rc;
+    k_tile_compact<<<ntiles, 256, 0, stream>>>(tkey, tval, b.tcount, b.toff, ntiles, b.keys_a, b.pids_a, b.counters);
+    MB_LAUNCHED();
+    if ((rc = stage_mark(stream, 1))) return rc;
     int bits = 1;
     while (bits < 32 && (((uint64_t)1) << bits) <= (uint64_t)g.invalid) ++bits;
-    if ((rc = stage_mark(stream, 1))) return rc;
-    uint32_t *skey, *sval;
-    rc = mb_sort_pairs(stream, b.keys_a, b.pids_a, b.keys_b, b.pids_b, n, nullptr, bits, false, b.sort_ws,
-                           b.sort_bytes, &skey, &sval);
+    uint32_t *ikey, *ival;
+    const uint32_t *n_items = b.counters + MB_CNT_NVALID;
+    rc = mb_sort_pairs(stream, b.keys_a, b.pids_a, b.keys_b, b.pids_b, n, n_items, bits, false, b.sort_ws, b.sort_bytes,
+                       &ikey, &ival);
     if (rc) return rc;
 
-    // K2 + ranks
+    // K2: index sweep over the sorted items
     if ((rc = stage_mark(stream, 2))) return rc;
     MB_CHECK_CUDA(cudaMemsetAsync(b.bitmap, 0, (size_t)vwords * sizeof(uint32_t), stream));
     if (b.ctab) MB_CHECK_CUDA(cudaMemsetAsync(b.ctab, 0xff, (size_t)g.invalid * sizeof(int), stream));
@@ -1188,7 +1399,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
         O.ucell = b.ucell; O.cstart = b.cstart; O.cseg = b.cseg; O.crun = b.crun;
         O.seg_start = b.seg_start; O.seg_frame = b.seg_frame; O.bitmap = b.bitmap; O.ctab = b.ctab;
         O.counters = b.counters; O.state = b.idx_state + 4; O.ticket = b.idx_state;
-        k_cell_index<<<itiles, 256, 0, stream>>>(skey, sval, n, pbits, g, O);
+        k_cell_index<<<itiles, 256, 0, stream>>>(ikey, ival, n_items, (uint32_t)tg.tpf, g, O);
         MB_LAUNCHED();
     }
     // K4
@@ -1199,7 +1410,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     MB_LAUNCHED();
     // K5, K6
     if ((rc = stage_mark(stream, 3))) return rc;
-    k_seg_sums<<<MB_NUM_SMS * 8, 256, 0, stream>>>(sval, b.rec, b.seg_start, npix, pbits, b.segws, (size_t)n, b.counters);
+    k_seg_sums<<<MB_NUM_SMS * 8, 256, 0, stream>>>(ival, b.rec, b.seg_start, b.segws, (size_t)n, b.counters);
     MB_LAUNCHED();
     {
         const size_t smem = (size_t)8 * 2 * ((T + 31) & ~31) * sizeof(float);
@@ -1216,7 +1427,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     }
     // K7, K8 (one round unless the runs outgrow the P buffer)
     AccArgs A;
-    A.skey = skey; A.sval = sval; A.pbits = pbits; A.rec = b.rec; A.smask = b.smask; A.soff = b.soff; A.roff = b.roff;
+    A.ikey = ikey; A.ival = ival; A.tg = tg; A.rec = b.rec; A.smask = b.smask; A.soff = b.soff; A.roff = b.roff;
     A.gcoef = b.gcoef; A.cap = (size_t)n; A.counters = b.counters;
     A.fi = MbFeatIndex{ npix, (uint32_t)W, (uint32_t)(H / fh), (uint32_t)(W / fw), (uint32_t)fw };
     A.fhw = (uint32_t)fh * (uint32_t)fw;

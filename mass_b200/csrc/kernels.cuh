@@ -50,9 +50,10 @@ int mbk_voxel_reduce(cudaStream_t stream, const uint32_t *keys, const uint32_t *
                      float *map, const MbGrid &g, float alpha, int mode);
 
 // cells.cu: batched cell-sorted pipeline (affine form of the update; see the file header)
-int mbk_batch_frames_that_fit(uint32_t npix, int nx, int ny, int nz, int F, size_t workspace_bytes, int T);
-size_t mbk_batch_workspace_bytes(uint32_t npix, int nx, int ny, int nz, int T, int F);
-size_t mbk_batch_min_workspace_bytes(uint32_t npix, int nx, int ny, int nz, int T, int F);
+int mbk_batch_frames_that_fit(int H, int W, int nx, int ny, int nz, int F, size_t workspace_bytes, int T);
+int mbk_batch_max_chunk_frames(int H, int W);
+size_t mbk_batch_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int F);
+size_t mbk_batch_min_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int F);
 int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth, const float *features,
                      const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw, int F,
                      const float *bins_x, int nx, const float *bins_y, int ny, const float *bins_z, int nz,

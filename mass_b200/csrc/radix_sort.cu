@@ -117,12 +117,23 @@ constexpr int OS_THREADS = 256;
 constexpr int OS_TILE = OS_THREADS * OS_ITEMS;
 constexpr int OS_BLOCKS = MB_NUM_SMS * 2;
 
+// elements per CTA: the tiles split evenly over the CTAs, a multiple of the tile
+__host__ __device__ inline uint32_t block_share(uint32_t n, uint32_t blocks)
+{
+    const uint32_t ntiles = (n + OS_TILE - 1) / OS_TILE;
+    return ((ntiles + blocks - 1) / blocks) * OS_TILE;
+}
+
 __global__ void __launch_bounds__(256)
-k_radix_block_hist(const uint32_t *__restrict__ keys, uint32_t n, uint32_t per_block, int shift,
-                   uint32_t *__restrict__ table)
+k_radix_block_hist(const uint32_t *__restrict__ keys, uint32_t n, const uint32_t *__restrict__ n_dev,
+                   uint32_t per_block, int shift, uint32_t *__restrict__ table)
 {
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
+    if (n_dev) {                                  // the real count lives on the device: same split, computed here
+        n = min(n, *n_dev);
+        per_block = block_share(n, gridDim.x);
+    }
     __syncthreads();
     const uint32_t beg = min(n, blockIdx.x * per_block), end = min(n, beg + per_block);
     // each thread takes 16 consecutive keys (per_block and beg are multiples of 4096)
@@ -174,13 +185,18 @@ struct ScatterSmem {
 
 __global__ void __launch_bounds__(OS_THREADS, 2)
 k_radix_block_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, uint32_t per_block,
-                      int shift, const uint32_t *__restrict__ table, int vals_iota)
+                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n,
+                      const uint32_t *__restrict__ n_dev, uint32_t per_block, int shift,
+                      const uint32_t *__restrict__ table, int vals_iota)
 {
     constexpr int R = 256, WARPS = OS_THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ScatterSmem &S = *reinterpret_cast<ScatterSmem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (n_dev) {
+        n = min(n, *n_dev);
+        per_block = block_share(n, gridDim.x);
+    }
     const uint32_t beg = min(n, blockIdx.x * per_block), end = min(n, beg + per_block);
     S.s_gpos[tid] = table[tid * gridDim.x + blockIdx.x];
 
@@ -300,14 +316,13 @@ int mb_sort_pairs(cudaStream_t stream, uint32_t *keys_a, uint32_t *vals_a, uint3
     *keys_out = keys_a;
     *vals_out = vals_a;
     if (n == 0) return MB_OK;
-    MB_REQUIRE(n_dev == nullptr, "mb_sort_pairs: device-side counts are not supported");
     MB_REQUIRE(workspace_bytes >= mb_sort_workspace_bytes(n), "sort workspace too small");
     const int passes = (key_bits + 7) / 8;
     MB_REQUIRE(passes >= 1 && passes <= 4, "mb_sort_pairs: bad key width");
     const size_t ntiles = ((size_t)n + OS_TILE - 1) / OS_TILE;
-    int blocks = ntiles < (size_t)OS_BLOCKS ? (int)ntiles : OS_BLOCKS;
-    const uint32_t per_block = (uint32_t)((ntiles + blocks - 1) / blocks) * OS_TILE;      // a multiple of the tile
-    blocks = (int)(((size_t)n + per_block - 1) / per_block);
+    // n is an upper bound when n_dev is given: the CTAs then split min(n, *n_dev) among themselves
+    const int blocks = ntiles < (size_t)OS_BLOCKS ? (int)ntiles : OS_BLOCKS;
+    const uint32_t per_block = block_share(n, (uint32_t)blocks);
     MB_CHECK_CUDA(cudaFuncSetAttribute(k_radix_block_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(ScatterSmem)));
     MbArena arena(workspace, workspace_bytes);
@@ -319,12 +334,12 @@ int mb_sort_pairs(cudaStream_t stream, uint32_t *keys_a, uint32_t *vals_a, uint3
     uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
     bool iota = vals_a_is_iota;
     for (int p = 0; p < passes; ++p) {
-        k_radix_block_hist<<<blocks, 256, 0, stream>>>(kin, n, per_block, 8 * p, table);
+        k_radix_block_hist<<<blocks, 256, 0, stream>>>(kin, n, n_dev, per_block, 8 * p, table);
         MB_LAUNCHED();
         int rc = mb_exclusive_scan_u32(stream, table, table, table_n, scan_ws, scan_bytes);
         if (rc) return rc;
-        k_radix_block_scatter<<<blocks, OS_THREADS, sizeof(ScatterSmem), stream>>>(kin, vin, kout, vout, n, per_block,
-                                                                                   8 * p, table, iota ? 1 : 0);
+        k_radix_block_scatter<<<blocks, OS_THREADS, sizeof(ScatterSmem), stream>>>(kin, vin, kout, vout, n, n_dev,
+                                                                                   per_block, 8 * p, table, iota ? 1 : 0);
         MB_LAUNCHED();
         iota = false;
         uint32_t *t;
