@@ -736,13 +736,14 @@ __device__ __forceinline__ void row_store(float *p, const float (&src)[VEC])
 }
 
 template <int VEC, int IT, bool ONEHOT, int U>
-__global__ void __launch_bounds__(ACC_THREADS, (VEC * IT <= 2 ? 5 : 1))
+__global__ void __launch_bounds__(ACC_THREADS, (VEC * IT <= 2 ? 4 : 1))
 k_cell_accumulate(const AccArgs A)
 {
     constexpr int NW = ACC_THREADS / 32;
     __shared__ __align__(16) float s_coef[NW][32][8];
     __shared__ uint32_t s_src[NW][32];
     __shared__ uint32_t s_pre[NW][TASK_ITEMS + 1], s_ival[NW][TASK_ITEMS], s_seg[NW][TASK_ITEMS];
+    __shared__ uint8_t s_p2i[NW][TASK_ITEMS * ITEM_MAX];          // item of every pixel of the task
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nitems = A.counters[MB_CNT_NVALID], nruns = A.counters[MB_CNT_RUNS];
     if (A.run_base >= nruns) return;
@@ -789,7 +790,9 @@ k_cell_accumulate(const AccArgs A)
                     const uint32_t o = __shfl_up_sync(FULL, inc, d);
                     if (lane >= d) inc += o;
                 }
-                s_pre[warp][32 * h + lane] = carry + inc - len[h];
+                const uint32_t pre = carry + inc - len[h];
+                s_pre[warp][32 * h + lane] = pre;
+                for (uint32_t o = 0; o < len[h]; ++o) s_p2i[warp][pre + o] = (uint8_t)(32 * h + lane);
                 carry += __shfl_sync(FULL, inc, 31);
                 uint32_t prevkey = __shfl_up_sync(FULL, key[h], 1);
                 if (lane == 0) prevkey = lastkey;
@@ -800,7 +803,6 @@ k_cell_accumulate(const AccArgs A)
             if (lane == 0) s_pre[warp][TASK_ITEMS] = carry;
             __syncwarp();
         }
-        const int nit = (int)(end - base);
         float acc[8][IT][VEC];
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -838,11 +840,7 @@ k_cell_accumulate(const AccArgs A)
                 float c[8];
                 uint32_t src = 0;
                 if (ok) {
-                    int lo = 0, hi = nit;                                 // last item whose prefix is <= qp
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (s_pre[warp][mid] <= qp) lo = mid; else hi = mid;
-                    }
+                    const int lo = s_p2i[warp][qp];
                     const uint32_t v = s_ival[warp][lo], off = qp - s_pre[warp][lo];
                     phead = off == 0 && ((ihead[lo >> 5] >> (lo & 31)) & 1u);
                     const uint32_t tile = v >> 14;
@@ -1203,7 +1201,7 @@ int dispatch_accumulate(cudaStream_t stream, const AccArgs &A, int vec, int it)
 #define MB_ACC(V, I, UU)                                                              \
     if (vec == V && it == I)                                                          \
         return oh ? launch_accumulate<V, I, true, UU>(stream, A) : launch_accumulate<V, I, false, UU>(stream, A)
-    MB_ACC(1, 1, 8); MB_ACC(1, 2, 4); MB_ACC(2, 1, 4); MB_ACC(2, 2, 4); MB_ACC(4, 1, 4); MB_ACC(4, 2, 2);
+    MB_ACC(1, 1, 8); MB_ACC(1, 2, 4); MB_ACC(2, 1, 8); MB_ACC(2, 2, 4); MB_ACC(4, 1, 4); MB_ACC(4, 2, 2);
 #undef MB_ACC
     mb_set_error("internal: no accumulate kernel for vec %d it %d", vec, it);
     return MB_ERR_ARG;
