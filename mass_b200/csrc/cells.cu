@@ -109,21 +109,27 @@ __device__ __forceinline__ int find_cell(const uint32_t *__restrict__ ucell, uin
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: one CTA per 32 x 32 pixel tile of one frame: voxelise its 1024 pixels, then group them by cell inside
-// shared memory.  Neighbouring pixels fall into the same cell (a (cell, frame) segment averages ~4 pixels),
-// so what leaves the tile is an ITEM list -- (cell key, tile, first slot, length <= 16) -- a few times
-// shorter than the pixel list; the pixel records are written in grouped order, so an item's pixels are
-// contiguous.  Grouping: the tile's distinct keys go into a 2048-slot hash table (atomicCAS), the pixels
-// are ranked inside their slot with the radix machinery (match.any per warp round, per-warp counters, fixed
-// (warp, round, lane) order), slots are laid out by a block scan.  Which slot a key gets is a race, so
-// the ORDER OF GROUPS inside a tile may differ run to run; nothing downstream depends on it (items are
-// sorted by cell key, and a cell has one group per tile).
-//   item value = tile << 14 | first slot << 4 | (length - 1);  pixel record = {ratio0, ratio1, ratio2, pixel in tile}
-constexpr int TILE_DIM = 32, TILE_PIX = TILE_DIM * TILE_DIM;
-constexpr int HASH_SLOTS = 2048;
+// K1: one WARP per 32 x 8 pixel tile of one frame: voxelise its 256 pixels (one image row of the tile per
+// round), and group them by cell inside shared memory.  Neighbouring pixels fall into the same cell (a
+// (cell, frame) segment averages ~4 pixels), so what leaves the tile is an ITEM list -- (cell key, tile, first
+// slot, length <= 16) -- a few times shorter than the pixel list; the pixel records are written in grouped
+// order, so an item's pixels are contiguous.  Grouping: per round, match.any finds the lanes that share a
+// key; the first of them looks the key up in (or adds it to) the warp's 512-slot hash table; a pixel's rank
+// inside its group is the group's count so far plus its rank among the round's matching lanes, i.e. the
+// pixels of a group are in (row, column) order.  Which slot a key gets depends on the probing races of one
+// round's leaders, so the ORDER OF GROUPS inside a tile may differ run to run; nothing downstream depends on
+// it (items are sorted by cell key, and a cell has one group per tile).
+//   item value = tile << 12 | first slot << 4 | (length - 1);  pixel record = {ratio0, ratio1, ratio2, pixel in tile}
+constexpr int TILE_W = 32, TILE_H = 8, TILE_PIX = TILE_W * TILE_H;
+constexpr int WHASH = 512;                       // hash slots per warp (>= 2 x pixels of a tile)
 constexpr int ITEM_MAX = 16;                     // pixels per item
 constexpr uint32_t HASH_EMPTY = 0xffffffffu;
 constexpr int TASK_ITEMS = 64;                   // items per accumulate task; runs never cross a task
+constexpr uint32_t MAX_TILES = 1u << 20;         // tile ids are 20 bits of the item value
+
+__device__ __forceinline__ uint32_t item_tile(uint32_t v) { return v >> 12; }
+__device__ __forceinline__ uint32_t item_pos(uint32_t v) { return (v >> 4) & (TILE_PIX - 1); }
+__device__ __forceinline__ uint32_t item_len(uint32_t v) { return (v & 15u) + 1u; }
 
 struct TileGeom {
     int H, W;                // camera
@@ -134,172 +140,169 @@ __host__ __device__ inline TileGeom make_tiles(int H, int W)
 {
     TileGeom t;
     t.H = H; t.W = W;
-    t.tiles_x = (W + TILE_DIM - 1) / TILE_DIM;
-    t.tpf = t.tiles_x * ((H + TILE_DIM - 1) / TILE_DIM);
+    t.tiles_x = (W + TILE_W - 1) / TILE_W;
+    t.tpf = t.tiles_x * ((H + TILE_H - 1) / TILE_H);
     return t;
 }
 
-struct TileSmem {
-    uint32_t hkey[HASH_SLOTS];
-    uint16_t hcnt[8][HASH_SLOTS];                // per warp: pixels of the slot seen so far / exclusive warp offsets
-    uint16_t gstart[HASH_SLOTS], istart[HASH_SLOTS], total[HASH_SLOTS];
-    uint32_t warp_sum[8];
+struct WarpTile {
+    uint32_t hkey[WHASH];
+    uint16_t cnt[WHASH], start[WHASH], istart[WHASH];
     float P[12], spacing[6];
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_tile_voxelise(const float *__restrict__ rays, const float *__restrict__ depth, const float *__restrict__ pose,
-                TileGeom tg, const float *__restrict__ bins_x, int nx, const float *__restrict__ bins_y, int ny,
-                const float *__restrict__ bins_z, int nz, CellGrid g, float min_d, float max_d,
+                TileGeom tg, uint32_t ntiles, const float *__restrict__ bins_x, int nx, const float *__restrict__ bins_y,
+                int ny, const float *__restrict__ bins_z, int nz, CellGrid g, float min_d, float max_d,
                 uint4 *__restrict__ rec, uint32_t *__restrict__ tkey, uint32_t *__restrict__ tval,
                 uint32_t *__restrict__ tcount, uint32_t *__restrict__ counters)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem &S = *reinterpret_cast<TileSmem *>(smem_raw);
+    __shared__ WarpTile s_w[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t frame = blockIdx.y, tif = blockIdx.x;
-    const uint32_t tile = frame * (uint32_t)tg.tpf + tif;
-    const int y0 = (int)(tif / (uint32_t)tg.tiles_x) * TILE_DIM, x0 = (int)(tif % (uint32_t)tg.tiles_x) * TILE_DIM;
-    if (tid < 12) S.P[tid] = pose[(size_t)frame * 12 + tid];
-    if (tid >= 32 && tid < 35) {
-        const int a = tid - 32;
+    if (blockIdx.x == 0 && tid < MB_NUM_COUNTERS) counters[tid] = 0;
+    const uint32_t tile = blockIdx.x * 8u + warp;
+    if (tile >= ntiles) return;
+    WarpTile &S = s_w[warp];
+    const uint32_t frame = tile / (uint32_t)tg.tpf, tif = tile - frame * (uint32_t)tg.tpf;
+    const int y0 = (int)(tif / (uint32_t)tg.tiles_x) * TILE_H, x0 = (int)(tif % (uint32_t)tg.tiles_x) * TILE_W;
+    if (lane < 12) S.P[lane] = pose[(size_t)frame * 12 + lane];
+    if (lane >= 12 && lane < 15) {
+        const int a = lane - 12;
         const float *bb = a == 0 ? bins_x : a == 1 ? bins_y : bins_z;
         const int nb = a == 0 ? nx : a == 1 ? ny : nz;
         S.spacing[2 * a] = __ldg(bb);
         S.spacing[2 * a + 1] = bins_scale(bb, nb);
     }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid < MB_NUM_COUNTERS) counters[tid] = 0;
-    for (int i = tid; i < HASH_SLOTS; i += 256) S.hkey[i] = HASH_EMPTY;
-    for (int i = tid; i < 8 * HASH_SLOTS / 2; i += 256) ((uint32_t *)&S.hcnt[0][0])[i] = 0u;
-    __syncthreads();
+    for (int i = lane; i < WHASH; i += 32) { S.hkey[i] = HASH_EMPTY; S.cnt[i] = 0; }
+    __syncwarp();
 
-    // ---- voxelise: pixel l = r * 256 + tid of the tile -------------------------------------------------
-    uint32_t key[4], slot[4], rk[4];
-    float q[4][3];
+    const uint32_t ltmask = (1u << lane) - 1u;
+    uint32_t sr[TILE_H];                              // slot | rank << 16 of the lane's pixel in row r (slot WHASH: invalid)
+    float q[TILE_H][3];
     const size_t fbase = (size_t)frame * tg.H * tg.W;
+    const int x = x0 + lane;
+    // the lane's 8 pixels (column x, rows y0 .. y0 + 7) in two halves of 4: loads first, then the fp32 chain of the
+    // reference, then one grouping round per image row
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int l = r * 256 + tid;
-        const int y = y0 + (l >> 5), x = x0 + (l & 31);
-        key[r] = HASH_EMPTY;
-        q[r][0] = q[r][1] = q[r][2] = 0.f;
-        if (y < tg.H && x < tg.W) {
-            const size_t p = (size_t)y * tg.W + x;
-            float r0, r1, r2;
-            orient(S.P, rays[3 * p], rays[3 * p + 1], rays[3 * p + 2], r0, r1, r2);
-            const BinResult b = bin_point_fast(bins_x, nx, bins_y, ny, bins_z, nz, S.spacing, S.P[9], S.P[10], S.P[11],
-                                               r0, r1, r2, depth[fbase + p], min_d, max_d);
-            if (b.ok) {
-                // map axes are (y flipped, x, z) = input axes (1, 0, 2): base_projection_layer.py:339
-                q[r][0] = b.q1; q[r][1] = b.q0; q[r][2] = b.q2;
-                const int e0 = q[r][0] < 0.5f ? b.i1 : b.i1 + 1;       // lower corner + 1
-                const int e1 = q[r][1] < 0.5f ? b.i0 : b.i0 + 1;
-                const int e2 = q[r][2] < 0.5f ? b.i2 : b.i2 + 1;
-                key[r] = cell_key(g, e0, e1, e2);
+    for (int half = 0; half < 2; ++half) {
+        float d[4], ray[4][3];
+        uint32_t key[4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int y = y0 + 4 * half + rr;
+            d[rr] = 0.f;
+            ray[rr][0] = ray[rr][1] = ray[rr][2] = 0.f;
+            if (y < tg.H && x < tg.W) {
+                const size_t p = (size_t)y * tg.W + x;
+                d[rr] = __ldg(depth + fbase + p);
+                ray[rr][0] = __ldg(rays + 3 * p); ray[rr][1] = __ldg(rays + 3 * p + 1); ray[rr][2] = __ldg(rays + 3 * p + 2);
             }
         }
-    }
-    // ---- distinct keys -> hash slots -----------------------------------------------------------------------
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        slot[r] = HASH_SLOTS;
-        if (key[r] != HASH_EMPTY) {
-            uint32_t h = (key[r] * 2654435761u) >> 21;
-            for (;;) {
-                const uint32_t old = atomicCAS(&S.hkey[h], HASH_EMPTY, key[r]);
-                if (old == HASH_EMPTY || old == key[r]) break;
-                h = (h + 1) & (HASH_SLOTS - 1);
+        for (int rr = 0; rr < 4; ++rr) {
+            const int r = 4 * half + rr;
+            key[rr] = 0xffffffe0u + lane;             // above every cell key: never matches another lane
+            q[r][0] = q[r][1] = q[r][2] = 0.f;
+            if (y0 + r < tg.H && x < tg.W) {
+                float r0, r1, r2;
+                orient(S.P, ray[rr][0], ray[rr][1], ray[rr][2], r0, r1, r2);
+                const BinResult b = bin_point_fast(bins_x, nx, bins_y, ny, bins_z, nz, S.spacing, S.P[9], S.P[10], S.P[11],
+                                                   r0, r1, r2, d[rr], min_d, max_d);
+                if (b.ok) {
+                    // map axes are (y flipped, x, z) = input axes (1, 0, 2): base_projection_layer.py:339
+                    q[r][0] = b.q1; q[r][1] = b.q0; q[r][2] = b.q2;
+                    const int e0 = q[r][0] < 0.5f ? b.i1 : b.i1 + 1;       // lower corner + 1
+                    const int e1 = q[r][1] < 0.5f ? b.i0 : b.i0 + 1;
+                    const int e2 = q[r][2] < 0.5f ? b.i2 : b.i2 + 1;
+                    key[rr] = cell_key(g, e0, e1, e2);
+                }
             }
-            slot[r] = h;
+        }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int r = 4 * half + rr;
+            const bool valid = key[rr] < 0xffffffe0u;
+            const uint32_t m = __match_any_sync(FULL, key[rr]);
+            const int leader = __ffs(m) - 1;
+            uint32_t sl = 0;
+            if (valid && lane == leader) {
+                uint32_t h = (key[rr] * 2654435761u) >> 23;           // 9 bits
+                for (;;) {
+                    const uint32_t old = atomicCAS(&S.hkey[h], HASH_EMPTY, key[rr]);
+                    if (old == HASH_EMPTY || old == key[rr]) break;
+                    h = (h + 1) & (WHASH - 1);
+                }
+                sl = h;
+            }
+            sl = __shfl_sync(FULL, sl, leader);
+            const uint32_t prev = valid ? S.cnt[sl] : 0u;
+            __syncwarp();
+            if (valid && lane == leader) S.cnt[sl] = (uint16_t)(prev + __popc(m));
+            __syncwarp();
+            sr[r] = valid ? (sl | ((prev + __popc(m & ltmask)) << 16)) : (uint32_t)WHASH;
         }
     }
-    // ---- rank inside the slot: order (warp, round, lane) ---------------------------------------------------
+    // ---- lay the groups out: lane owns slots lane, lane + 32, ... ---------------------------------------------
+    uint32_t mine = 0;                                // pixels | items << 16 of this lane's slots
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const bool valid = slot[r] < HASH_SLOTS;
-        const uint32_t m = __match_any_sync(FULL, valid ? slot[r] : HASH_SLOTS + lane);
-        const uint32_t rank = __popc(m & ((1u << lane) - 1u));
-        const uint32_t prev = valid ? S.hcnt[warp][slot[r]] : 0u;
-        __syncwarp();
-        if (valid && rank == 0) S.hcnt[warp][slot[r]] = (uint16_t)(prev + __popc(m));
-        __syncwarp();
-        rk[r] = prev + rank;
+    for (int j = 0; j < WHASH / 32; ++j) {
+        const uint32_t c = S.cnt[lane + 32 * j];
+        mine += c | (((c + ITEM_MAX - 1) / ITEM_MAX) << 16);
     }
-    __syncthreads();
-    // ---- lay the slots out: thread t owns slots t, t + 256, ... -------------------------------------------------
-    uint32_t mine = 0;                              // pixels | items << 16 of this thread's slots
-#pragma unroll
-    for (int j = 0; j < HASH_SLOTS / 256; ++j) {
-        const int sl = tid + 256 * j;
-        uint32_t run = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const uint32_t c = S.hcnt[w][sl];
-            S.hcnt[w][sl] = (uint16_t)run;
-            run += c;
-        }
-        S.total[sl] = (uint16_t)run;
-        mine += run | (((run + ITEM_MAX - 1) / ITEM_MAX) << 16);
-    }
-    uint32_t inc = mine;                            // block exclusive scan of the packed pair
+    uint32_t inc = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t o = __shfl_up_sync(FULL, inc, d);
         if (lane >= d) inc += o;
     }
-    if (lane == 31) S.warp_sum[warp] = inc;
-    __syncthreads();
+    const uint32_t nitems = __shfl_sync(FULL, inc, 31) >> 16;
     uint32_t base = inc - mine;
-    for (int w = 0; w < warp; ++w) base += S.warp_sum[w];
-    uint32_t nitems = 0;
-    for (int w = 0; w < 8; ++w) nitems += S.warp_sum[w] >> 16;
-#pragma unroll
-    for (int j = 0; j < HASH_SLOTS / 256; ++j) {
-        const int sl = tid + 256 * j;
-        const uint32_t run = S.total[sl];
-        S.gstart[sl] = (uint16_t)(base & 0xffffu);
-        S.istart[sl] = (uint16_t)(base >> 16);
-        base += run | (((run + ITEM_MAX - 1) / ITEM_MAX) << 16);
-    }
-    __syncthreads();
-    // ---- pixel records in grouped order, items ------------------------------------------------------------------
     const size_t tbase = (size_t)tile * TILE_PIX;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-        if (slot[r] < HASH_SLOTS) {
-            const uint32_t pos = (uint32_t)S.gstart[slot[r]] + S.hcnt[warp][slot[r]] + rk[r];
-            rec[tbase + pos] = make_uint4(__float_as_uint(q[r][0]), __float_as_uint(q[r][1]), __float_as_uint(q[r][2]),
-                                          (uint32_t)(r * 256 + tid));
-        }
-#pragma unroll
-    for (int j = 0; j < HASH_SLOTS / 256; ++j) {
-        const int sl = tid + 256 * j;
-        const uint32_t run = S.total[sl];
-        if (run) {
-            const uint32_t k = S.hkey[sl], gs = S.gstart[sl], is = S.istart[sl];
-            for (uint32_t o = 0, n = 0; o < run; o += ITEM_MAX, ++n) {
+    for (int j = 0; j < WHASH / 32; ++j) {
+        const int sl = lane + 32 * j;
+        const uint32_t c = S.cnt[sl];
+        S.start[sl] = (uint16_t)(base & 0xffffu);
+        if (c) {
+            const uint32_t k = S.hkey[sl], gs = base & 0xffffu, is = base >> 16;
+            for (uint32_t o = 0, n = 0; o < c; o += ITEM_MAX, ++n) {
                 tkey[tbase + is + n] = k;
-                tval[tbase + is + n] = (tile << 14) | ((gs + o) << 4) | (min((uint32_t)ITEM_MAX, run - o) - 1u);
+                tval[tbase + is + n] = (tile << 12) | ((gs + o) << 4) | (min((uint32_t)ITEM_MAX, c - o) - 1u);
             }
         }
+        base += c | (((c + ITEM_MAX - 1) / ITEM_MAX) << 16);
     }
-    if (tid == 0) tcount[tile] = nitems;
+    __syncwarp();
+    // ---- pixel records in grouped order ------------------------------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < TILE_H; ++r) {
+        const uint32_t sl = sr[r] & 0xffffu;
+        if (sl < WHASH) {
+            const uint32_t pos = (uint32_t)S.start[sl] + (sr[r] >> 16);
+            rec[tbase + pos] = make_uint4(__float_as_uint(q[r][0]), __float_as_uint(q[r][1]), __float_as_uint(q[r][2]),
+                                          (uint32_t)(r * TILE_W + lane));
+        }
+    }
+    if (lane == 0) tcount[tile] = nitems;
 }
 
-// K1b: dense item list in tile order (toff = exclusive scan of the tile counts)
+// K1b: dense item list in tile order (toff = exclusive scan of the tile counts); one warp per tile
 __global__ void __launch_bounds__(256)
 k_tile_compact(const uint32_t *__restrict__ tkey, const uint32_t *__restrict__ tval, const uint32_t *__restrict__ tcount,
                const uint32_t *__restrict__ toff, uint32_t ntiles, uint32_t *__restrict__ ikey,
                uint32_t *__restrict__ ival, uint32_t *__restrict__ counters)
 {
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = blockIdx.x * 8u + (threadIdx.x >> 5);
+    if (tile >= ntiles) return;
+    const int lane = threadIdx.x & 31;
     const uint32_t cnt = tcount[tile], off = toff[tile];
     const size_t tbase = (size_t)tile * TILE_PIX;
-    for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+    for (uint32_t j = lane; j < cnt; j += 32) {
         ikey[off + j] = tkey[tbase + j];
         ival[off + j] = tval[tbase + j];
     }
-    if (tile == ntiles - 1 && threadIdx.x == 0) counters[MB_CNT_NVALID] = off + cnt;     // number of items
+    if (tile == ntiles - 1 && lane == 0) counters[MB_CNT_NVALID] = off + cnt;     // number of items
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -358,7 +361,7 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
         pv = __shfl_sync(FULL, val[r], 31);
         const bool valid = i < n;
         const bool chead = valid && (i == 0 || kprev != key[r]);
-        const bool shead = valid && (chead || (vprev >> 14) / tpf != (val[r] >> 14) / tpf);
+        const bool shead = valid && (chead || item_tile(vprev) / tpf != item_tile(val[r]) / tpf);
         const bool rhead = valid && (chead || (i % TASK_ITEMS) == 0);
         cm[r] = __ballot_sync(FULL, chead);
         sm[r] = __ballot_sync(FULL, shead);
@@ -408,7 +411,7 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
             const uint32_t crank = cb + __popc(cm[r] & lt), srank = sb + __popc(sm[r] & lt), rrank = rb + __popc(rm[r] & lt);
             if ((sm[r] >> lane) & 1u) {
                 O.seg_start[srank] = i;
-                O.seg_frame[srank] = (val[r] >> 14) / tpf;
+                O.seg_frame[srank] = item_tile(val[r]) / tpf;
             }
             if ((cm[r] >> lane) & 1u) {
                 const uint32_t k = key[r];
@@ -487,8 +490,8 @@ k_seg_sums(const uint32_t *__restrict__ ival, const uint4 *__restrict__ rec, con
         for (int k = 0; k < 8; ++k) { W[k] = 0.f; S2[k] = 0.f; }
         for (uint32_t it = beg; it < end; ++it) {
             const uint32_t v = ival[it];
-            const uint4 *pr = rec + (size_t)(v >> 14) * TILE_PIX + ((v >> 4) & 1023u);
-            const uint32_t len = (v & 15u) + 1u;
+            const uint4 *pr = rec + (size_t)item_tile(v) * TILE_PIX + item_pos(v);
+            const uint32_t len = item_len(v);
             for (uint32_t i = 0; i < len; i += 4) {
                 uint4 r[4];
 #pragma unroll
@@ -775,7 +778,7 @@ k_cell_accumulate(const AccArgs A)
                 if (i < end) {
                     const uint32_t v = A.ival[i];
                     key[h] = A.ikey[i];
-                    len[h] = (v & 15u) + 1u;
+                    len[h] = item_len(v);
                     const uint32_t w = i >> 5;
                     s_ival[warp][32 * h + lane] = v;
                     s_seg[warp][32 * h + lane] = A.soff[w] + __popc(A.smask[w] & lemask) - 1u;
@@ -843,8 +846,8 @@ k_cell_accumulate(const AccArgs A)
                     const int lo = s_p2i[warp][qp];
                     const uint32_t v = s_ival[warp][lo], off = qp - s_pre[warp][lo];
                     phead = off == 0 && ((ihead[lo >> 5] >> (lo & 31)) & 1u);
-                    const uint32_t tile = v >> 14;
-                    const uint4 r = __ldg(A.rec + (size_t)tile * TILE_PIX + ((v >> 4) & 1023u) + off);
+                    const uint32_t tile = item_tile(v);
+                    const uint4 r = __ldg(A.rec + (size_t)tile * TILE_PIX + item_pos(v) + off);
                     const uint32_t s = s_seg[warp][lo];
                     float gk[8];
 #pragma unroll
@@ -854,7 +857,7 @@ k_cell_accumulate(const AccArgs A)
                     for (int k = 0; k < 8; ++k) c[k] = c[k] * c[k] * gk[k];
                     const uint32_t frame = tile / (uint32_t)A.tg.tpf, tif = tile - frame * (uint32_t)A.tg.tpf;
                     const uint32_t tyo = tif / (uint32_t)A.tg.tiles_x, txo = tif - tyo * (uint32_t)A.tg.tiles_x;
-                    const uint32_t y = tyo * TILE_DIM + (r.w >> 5), x = txo * TILE_DIM + (r.w & 31u);
+                    const uint32_t y = tyo * TILE_H + (r.w >> 5), x = txo * TILE_W + (r.w & 31u);
                     if (ONEHOT) {
                         src = (uint32_t)A.class_ids[(size_t)frame * np + y * A.fi.W + x];
                     } else {
@@ -1287,7 +1290,7 @@ static uint64_t padded_pixels(int H, int W, int T)
 {
     const TileGeom tg = make_tiles(H, W);
     const uint64_t ntiles = (uint64_t)T * tg.tpf;
-    if (ntiles >= (1u << 18) || T > MB_MAX_CHUNK_FRAMES) return 0;      // tile ids are 18 bits of the item value
+    if (ntiles >= MAX_TILES || T > MB_MAX_CHUNK_FRAMES) return 0;
     return ntiles * TILE_PIX;
 }
 
@@ -1312,11 +1315,11 @@ size_t mbk_batch_min_workspace_bytes(int H, int W, int nx, int ny, int nz, int T
     return carve_cells(b, nullptr, 0, n, g) + minruns * run_bytes(F) + 512;
 }
 
-// largest number of frames one chunk can hold at all (tile ids are 18 bits; MB_MAX_CHUNK_FRAMES frames)
+// largest number of frames one chunk can hold at all (20-bit tile ids; MB_MAX_CHUNK_FRAMES frames)
 int mbk_batch_max_chunk_frames(int H, int W)
 {
     const TileGeom tg = make_tiles(H, W);
-    int t = (int)(((1u << 18) - 1) / (uint32_t)tg.tpf);
+    int t = (int)((MAX_TILES - 1) / (uint32_t)tg.tpf);
     if (t > MB_MAX_CHUNK_FRAMES) t = MB_MAX_CHUNK_FRAMES;
     return t;
 }
@@ -1349,7 +1352,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     MB_REQUIRE(padded != 0 && padded < 0x7fffffffull, "too many frames or pixels per chunk");
     const uint32_t n = (uint32_t)padded, ntiles = n / TILE_PIX;
     const CellGrid g = make_cells(ny - 1, nx - 1, nz - 1);
-    MB_REQUIRE((uint64_t)g.E0 * g.E1 * g.E2 < 0xfffffff0ull, "map too large for 32-bit cell keys");
+    MB_REQUIRE((uint64_t)g.E0 * g.E1 * g.E2 < 0xffffffe0ull, "map too large for 32-bit cell keys");
     MB_REQUIRE(class_ids != nullptr || (uint64_t)T * fh * fw < 0xffffffffull, "too many feature rows per chunk");
     CellBuffers b;
     MB_REQUIRE(carve_cells(b, workspace, workspace_bytes, n, g) + 512 <= workspace_bytes, "batch workspace too small");
@@ -1368,13 +1371,12 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     int rc;
     if ((rc = stage_mark(stream, 0))) return rc;
     uint32_t *tkey = b.keys_b, *tval = b.pids_b;          // tile-local item lists live in the sort's second buffers
-    MB_CHECK_CUDA(cudaFuncSetAttribute(k_tile_voxelise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
-    dim3 grid((unsigned)tg.tpf, (unsigned)T);
-    k_tile_voxelise<<<grid, 256, sizeof(TileSmem), stream>>>(rays, depth, pose, tg, bins_x, nx, bins_y, ny, bins_z, nz, g,
-                                                             min_d, max_d, b.rec, tkey, tval, b.tcount, b.counters);
+    k_tile_voxelise<<<(ntiles + 7) / 8, 256, 0, stream>>>(rays, depth, pose, tg, ntiles, bins_x, nx, bins_y, ny, bins_z, nz, g,
+                                                          min_d, max_d, b.rec, tkey, tval, b.tcount, b.counters);
     MB_LAUNCHED();
     if ((rc = mb_exclusive_scan_u32(stream, b.tcount, b.toff, ntiles, b.scan_ws, b.scan_bytes))) return rc;
-    k_tile_compact<<<ntiles, 256, 0, stream>>>(tkey, tval, b.tcount, b.toff, ntiles, b.keys_a, b.pids_a, b.counters);
+    k_tile_compact<<<(ntiles + 7) / 8, 256, 0, stream>>>(tkey, tval, b.tcount, b.toff, ntiles, b.keys_a, b.pids_a,
+                                                         b.counters);
     MB_LAUNCHED();
     if ((rc = stage_mark(stream, 1))) return rc;
     int bits = 1;

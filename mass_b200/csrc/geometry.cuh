@@ -100,7 +100,30 @@ __device__ __forceinline__ float bins_scale(const float *__restrict__ bins, int 
     return (float)(n - 1) / (__ldg(bins + n - 1) - __ldg(bins));
 }
 
-// bin_point with precomputed spacing: spacing = {b0_x, scale_x, b0_y, scale_y, b0_z, scale_z}
+// Bucket of x for callers that only need VALID buckets: returns true iff bins[0] <= x < bins[n-1] (and x is
+// not NaN), i.e. iff torch.bucketize(x, bins, right=True) - 1 lies in [0, n-2]; then i is that value and
+// lo = bins[i], hi = bins[i+1].  One guess, at most one predicated step for near-uniform tables, and a
+// walk that only general tables ever enter.
+__device__ __forceinline__ bool bucket_valid(const float *__restrict__ bins, int n, float x, float b0, float scale,
+                                             int &i, float &lo, float &hi)
+{
+    const float gidx = (x - b0) * scale;
+    int k = (int)fminf(fmaxf(gidx, 0.f), (float)(n - 2));        // NaN -> 0
+    lo = __ldg(bins + k);
+    hi = __ldg(bins + k + 1);
+    if (x >= hi) {
+        if (k < n - 2) { ++k; lo = hi; hi = __ldg(bins + k + 1); }
+    } else if (x < lo) {
+        if (k > 0) { --k; hi = lo; lo = __ldg(bins + k); }
+    }
+    while (x >= hi && k < n - 2) { ++k; lo = hi; hi = __ldg(bins + k + 1); }
+    while (x < lo && k > 0) { --k; hi = lo; lo = __ldg(bins + k); }
+    i = k;
+    return x >= lo && x < hi;
+}
+
+// bin_point with precomputed spacing: spacing = {b0_x, scale_x, b0_y, scale_y, b0_z, scale_z}.  Indices and
+// ratios are only meaningful when ok.
 __device__ __forceinline__ BinResult bin_point_fast(const float *__restrict__ bins0, int n0,
                                                     const float *__restrict__ bins1, int n1,
                                                     const float *__restrict__ bins2, int n2,
@@ -111,19 +134,16 @@ __device__ __forceinline__ BinResult bin_point_fast(const float *__restrict__ bi
     const float x0 = __fadd_rn(o0, __fmul_rn(r0, d));
     const float x1 = __fadd_rn(o1, __fmul_rn(r1, d));
     const float x2 = __fadd_rn(o2, __fmul_rn(r2, d));
-    const Bucket k0 = bucket_right_edges(bins0, n0, x0, spacing[0], spacing[1]);
-    const Bucket k1 = bucket_right_edges(bins1, n1, x1, spacing[2], spacing[3]);
-    const Bucket k2 = bucket_right_edges(bins2, n2, x2, spacing[4], spacing[5]);
-    b.ok = (d >= min_d) && (d <= max_d) && k0.i >= 0 && k0.i < n0 - 1 && k1.i >= 0 && k1.i < n1 - 1 &&
-           k2.i >= 0 && k2.i < n2 - 1;
-    b.i0 = k0.i; b.i1 = k1.i; b.i2 = k2.i;
-    b.q0 = b.q1 = b.q2 = 0.f;
-    if (b.ok) {
-        b.q0 = __fdiv_rn(__fsub_rn(x0, k0.lo), __fsub_rn(k0.hi, k0.lo));
-        b.q1 = __fsub_rn(1.0f, __fdiv_rn(__fsub_rn(x1, k1.lo), __fsub_rn(k1.hi, k1.lo)));
-        b.q2 = __fdiv_rn(__fsub_rn(x2, k2.lo), __fsub_rn(k2.hi, k2.lo));
-        b.i1 = n1 - 2 - k1.i;
-    }
+    float l0, h0, l1, h1, l2, h2;
+    int i1;
+    const bool v0 = bucket_valid(bins0, n0, x0, spacing[0], spacing[1], b.i0, l0, h0);
+    const bool v1 = bucket_valid(bins1, n1, x1, spacing[2], spacing[3], i1, l1, h1);
+    const bool v2 = bucket_valid(bins2, n2, x2, spacing[4], spacing[5], b.i2, l2, h2);
+    b.ok = (d >= min_d) && (d <= max_d) && v0 && v1 && v2;
+    b.q0 = __fdiv_rn(__fsub_rn(x0, l0), __fsub_rn(h0, l0));
+    b.q1 = __fsub_rn(1.0f, __fdiv_rn(__fsub_rn(x1, l1), __fsub_rn(h1, l1)));
+    b.q2 = __fdiv_rn(__fsub_rn(x2, l2), __fsub_rn(h2, l2));
+    b.i1 = n1 - 2 - i1;
     return b;
 }
 
