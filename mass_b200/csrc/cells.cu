@@ -109,8 +109,8 @@ __device__ __forceinline__ int find_cell(const uint32_t *__restrict__ ucell, uin
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: one WARP per 32 x 8 pixel tile of one frame: voxelise its 256 pixels (one image row of the tile per
-// round), and group them by cell inside shared memory.  Neighbouring pixels fall into the same cell (a
+// K1: after the per-pixel voxelisation, one WARP per 32 x 8 pixel tile of one frame groups the tile's 256 pixels by
+// cell inside shared memory (one image row of the tile per round).  Neighbouring pixels fall into the same cell (a
 // (cell, frame) segment averages ~4 pixels), so what leaves the tile is an ITEM list -- (cell key, tile, first
 // slot, length <= 16) -- a few times shorter than the pixel list; the pixel records are written in grouped
 // order, so an item's pixels are contiguous.  Grouping: per round, match.any finds the lanes that share a
@@ -145,103 +145,98 @@ __host__ __device__ inline TileGeom make_tiles(int H, int W)
     return t;
 }
 
+// K1a: grid = (pixel blocks, frames): pixel -> {cell key (or >= 0xffffffe0: invalid), 3 in-voxel ratios}, in
+// image order.  Pure per-pixel math at full occupancy; the grouping kernel below re-reads it.
+__global__ void __launch_bounds__(256)
+k_cell_voxelise(const float *__restrict__ rays, const float *__restrict__ depth, const float *__restrict__ pose,
+                uint32_t npix, const float *__restrict__ bins_x, int nx, const float *__restrict__ bins_y, int ny,
+                const float *__restrict__ bins_z, int nz, CellGrid g, float min_d, float max_d,
+                uint4 *__restrict__ pix, uint32_t *__restrict__ counters)
+{
+    __shared__ float P[12], spacing[6];
+    const uint32_t t = blockIdx.y;
+    if (threadIdx.x < 12) P[threadIdx.x] = pose[(size_t)t * 12 + threadIdx.x];
+    if (threadIdx.x >= 32 && threadIdx.x < 35) {
+        const int a = threadIdx.x - 32;
+        const float *bb = a == 0 ? bins_x : a == 1 ? bins_y : bins_z;
+        const int nb = a == 0 ? nx : a == 1 ? ny : nz;
+        spacing[2 * a] = __ldg(bb);
+        spacing[2 * a + 1] = bins_scale(bb, nb);
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < MB_NUM_COUNTERS) counters[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const size_t pid = (size_t)t * npix + p;
+    float r0, r1, r2;
+    orient(P, rays[3 * (size_t)p], rays[3 * (size_t)p + 1], rays[3 * (size_t)p + 2], r0, r1, r2);
+    const BinResult b = bin_point_fast(bins_x, nx, bins_y, ny, bins_z, nz, spacing, P[9], P[10], P[11], r0, r1, r2,
+                                       depth[pid], min_d, max_d);
+    uint4 out = make_uint4(0xffffffffu, 0u, 0u, 0u);
+    if (b.ok) {
+        // map axes are (y flipped, x, z) = input axes (1, 0, 2): base_projection_layer.py:339
+        const float q0 = b.q1, q1 = b.q0, q2 = b.q2;
+        const int e0 = q0 < 0.5f ? b.i1 : b.i1 + 1;       // lower corner + 1
+        const int e1 = q1 < 0.5f ? b.i0 : b.i0 + 1;
+        const int e2 = q2 < 0.5f ? b.i2 : b.i2 + 1;
+        out = make_uint4(cell_key(g, e0, e1, e2), __float_as_uint(q0), __float_as_uint(q1), __float_as_uint(q2));
+    }
+    pix[pid] = out;
+}
+
 struct WarpTile {
     uint32_t hkey[WHASH];
-    uint16_t cnt[WHASH], start[WHASH], istart[WHASH];
-    float P[12], spacing[6];
+    uint16_t cnt[WHASH], start[WHASH];
 };
 
-__global__ void __launch_bounds__(256, 3)
-k_tile_voxelise(const float *__restrict__ rays, const float *__restrict__ depth, const float *__restrict__ pose,
-                TileGeom tg, uint32_t ntiles, const float *__restrict__ bins_x, int nx, const float *__restrict__ bins_y,
-                int ny, const float *__restrict__ bins_z, int nz, CellGrid g, float min_d, float max_d,
-                uint4 *__restrict__ rec, uint32_t *__restrict__ tkey, uint32_t *__restrict__ tval,
-                uint32_t *__restrict__ tcount, uint32_t *__restrict__ counters)
+// K1b: one warp per 32 x 8 tile groups the tile's pixels by cell (see above) and writes the grouped records
+// and the tile's items.
+__global__ void __launch_bounds__(256)
+k_tile_group(const uint4 *__restrict__ pix, TileGeom tg, uint32_t ntiles, uint4 *__restrict__ rec,
+             uint32_t *__restrict__ tkey, uint32_t *__restrict__ tval, uint32_t *__restrict__ tcount)
 {
     __shared__ WarpTile s_w[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (blockIdx.x == 0 && tid < MB_NUM_COUNTERS) counters[tid] = 0;
     const uint32_t tile = blockIdx.x * 8u + warp;
     if (tile >= ntiles) return;
     WarpTile &S = s_w[warp];
     const uint32_t frame = tile / (uint32_t)tg.tpf, tif = tile - frame * (uint32_t)tg.tpf;
     const int y0 = (int)(tif / (uint32_t)tg.tiles_x) * TILE_H, x0 = (int)(tif % (uint32_t)tg.tiles_x) * TILE_W;
-    if (lane < 12) S.P[lane] = pose[(size_t)frame * 12 + lane];
-    if (lane >= 12 && lane < 15) {
-        const int a = lane - 12;
-        const float *bb = a == 0 ? bins_x : a == 1 ? bins_y : bins_z;
-        const int nb = a == 0 ? nx : a == 1 ? ny : nz;
-        S.spacing[2 * a] = __ldg(bb);
-        S.spacing[2 * a + 1] = bins_scale(bb, nb);
-    }
     for (int i = lane; i < WHASH; i += 32) { S.hkey[i] = HASH_EMPTY; S.cnt[i] = 0; }
-    __syncwarp();
-
     const uint32_t ltmask = (1u << lane) - 1u;
-    uint32_t sr[TILE_H];                              // slot | rank << 16 of the lane's pixel in row r (slot WHASH: invalid)
-    float q[TILE_H][3];
     const size_t fbase = (size_t)frame * tg.H * tg.W;
     const int x = x0 + lane;
-    // the lane's 8 pixels (column x, rows y0 .. y0 + 7) in two halves of 4: loads first, then the fp32 chain of the
-    // reference, then one grouping round per image row
+    uint32_t pkey[TILE_H];                            // keys of the lane's 8 pixels: column x, rows y0 .. y0 + 7
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        float d[4], ray[4][3];
-        uint32_t key[4];
+    for (int r = 0; r < TILE_H; ++r) {
+        pkey[r] = 0xffffffffu;
+        if (y0 + r < tg.H && x < tg.W) pkey[r] = __ldg(pix + fbase + (size_t)(y0 + r) * tg.W + x).x;
+    }
+    __syncwarp();
+    uint32_t sr[TILE_H];                              // slot | rank << 16 (slot WHASH: invalid pixel)
+    // ---- one grouping round per image row ------------------------------------------------------------------------
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            const int y = y0 + 4 * half + rr;
-            d[rr] = 0.f;
-            ray[rr][0] = ray[rr][1] = ray[rr][2] = 0.f;
-            if (y < tg.H && x < tg.W) {
-                const size_t p = (size_t)y * tg.W + x;
-                d[rr] = __ldg(depth + fbase + p);
-                ray[rr][0] = __ldg(rays + 3 * p); ray[rr][1] = __ldg(rays + 3 * p + 1); ray[rr][2] = __ldg(rays + 3 * p + 2);
+    for (int r = 0; r < TILE_H; ++r) {
+        const bool valid = pkey[r] < 0xffffffe0u;
+        const uint32_t key = valid ? pkey[r] : 0xffffffe0u + lane;   // invalid lanes never match another lane
+        const uint32_t m = __match_any_sync(FULL, key);
+        const int leader = __ffs(m) - 1;
+        uint32_t sl = 0;
+        if (valid && lane == leader) {
+            uint32_t h = (key * 2654435761u) >> 23;                   // 9 bits
+            for (;;) {
+                const uint32_t old = atomicCAS(&S.hkey[h], HASH_EMPTY, key);
+                if (old == HASH_EMPTY || old == key) break;
+                h = (h + 1) & (WHASH - 1);
             }
+            sl = h;
         }
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            const int r = 4 * half + rr;
-            key[rr] = 0xffffffe0u + lane;             // above every cell key: never matches another lane
-            q[r][0] = q[r][1] = q[r][2] = 0.f;
-            if (y0 + r < tg.H && x < tg.W) {
-                float r0, r1, r2;
-                orient(S.P, ray[rr][0], ray[rr][1], ray[rr][2], r0, r1, r2);
-                const BinResult b = bin_point_fast(bins_x, nx, bins_y, ny, bins_z, nz, S.spacing, S.P[9], S.P[10], S.P[11],
-                                                   r0, r1, r2, d[rr], min_d, max_d);
-                if (b.ok) {
-                    // map axes are (y flipped, x, z) = input axes (1, 0, 2): base_projection_layer.py:339
-                    q[r][0] = b.q1; q[r][1] = b.q0; q[r][2] = b.q2;
-                    const int e0 = q[r][0] < 0.5f ? b.i1 : b.i1 + 1;       // lower corner + 1
-                    const int e1 = q[r][1] < 0.5f ? b.i0 : b.i0 + 1;
-                    const int e2 = q[r][2] < 0.5f ? b.i2 : b.i2 + 1;
-                    key[rr] = cell_key(g, e0, e1, e2);
-                }
-            }
-        }
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            const int r = 4 * half + rr;
-            const bool valid = key[rr] < 0xffffffe0u;
-            const uint32_t m = __match_any_sync(FULL, key[rr]);
-            const int leader = __ffs(m) - 1;
-            uint32_t sl = 0;
-            if (valid && lane == leader) {
-                uint32_t h = (key[rr] * 2654435761u) >> 23;           // 9 bits
-                for (;;) {
-                    const uint32_t old = atomicCAS(&S.hkey[h], HASH_EMPTY, key[rr]);
-                    if (old == HASH_EMPTY || old == key[rr]) break;
-                    h = (h + 1) & (WHASH - 1);
-                }
-                sl = h;
-            }
-            sl = __shfl_sync(FULL, sl, leader);
-            const uint32_t prev = valid ? S.cnt[sl] : 0u;
-            __syncwarp();
-            if (valid && lane == leader) S.cnt[sl] = (uint16_t)(prev + __popc(m));
-            __syncwarp();
-            sr[r] = valid ? (sl | ((prev + __popc(m & ltmask)) << 16)) : (uint32_t)WHASH;
-        }
+        sl = __shfl_sync(FULL, sl, leader);
+        const uint32_t prev = valid ? S.cnt[sl] : 0u;
+        __syncwarp();
+        if (valid && lane == leader) S.cnt[sl] = (uint16_t)(prev + __popc(m));
+        __syncwarp();
+        sr[r] = valid ? (sl | ((prev + __popc(m & ltmask)) << 16)) : (uint32_t)WHASH;
     }
     // ---- lay the groups out: lane owns slots lane, lane + 32, ... ---------------------------------------------
     uint32_t mine = 0;                                // pixels | items << 16 of this lane's slots
@@ -280,14 +275,14 @@ k_tile_voxelise(const float *__restrict__ rays, const float *__restrict__ depth,
         const uint32_t sl = sr[r] & 0xffffu;
         if (sl < WHASH) {
             const uint32_t pos = (uint32_t)S.start[sl] + (sr[r] >> 16);
-            rec[tbase + pos] = make_uint4(__float_as_uint(q[r][0]), __float_as_uint(q[r][1]), __float_as_uint(q[r][2]),
-                                          (uint32_t)(r * TILE_W + lane));
+            const uint4 px = __ldg(pix + fbase + (size_t)(y0 + r) * tg.W + x);       // second read: L2
+            rec[tbase + pos] = make_uint4(px.y, px.z, px.w, (uint32_t)(r * TILE_W + lane));
         }
     }
     if (lane == 0) tcount[tile] = nitems;
 }
 
-// K1b: dense item list in tile order (toff = exclusive scan of the tile counts); one warp per tile
+// K1c: dense item list in tile order (toff = exclusive scan of the tile counts); one warp per tile
 __global__ void __launch_bounds__(256)
 k_tile_compact(const uint32_t *__restrict__ tkey, const uint32_t *__restrict__ tval, const uint32_t *__restrict__ tcount,
                const uint32_t *__restrict__ toff, uint32_t ntiles, uint32_t *__restrict__ ikey,
@@ -1105,7 +1100,7 @@ k_affine_apply_rows(float *__restrict__ map, int F, const int64_t *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 struct CellBuffers {
     uint32_t *counters;
-    uint4 *rec;
+    uint4 *rec, *pix;
     uint32_t *keys_a, *keys_b, *pids_a, *pids_b;
     uint32_t *tcount, *toff;
     uint32_t *smask, *soff, *roff, *idx_state;
@@ -1134,6 +1129,7 @@ size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const Cel
     const size_t vcap = V < 8 * ncap ? V : 8 * ncap;                                       // touched voxels
     b.counters = a.take<uint32_t>(MB_NUM_COUNTERS);       // first: mb_layer_update_status reads them at offset 0
     b.rec = a.take<uint4>(n);
+    b.pix = a.take<uint4>(n);
     b.keys_a = a.take<uint32_t>(n); b.keys_b = a.take<uint32_t>(n);
     b.pids_a = a.take<uint32_t>(n); b.pids_b = a.take<uint32_t>(n);
     b.tcount = a.take<uint32_t>(ntiles + 1); b.toff = a.take<uint32_t>(ntiles + 1);
@@ -1371,8 +1367,11 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     int rc;
     if ((rc = stage_mark(stream, 0))) return rc;
     uint32_t *tkey = b.keys_b, *tval = b.pids_b;          // tile-local item lists live in the sort's second buffers
-    k_tile_voxelise<<<(ntiles + 7) / 8, 256, 0, stream>>>(rays, depth, pose, tg, ntiles, bins_x, nx, bins_y, ny, bins_z, nz, g,
-                                                          min_d, max_d, b.rec, tkey, tval, b.tcount, b.counters);
+    dim3 vgrid((npix + 255) / 256, (unsigned)T);
+    k_cell_voxelise<<<vgrid, 256, 0, stream>>>(rays, depth, pose, npix, bins_x, nx, bins_y, ny, bins_z, nz, g, min_d, max_d,
+                                               b.pix, b.counters);
+    MB_LAUNCHED();
+    k_tile_group<<<(ntiles + 7) / 8, 256, 0, stream>>>(b.pix, tg, ntiles, b.rec, tkey, tval, b.tcount);
     MB_LAUNCHED();
     if ((rc = mb_exclusive_scan_u32(stream, b.tcount, b.toff, ntiles, b.scan_ws, b.scan_bytes))) return rc;
     k_tile_compact<<<(ntiles + 7) / 8, 256, 0, stream>>>(tkey, tval, b.tcount, b.toff, ntiles, b.keys_a, b.pids_a,
