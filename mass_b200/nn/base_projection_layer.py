@@ -82,10 +82,10 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         return self.get_feature_map()
 
     # -- the hot path ----------------------------------------------------------------------------
-    def _fuse(self, pose, depth, features, class_ids, T, fold=None):
-        """pose [T,12] CPU f32; depth [T,H,W] ; features [T,fh,fw,F] or class_ids [T,H,W] int64.
-        fold = (partial_b, partial_a): fold the frames into a partial map instead of self.data
-        (frame-sharded scenes, mass_b200/nn/sharded.py)."""
+    def _prepare(self, pose, depth, features, class_ids, T):
+        """Host side of an update: moves / casts the inputs to device tensors of the library's layout and
+        sizes the scratch buffer.  pose [T,12] (CPU or device) f32; depth [T,H,W]; features [T,fh,fw,F] or
+        class_ids [T,H,W] int64.  Returns the argument record `_launch` takes."""
         device = _lib.require_cuda(self.data.device)
         if self.data.dtype != torch.float32 or not self.data.is_contiguous():
             raise ValueError("layer.data must be a contiguous float32 tensor")
@@ -107,6 +107,14 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
                 # the reference's repeat_interleave would produce a mis-shaped image here
                 raise ValueError("feature image %dx%d does not divide the camera %dx%d" % (fh, fw, H, W))
             features = features.contiguous()
+        return dict(pose=pose, depth=depth, features=features, class_ids=class_ids, T=T, fh=fh, fw=fw, device=device)
+
+    def _launch(self, prep, fold=None):
+        """Device side of an update: enqueues the kernels on the current stream.  No host work besides the
+        launches, no allocation once the scratch buffer exists: a call with the same `prep` can be captured
+        in a CUDA graph and replayed."""
+        device, T, fh, fw = prep["device"], prep["T"], prep["fh"], prep["fw"]
+        H, W, F = self.camera_height, self.camera_width, self.feature_size
         L = _lib.lib()
         nx, ny, nz = self.bins_x.numel(), self.bins_y.numel(), self.bins_z.numel()
         mode = _lib.MODE_EXACT if (self.exact and fold is None) else _lib.MODE_FAST
@@ -119,19 +127,42 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         if fold is not None:
             partial_b, partial_a = fold
             _lib.check(L.mb_layer_fold(
-                _lib.stream_ptr(device), _lib.ptr(self.rays), _lib.ptr(depth), _lib.ptr(features),
-                _lib.ptr(class_ids), _lib.ptr(pose), T, H, W, fh, fw, F, _lib.ptr(self.bins_x), nx,
+                _lib.stream_ptr(device), _lib.ptr(self.rays), _lib.ptr(prep["depth"]), _lib.ptr(prep["features"]),
+                _lib.ptr(prep["class_ids"]), _lib.ptr(prep["pose"]), T, H, W, fh, fw, F, _lib.ptr(self.bins_x), nx,
                 _lib.ptr(self.bins_y), ny, _lib.ptr(self.bins_z), nz, _lib.ptr(partial_b), _lib.ptr(partial_a),
                 float(self.interpolation_weight), float(self.min_ray_depth), float(self.max_ray_depth),
                 _lib.ptr(ws), ws.numel()))
             return self
         _lib.check(L.mb_layer_update(
-            _lib.stream_ptr(device), _lib.ptr(self.rays), _lib.ptr(depth), _lib.ptr(features),
-            _lib.ptr(class_ids), _lib.ptr(pose), T, H, W, fh, fw, F, _lib.ptr(self.bins_x), nx,
+            _lib.stream_ptr(device), _lib.ptr(self.rays), _lib.ptr(prep["depth"]), _lib.ptr(prep["features"]),
+            _lib.ptr(prep["class_ids"]), _lib.ptr(prep["pose"]), T, H, W, fh, fw, F, _lib.ptr(self.bins_x), nx,
             _lib.ptr(self.bins_y), ny, _lib.ptr(self.bins_z), nz, _lib.ptr(self.data),
             float(self.interpolation_weight), float(self.min_ray_depth), float(self.max_ray_depth),
             mode, _lib.ptr(ws), ws.numel()))
         return self
+
+    def _fuse(self, pose, depth, features, class_ids, T, fold=None):
+        """fold = (partial_b, partial_a): fold the frames into a partial map instead of self.data
+        (frame-sharded scenes, mass_b200/nn/sharded.py)."""
+        return self._launch(self._prepare(pose, depth, features, class_ids, T), fold=fold)
+
+    def prepare_batch(self, observations):
+        """The host half of update_batch: returns a record of device tensors for `update_prepared`.  Lets a
+        caller that replays the same frames (benchmarks, CUDA graphs) pay the host work once."""
+        if isinstance(observations, (list, tuple)):
+            keys = observations[0].keys()
+            observations = {k: torch.stack([torch.as_tensor(o[k]) for o in observations]) for k in keys}
+        T = int(torch.as_tensor(observations["yaw"]).reshape(-1).shape[0])
+        pose = camera_pose(torch.as_tensor(observations["position"]).reshape(T, 3),
+                           torch.as_tensor(observations["yaw"]).reshape(T),
+                           torch.as_tensor(observations["elevation"]).reshape(T))
+        if "features" in observations:
+            return self._prepare(pose, observations["depth"], observations["features"], None, T)
+        return self._prepare(pose, observations["depth"], None, observations["class_ids"], T)
+
+    def update_prepared(self, prep):
+        """The device half of update_batch (graph-capturable)."""
+        return self._launch(prep)
 
     def check(self):
         """Synchronises and raises if the batched kernels flagged an error during the last
