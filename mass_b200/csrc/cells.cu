@@ -1187,7 +1187,9 @@ void pick_vec(const float *features, const float *map, const float *P, int F, in
     vec = 1;
     if (F % 4 == 0 && al % 16 == 0) vec = 4;
     else if (F % 2 == 0 && al % 8 == 0) vec = 2;
-    it = F > 32 * vec ? 2 : 1;
+    // one iteration per lane and several channel blocks (grid.y) beat two iterations: three times the warps per SM
+    // for twice the (cheap) coefficient staging; two iterations only where a second block would be nearly empty
+    it = (F > 32 * vec && F <= 32 * vec + 8 * vec) ? 2 : 1;
 }
 
 template <int VEC, int IT, bool ONEHOT, int U>
