@@ -135,6 +135,17 @@ int mb_instance_pool(void *stream, const int32_t *boxes, int nboxes, const float
                      int F, int semantic_category, const float *feat_map, int FF, const float *centres_x,
                      const float *centres_y, const float *centres_z, float *out);
 
+/* ---- next to the path: the two readers of the whole map ----------------------------
+ * amax [S0][S1][F]    = max over z of map[y][x][z][f]   (agent.py:330-331, 391-392: data.amax(dim=2), the input of
+ *                       the semantic search policy); may be NULL
+ * blocked [S0][S1] u8 = any z in [z_lo, z_hi): sum_f |map[y][x][z][f]| > obstacle_threshold
+ *                       (mass/navigation_policy.py:207-216: torch.norm(data, p=1, dim=3) > thr, sliced, any(dim=2));
+ *                       may be NULL.  Exact for the reference's default threshold 0; for other thresholds the
+ *                       fp32 summation order over f may differ from ATen's.
+ * One pass over the map. */
+int mb_column_summary(void *stream, const float *map, int S0, int S1, int S2, int F, int z_lo, int z_hi,
+                      float obstacle_threshold, float *amax, uint8_t *blocked);
+
 /* ---- a12: predict_scene_differences (mass/utils/experimentation.py:261-287) ------------------------------
  * mb_pairwise_l2: out[i][j] = ||a[i] - b[j]||_2 from direct differences (torch.linalg.norm of the
  *   broadcast difference), a [n][d], b [m][d], out [n][m].

@@ -329,6 +329,15 @@ MB_API int mb_class_presence(void *stream, const float *map, int S0, int S1, int
                               contour_threshold, image, workspace, workspace_bytes);
 }
 
+MB_API int mb_column_summary(void *stream, const float *map, int S0, int S1, int S2, int F, int z_lo, int z_hi,
+                             float obstacle_threshold, float *amax, uint8_t *blocked)
+{
+    MB_REQUIRE(map && (amax || blocked), "mb_column_summary: null pointer");
+    MB_REQUIRE(S0 > 0 && S1 > 0 && S2 > 0 && F > 0, "mb_column_summary: bad map shape");
+    MB_REQUIRE(0 <= z_lo && z_lo <= z_hi && z_hi <= S2, "mb_column_summary: depth slice [%d, %d) outside [0, %d]", z_lo, z_hi, S2);
+    return mbk_column_summary((cudaStream_t)stream, map, S0, S1, S2, F, z_lo, z_hi, obstacle_threshold, amax, blocked);
+}
+
 MB_API int mb_instance_pool(void *stream, const int32_t *boxes, int nboxes, const float *sem_map, int S0, int S1, int S2,
                             int F, int semantic_category, const float *feat_map, int FF, const float *centres_x,
                             const float *centres_y, const float *centres_z, float *out)

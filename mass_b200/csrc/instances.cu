@@ -83,6 +83,82 @@ k_presence_from_sums(const float *__restrict__ sums, int S0, int S1, int S2, flo
 }
 
 // ---------------------------------------------------------------------------------------------
+// column summaries (the readers of the whole map that sit next to the path):
+//   amax[y][x][f]  = max over z of map[y][x][z][f]                       (/root/reference/agent.py:330-331, 391-392)
+//   blocked[y][x]  = any z in [z_lo, z_hi): sum_f |map[y][x][z][f]| > thr  (mass/navigation_policy.py:207-216)
+// One warp per (y, x) column: the column is one contiguous block of S2 * F floats, read once.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_column_summary(const float *__restrict__ map, size_t ncols, int S2, int F, int z_lo, int z_hi, float thr,
+                 float *__restrict__ amax, uint8_t *__restrict__ blocked)
+{
+    constexpr int UZ = 8;                            // z rows requested before the first is used
+    const int lane = threadIdx.x & 31;
+    const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t col = wid; col < ncols; col += nw) {
+        const float *p = map + col * (size_t)S2 * F;
+        float rowsum_hi = 0.f;                       // unused; keeps the structure symmetric
+        (void)rowsum_hi;
+        bool any = false;
+        const int nblk = (F + 32 * VEC - 1) / (32 * VEC);
+        for (int cb = 0; cb < nblk; ++cb) {          // channel blocks of 32 * VEC (one pass over z per block)
+            const int f = (cb * 32 + lane) * VEC;
+            const bool on = f < F;
+            float m[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) m[j] = -INFINITY;
+            for (int z0 = 0; z0 < S2; z0 += UZ) {
+                float v[UZ][VEC];
+#pragma unroll
+                for (int u = 0; u < UZ; ++u) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) v[u][j] = 0.f;
+                    if (on && z0 + u < S2) {
+                        const float *q = p + (size_t)(z0 + u) * F + f;
+                        if (VEC == 1) v[u][0] = __ldg(q);
+                        if (VEC == 2) { const float2 t = __ldg((const float2 *)q); v[u][0] = t.x; v[u][VEC > 1 ? 1 : 0] = t.y; }
+                        if (VEC == 4) {
+                            const float4 t = __ldg((const float4 *)q);
+                            v[u][0] = t.x; v[u][VEC > 1 ? 1 : 0] = t.y; v[u][VEC > 2 ? 2 : 0] = t.z; v[u][VEC > 2 ? 3 : 0] = t.w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UZ; ++u) {
+                    if (on && z0 + u < S2) {
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) m[j] = fmaxf(m[j], v[u][j]);
+                    }
+                    if (blocked != nullptr && nblk == 1 && z0 + u >= z_lo && z0 + u < z_hi) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) s += fabsf(v[u][j]);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+                        any |= s > thr;
+                    }
+                }
+            }
+            if (amax != nullptr && on) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) amax[col * F + f + j] = m[j];
+            }
+        }
+        if (blocked != nullptr && nblk > 1) {
+            // wide rows: a second sweep over the slice (L1/L2 hits), lanes stride over the channels of one z row
+            for (int z = z_lo; z < z_hi; ++z) {
+                float s = 0.f;
+                for (int f = lane; f < F; f += 32) s += fabsf(__ldg(p + (size_t)z * F + f));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+                any |= s > thr;
+            }
+        }
+        if (blocked != nullptr && lane == 0) blocked[col] = any ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // instance pooling: one CTA per bounding box (x, y, w, h) over the full depth of the map.
 //   out row = [confidence, coord_x, coord_y, coord_z, size, feature[FF]]
 constexpr int POOL_THREADS = 256;
@@ -369,6 +445,21 @@ int mbk_class_presence(cudaStream_t stream, const float *map, int S0, int S1, in
     MB_LAUNCHED();
     const int k = 2 * pad + 1;
     k_presence_from_sums<<<blocks, 256, 0, stream>>>(t0, S0, S1, S2, (float)(k * k * k), thr, image);
+    MB_LAUNCHED();
+    return MB_OK;
+}
+
+int mbk_column_summary(cudaStream_t stream, const float *map, int S0, int S1, int S2, int F, int z_lo, int z_hi, float thr,
+                       float *amax, uint8_t *blocked)
+{
+    const size_t ncols = (size_t)S0 * S1;
+    const uintptr_t al = (uintptr_t)map | (uintptr_t)amax;
+    if (F % 4 == 0 && al % 16 == 0)
+        k_column_summary<4><<<MB_NUM_SMS * 8, 256, 0, stream>>>(map, ncols, S2, F, z_lo, z_hi, thr, amax, blocked);
+    else if (F % 2 == 0 && al % 8 == 0)
+        k_column_summary<2><<<MB_NUM_SMS * 8, 256, 0, stream>>>(map, ncols, S2, F, z_lo, z_hi, thr, amax, blocked);
+    else
+        k_column_summary<1><<<MB_NUM_SMS * 8, 256, 0, stream>>>(map, ncols, S2, F, z_lo, z_hi, thr, amax, blocked);
     MB_LAUNCHED();
     return MB_OK;
 }

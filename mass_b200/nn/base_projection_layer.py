@@ -202,6 +202,25 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
             return self._fuse(pose, observations["depth"], observations["features"], None, T, fold=fold)
         return self._fuse(pose, observations["depth"], None, observations["class_ids"], T, fold=fold)
 
+    # -- whole-map readers next to the path ------------------------------------------------
+    def column_summary(self, depth_slice: slice = None, obstacle_threshold: float = 0.0,
+                       want_amax: bool = True, want_blocked: bool = True):
+        """One pass over the map: (amax [S0, S1, F] = data.amax(dim=2), blocked [S0, S1] bool =
+        (norm(data, p=1, dim=3) > obstacle_threshold)[:, :, depth_slice].any(dim=2)).
+        Reference: agent.py:330-331 (policy input), mass/navigation_policy.py:207-216 (obstacles)."""
+        data = self.data
+        device = _lib.require_cuda(data.device)
+        S0, S1, S2, F = data.shape
+        z_lo, z_hi, step = (depth_slice or slice(None)).indices(S2)
+        if step != 1:
+            raise ValueError("depth_slice must have step 1")
+        z_hi = max(z_hi, z_lo)
+        amax = torch.empty(S0, S1, F, dtype=torch.float32, device=device) if want_amax else None
+        blocked = torch.empty(S0, S1, dtype=torch.uint8, device=device) if want_blocked else None
+        _lib.check(_lib.lib().mb_column_summary(_lib.stream_ptr(device), _lib.ptr(data), S0, S1, S2, F, z_lo, z_hi,
+                                                float(obstacle_threshold), _lib.ptr(amax), _lib.ptr(blocked)))
+        return amax, (blocked.bool() if blocked is not None else None)
+
     # -- rendering + coordinate helpers (not on the hot path; plain torch) --------------------------
     def top_down(self, depth_slice: slice = slice(0, 32)):
         """Features of the top-most non-empty voxel per (y, x) column.

@@ -1,0 +1,39 @@
+"""Column summaries against the reference's own torch expressions evaluated on the CPU."""
+import numpy as np
+import pytest
+import torch
+from torch.nn import functional
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("F", [1, 5, 32, 54, 100])
+def test_column_summary_matches_reference_expressions(F):
+    from mass_b200.nn.base_projection_layer import BaseProjectionLayer
+    from mass_b200.utils import navigation
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(F)
+    layer = BaseProjectionLayer(camera_height=8, camera_width=8, map_height=40, map_width=36, map_depth=24,
+                                feature_size=F, grid_resolution=0.1).to(dev)
+    data = (rng.standard_normal((40, 36, 24, F)) * (rng.random((40, 36, 24, 1)) < 0.05)).astype(np.float32)
+    layer.data.copy_(torch.from_numpy(data))
+    cpu = torch.from_numpy(data)
+    amax, blocked = layer.column_summary()
+    assert torch.equal(amax.cpu(), cpu.amax(dim=2))                              # agent.py:330-331
+    assert torch.equal(blocked.cpu(), (torch.norm(cpu, p=1, dim=3) > 0.0).any(dim=2))
+    for sl, pad in ((slice(4, 20), 3), (slice(0, 24), 0), (slice(10, 11), 1)):
+        # mass/navigation_policy.py:207-221
+        nav = torch.norm(cpu, p=1, dim=3) > 0.0
+        nav = torch.logical_not(nav[:, :, sl].any(dim=2)).to(torch.float32)
+        ref = 1 - functional.max_pool2d(1 - nav.unsqueeze(0), 2 * pad + 1, stride=1, padding=pad).squeeze(0)
+        got = navigation.navigable_area(layer, padding=pad, depth_slice=sl)
+        assert torch.equal(got.cpu(), ref)
+    assert torch.equal(navigation.search_policy_input(layer).cpu(), cpu.amax(dim=2).unsqueeze(0).permute(0, 3, 1, 2))
+    # a positive threshold: equal wherever the L1 norm is not within rounding of the threshold
+    thr = 0.7
+    l1 = torch.norm(cpu.double(), p=1, dim=3)
+    _, blk = layer.column_summary(obstacle_threshold=thr)
+    sure = ((l1 - thr).abs() > 1e-4).all(dim=2)
+    assert torch.equal(blk.cpu()[sure], (l1 > thr).any(dim=2)[sure])
+    with pytest.raises(ValueError):
+        layer.column_summary(depth_slice=slice(0, 24, 2))
