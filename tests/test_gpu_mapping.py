@@ -469,3 +469,19 @@ def test_sharded_nccl_two_gpus():
                            os.path.join(root, "tests", "dist_sharded_check.py")],
                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-3000:]
+
+
+def test_batched_large_map_without_dense_cell_table(dev, oracle):
+    """A map so much larger than the batch that the dense cell -> index table is not worth its memset: the
+    source lookup falls back to a binary search over the unique cell list."""
+    H, W, T, F = 16, 24, 3, 2
+    kw = dict(camera_height=H, camera_width=W, vertical_fov=90.0, map_height=520, map_width=520, map_depth=80,
+              feature_size=F, grid_resolution=0.02, interpolation_weight=0.5, origin_z=0.5)
+    rng = np.random.default_rng(9)
+    frames = _random_frames(rng, T, H, W, H, W, F, depth_lo=0.5, depth_hi=2.5)
+    ref = _oracle_run(oracle, kw, frames, T)
+    layer = make_layer(kw, dev, exact=False)
+    layer.update_batch(frames)
+    got = layer.data.cpu().numpy()
+    assert np.array_equal((got != 0).any(-1), (ref != 0).any(-1))
+    assert_close_rel(got, ref)
