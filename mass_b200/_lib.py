@@ -130,3 +130,19 @@ class Workspace:
         if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
             self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
         return self.buf
+
+
+_shared = {}
+
+
+def shared_workspace(device):
+    """One grow-only scratch buffer per device, shared by every layer on it (an episode keeps five maps; each
+    batched update wants GBs of scratch).  Sharing is safe while the updates of a device are enqueued on one
+    stream, which is how the reference drives its layers; give a layer its own `Workspace()` (layer._ws) to update
+    it from another stream."""
+    key = torch.device(device)
+    if key.type == "cuda" and key.index is None:
+        key = torch.device("cuda", torch.cuda.current_device())
+    if key not in _shared:
+        _shared[key] = Workspace()
+    return _shared[key]

@@ -85,5 +85,6 @@ class SemanticProjectionLayer(BaseProjectionLayer):
         tensors in OpenCV contour order.  Reference: semantic_projection_layer.py:257-362."""
         found = instances.find_instances(self, semantic_category, confidence_threshold, contour_padding,
                                          contour_threshold, feature_map)
-        self.boxes = found.boxes
-        return found.confidences, found.coordinates, found.sizes, found.features
+        self.boxes = list(found.boxes)
+        features = None if found.features is None else list(found.features)
+        return list(found.confidences), list(found.coordinates), list(found.sizes), features

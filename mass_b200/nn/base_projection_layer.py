@@ -62,7 +62,8 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         self.register_buffer('bins_x', _edges(origin_x, map_width, grid_resolution))
         self.register_buffer('bins_y', _edges(origin_y, map_height, grid_resolution))
         self.register_buffer('bins_z', _edges(origin_z, map_depth, grid_resolution))
-        self._ws = _lib.Workspace()
+        self._ws = None                  # None: the device's shared scratch buffer (_lib.shared_workspace)
+        self._updates = 0                # bumped by every kernel that writes the map (see map_state)
         self.workspace_limit = None      # optional cap (bytes) on the device scratch buffer of update()
 
     # -- state ---------------------------------------------------------------------------------
@@ -109,12 +110,20 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
             features = features.contiguous()
         return dict(pose=pose, depth=depth, features=features, class_ids=class_ids, T=T, fh=fh, fw=fw, device=device)
 
+    def map_state(self):
+        """Changes whenever the map may have changed: by this package's kernels (which write through the raw
+        pointer and so do not bump torch's version counter), by torch in-place ops on `data`, or by rebinding
+        `data`.  Derived results (find()'s instance lists) are cached against it."""
+        return (self._updates, self.data._version, self.data.data_ptr())
+
     def _launch(self, prep, fold=None):
         """Device side of an update: enqueues the kernels on the current stream.  No host work besides the
         launches, no allocation once the scratch buffer exists: a call with the same `prep` can be captured
         in a CUDA graph and replayed."""
         device, T, fh, fw = prep["device"], prep["T"], prep["fh"], prep["fw"]
         H, W, F = self.camera_height, self.camera_width, self.feature_size
+        if fold is None:
+            self._updates += 1
         L = _lib.lib()
         nx, ny, nz = self.bins_x.numel(), self.bins_y.numel(), self.bins_z.numel()
         mode = _lib.MODE_EXACT if (self.exact and fold is None) else _lib.MODE_FAST
@@ -123,7 +132,8 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
             # a smaller scratch buffer makes the library split the call (fewer frames per chunk, more
             # rounds of the feature pass); below the one-frame minimum the call fails
             want = min(want, int(self.workspace_limit))
-        ws = self._ws.get(want, device)
+        ws = (self._ws or _lib.shared_workspace(device)).get(want, device)
+        self._last_ws = ws
         if fold is not None:
             partial_b, partial_a = fold
             _lib.check(L.mb_layer_fold(
@@ -131,14 +141,14 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
                 _lib.ptr(prep["class_ids"]), _lib.ptr(prep["pose"]), T, H, W, fh, fw, F, _lib.ptr(self.bins_x), nx,
                 _lib.ptr(self.bins_y), ny, _lib.ptr(self.bins_z), nz, _lib.ptr(partial_b), _lib.ptr(partial_a),
                 float(self.interpolation_weight), float(self.min_ray_depth), float(self.max_ray_depth),
-                _lib.ptr(ws), ws.numel()))
+                _lib.ptr(ws), want))
             return self
         _lib.check(L.mb_layer_update(
             _lib.stream_ptr(device), _lib.ptr(self.rays), _lib.ptr(prep["depth"]), _lib.ptr(prep["features"]),
             _lib.ptr(prep["class_ids"]), _lib.ptr(prep["pose"]), T, H, W, fh, fw, F, _lib.ptr(self.bins_x), nx,
             _lib.ptr(self.bins_y), ny, _lib.ptr(self.bins_z), nz, _lib.ptr(self.data),
             float(self.interpolation_weight), float(self.min_ray_depth), float(self.max_ray_depth),
-            mode, _lib.ptr(ws), ws.numel()))
+            mode, _lib.ptr(ws), want))
         return self
 
     def _fuse(self, pose, depth, features, class_ids, T, fold=None):
@@ -167,12 +177,12 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
     def check(self):
         """Synchronises and raises if the batched kernels flagged an error during the last
         non-exact update (an in-order row update that timed out: never expected)."""
-        if self.exact or self._ws.buf is None:
+        if self.exact or getattr(self, "_last_ws", None) is None:
             torch.cuda.synchronize(self.data.device)
             return self
         import ctypes
         bits = ctypes.c_uint32(0)
-        _lib.check(_lib.lib().mb_layer_update_status(_lib.stream_ptr(self.data.device), _lib.ptr(self._ws.buf),
+        _lib.check(_lib.lib().mb_layer_update_status(_lib.stream_ptr(self.data.device), _lib.ptr(self._last_ws),
                                                      ctypes.byref(bits)))
         if bits.value:
             raise RuntimeError("libmassb200: batched update reported error bits 0x%x" % bits.value)

@@ -57,8 +57,21 @@ def predict_scene_differences(semantic_projection_layer0, semantic_projection_la
         if len(conf0) == 0 or len(conf1) == 0:
             continue
         goal0, goal1 = torch.stack(goal0, dim=0), torch.stack(goal1, dim=0)
-        rows, cols, distance = match_instances(feature0, feature1, goal0, goal1, size0, size1, object_pickable)
-        far = (distance > distance_threshold).cpu().numpy()
+        # the assignment of a class is a pure function of the four maps: the agent's loop (agent.py:424-450) asks
+        # again after every rearranged object, so it is kept until a map changes
+        state = tuple(None if m is None else (id(m), m.map_state()) for m in
+                      (semantic_projection_layer0, semantic_projection_layer1, resnet_projection_layer0,
+                       resnet_projection_layer1))
+        memo = getattr(semantic_projection_layer0, "_match_cache", None)
+        if memo is None or memo[0] != state:
+            memo = (state, {})
+            semantic_projection_layer0._match_cache = memo
+        key = (candidate_object, float(confidence_threshold), int(contour_padding), float(contour_threshold),
+               float(distance_threshold))
+        if key not in memo[1]:
+            rows, cols, distance = match_instances(feature0, feature1, goal0, goal1, size0, size1, object_pickable)
+            memo[1][key] = (rows, cols, (distance > distance_threshold).cpu().numpy())
+        rows, cols, far = memo[1][key]
         for instance0, instance1 in zip(rows, cols):
             if (object_pickable and far[instance0, instance1]) or object_openable:
                 object_to_move = candidate_object

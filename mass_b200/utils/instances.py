@@ -73,19 +73,48 @@ def pool_boxes(layer, semantic_category, boxes, feature_map=None):
     return out
 
 
+def _presence_image(layer, semantic_category, contour_padding, contour_threshold):
+    """Host uint8 [S0, S1] image of one class.  Without smoothing (the agent's default, agent.py:846-847)
+    any_z(v > thr) == (max_z v > thr), so ONE sweep over the map (mb_column_summary) serves all classes; the
+    per-class images are kept on the host until the map changes."""
+    if contour_padding != 0:
+        return class_presence(layer, semantic_category, contour_padding, contour_threshold).cpu().numpy()
+    state = (layer.map_state(), float(contour_threshold))
+    cache = getattr(layer, "_presence_cache", None)
+    if cache is None or cache[0] != state:
+        amax, _ = layer.column_summary(want_blocked=False)
+        stack = (amax > contour_threshold).to(torch.uint8).permute(2, 0, 1).contiguous().cpu().numpy()
+        cache = (state, stack)
+        layer._presence_cache = cache
+    if not 0 <= int(semantic_category) < cache[1].shape[0]:
+        raise IndexError("semantic_category %d is outside [0, %d)" % (semantic_category, cache[1].shape[0]))
+    return cache[1][int(semantic_category)]
+
+
 def find_instances(layer, semantic_category, confidence_threshold, contour_padding, contour_threshold,
                    feature_map):
-    image = class_presence(layer, semantic_category, contour_padding, contour_threshold)
-    boxes = contour_boxes(image.cpu().numpy())
+    """find() is a pure function of the two maps and its arguments: results are cached until a map changes
+    (the agent's matching loop asks for the same classes again after every rearranged object)."""
+    key = (int(semantic_category), float(confidence_threshold), int(contour_padding), float(contour_threshold),
+           layer.map_state(), None if feature_map is None else (id(feature_map), feature_map.map_state()))
+    memo = getattr(layer, "_find_cache", None)
+    if memo is None or memo[0] != key[4]:
+        memo = (key[4], {})
+        layer._find_cache = memo
+    if key in memo[1]:
+        return memo[1][key]
+    image = _presence_image(layer, semantic_category, contour_padding, contour_threshold)
+    boxes = contour_boxes(image)
     rows = pool_boxes(layer, semantic_category, boxes, feature_map)
     keep = (rows[:, 0] > confidence_threshold).cpu().numpy() if len(boxes) else np.zeros(0, bool)
     kept = [i for i in range(len(boxes)) if keep[i]]
-    return Instances(
+    memo[1][key] = found = Instances(
         boxes=[boxes[i] for i in kept],
         confidences=[rows[i, 0] for i in kept],
         coordinates=[rows[i, 1:4] for i in kept],
         sizes=[rows[i, 4] for i in kept],
         features=[rows[i, 5:] for i in kept] if feature_map is not None else None)
+    return found
 
 
 def pairwise_l2(a, b):

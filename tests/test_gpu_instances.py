@@ -89,6 +89,33 @@ def test_find_confidence_threshold_and_errors(block_layers):
         s.find(7, 0.0, 0, 0.0, f.__class__(feature_size=16, **layer_kwargs(golden_kwargs(g))))   # CPU feature map
 
 
+def test_find_cache_follows_the_map(block_layers, dev):
+    """find() results are cached against the map state: kernel updates, torch in-place writes and feature-map
+    changes must all invalidate them."""
+    g, layers = block_layers
+    s, f = layers[1]
+    saved_s, saved_f = s.data.clone(), f.data.clone()
+    try:
+        conf, coord, size, feats = s.find(7, 0.0, 0, 0.0, f)
+        assert len(conf) > 0
+        again = s.find(7, 0.0, 0, 0.0, f)
+        assert torch.equal(torch.stack(again[0]), torch.stack(conf))
+        f.data.mul_(2.0)                                           # torch in-place op on the feature map
+        feats2 = s.find(7, 0.0, 0, 0.0, f)[3]
+        np.testing.assert_allclose(stack(feats2), 2.0 * stack(feats), rtol=1e-6)
+        s.data[..., 7].zero_()                                     # torch in-place op on the semantic map
+        assert len(s.find(7, 0.0, 0, 0.0, f)[0]) == 0
+        # a kernel update (raw-pointer write) also invalidates: put one observation into the map
+        obs = dict(position=np.array([0.3, -0.1, 0.9], np.float32), yaw=np.float32(0.3), elevation=np.float32(-0.4),
+                   depth=np.full((s.camera_height, s.camera_width, 1), 0.6, np.float32),
+                   semantic=np.full((s.camera_height, s.camera_width, 1), 7, np.int64))
+        s.update(obs)
+        assert len(s.find(7, 0.0, 0, 0.0, f)[0]) > 0
+    finally:
+        s.data.copy_(saved_s)
+        f.data.copy_(saved_f)
+
+
 def test_pairwise_l2_golden(dev):
     from mass_b200.utils import instances
     g = golden("pairwise.npz")

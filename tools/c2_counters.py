@@ -15,6 +15,6 @@ depth = torch.from_numpy(walk["depth"]).to(dev)
 probs = torch.from_numpy(walk["probs_low"]).to(dev).repeat_interleave(8, 1).repeat_interleave(8, 2).contiguous()
 layer.update_batch(dict(position=walk["position"], yaw=walk["yaw"], elevation=walk["elevation"], depth=depth, features=probs))
 torch.cuda.synchronize()
-c = layer._ws.buf[:64].view(torch.int32).cpu().tolist()
-names = ["heads", "nvalid", "cells", "segs", "runs", "error", "vox"]
+c = layer._last_ws[:64].view(torch.int32).cpu().tolist()
+names = ["heads", "items", "cells", "segs", "runs", "error", "vox"]
 print({n: c[i] for i, n in enumerate(names)}, "pixels", T * 224 * 224)
