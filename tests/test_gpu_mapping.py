@@ -419,6 +419,61 @@ def test_batched_c2_prefix_vs_oracle(dev, oracle):
     assert_close_rel(got.reshape(-1, 54)[idx], ref.data.reshape(-1, 54)[idx])
 
 
+def test_c2_full_size_properties(dev):
+    """BASELINE config 2 at FULL size (500 frames 224x224x54 into 384x384x96) through size-independent
+    properties: (1) the batched update is bit-reproducible run to run; (2) fusing the walkthrough as one batch or
+    as two consecutive batches (frames do not commute, batches compose) agrees within 1e-5 with identical
+    occupancy; (3) the occupied set equals the union of the 8-neighbour voxel sets derived from bin_rays' indices
+    frame by frame (the bit-exact index path); (4) one-hot class ids and the materialised one-hot features agree."""
+    import bench
+    from mass_b200.utils import projection, synthetic
+    T = 500
+    walk = bench.make_walkthrough(T)
+    kw = dict(bench.C2, **synthetic.MAP_ORIGIN)
+    depth = torch.from_numpy(walk["depth"]).to(dev)
+    probs = torch.from_numpy(walk["probs_low"]).to(dev).repeat_interleave(8, 1).repeat_interleave(8, 2).contiguous()
+    obs = dict(position=walk["position"], yaw=walk["yaw"], elevation=walk["elevation"], depth=depth, features=probs)
+    a = make_layer(kw, dev, exact=False).update_batch(obs)
+    b = make_layer(kw, dev, exact=False).update_batch(obs)
+    assert torch.equal(a.data, b.data)                                              # (1)
+    del b
+    c = make_layer(kw, dev, exact=False)
+    c.update_batch({k: v[:230] for k, v in obs.items()})
+    c.update_batch({k: v[230:] for k, v in obs.items()})
+    occ = (a.data != 0).any(-1)
+    assert torch.equal(occ, (c.data != 0).any(-1))                                  # (2)
+    assert bool(((a.data - c.data).abs() <= 1e-5 * a.data.abs()).all())
+    del c
+    # (3) occupancy from the index path alone, every 25th frame checked as a subset, all frames as the union
+    union = torch.zeros(384 * 384 * 96, dtype=torch.bool, device=dev)
+    S = torch.tensor([384, 384, 96], device=dev)
+    for t in range(T):
+        eye = projection.spherical_to_cartesian(torch.tensor(walk["yaw"][t]), torch.tensor(walk["elevation"][t]))
+        up = projection.spherical_to_cartesian(torch.tensor(walk["yaw"][t]), torch.tensor(walk["elevation"][t]) + np.pi / 2)
+        rays = projection.transform_rays(a.rays, eye, up)
+        ind0, ind1, ind2, r0, r1, r2 = projection.bin_rays(
+            a.bins_x, a.bins_y, a.bins_z, torch.as_tensor(walk["position"][t]).to(dev), rays, depth[t])
+        # map axes (y flipped, x, z) = (ind1, ind0, ind2); neighbours as update_feature_map picks them
+        idx = torch.stack([ind1, ind0, ind2], 1)
+        rat = torch.stack([r1, r0, r2], 1)
+        lower = torch.where(rat < 0.5, (idx - 1).clamp(min=0), idx)
+        upper = torch.where(rat < 0.5, idx, torch.minimum(idx + 1, S - 1))
+        for k in range(8):
+            sel = torch.tensor([(k >> 2) & 1, (k >> 1) & 1, k & 1], device=dev, dtype=torch.bool)
+            v = torch.where(sel, upper, lower)
+            union[(v[:, 0] * 384 + v[:, 1]) * 96 + v[:, 2]] = True
+    assert torch.equal(union.reshape(384, 384, 96), occ)                            # (3)
+    del union
+    # (4) class ids vs materialised one-hot, 40 frames
+    ids = probs[:40].argmax(-1)
+    onehot = torch.nn.functional.one_hot(ids, 54).float()
+    sub = {k: v[:40] for k, v in obs.items() if k != "features"}
+    d = make_layer(kw, dev, exact=False).update_batch(dict(sub, features=onehot))
+    e = make_layer(kw, dev, exact=False).update_batch(dict(sub, class_ids=ids))
+    assert torch.equal((d.data != 0), (e.data != 0))
+    assert bool(((d.data - e.data).abs() <= 1e-6 * d.data.abs()).all())
+
+
 # ---- frame-sharded scenes (SURVEY.md 8e) -----------------------------------------------------------
 def test_fold_and_ordered_apply_equal_sequential(dev, oracle):
     """One GPU standing in for three ranks: contiguous frame chunks folded into sparse partials from the
