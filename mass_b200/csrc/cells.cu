@@ -1157,8 +1157,9 @@ size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const Cel
     b.vrun = a.take<uint2>((vcap + 1) * 8);
     {
         // dense lookup table over the extended grid when it is not out of proportion to the batch
-        size_t budget = (size_t)32 * n;
-        if (budget < ((size_t)64 << 20)) budget = (size_t)64 << 20;
+        // (it is re-initialised by every call: 4 bytes per cell of the extended grid; a one-frame call on a large
+        // map is better off with the binary search over its few thousand cells)
+        const size_t budget = (size_t)32 * n;
         const bool dense = (size_t)g.invalid * sizeof(int) <= budget;
         b.ctab = dense ? a.take<int>((size_t)g.invalid) : nullptr;
         if (!dense) b.ctab = nullptr;
@@ -1284,12 +1285,12 @@ int mbk_affine_apply_rows(cudaStream_t stream, float *map, int F, const int64_t 
 // bytes per P run (8 rows of F floats)
 static size_t run_bytes(int F) { return (size_t)8 * F * sizeof(float); }
 
-// P budget asked for by default: room for min(worst case, one run per 8 pixels), at least 64 MB
+// P budget asked for by default: room for min(worst case, one run per 8 pixels), at least 128 MB
 static size_t default_P_bytes(uint32_t n, const CellGrid &g, int F)
 {
     const size_t worst = worst_runs(n, g) * run_bytes(F);
     size_t want = ((size_t)n / 8 + 1024) * run_bytes(F);
-    if (want < ((size_t)64 << 20)) want = (size_t)64 << 20;
+    if (want < ((size_t)128 << 20)) want = (size_t)128 << 20;
     return want < worst ? want : worst;
 }
 

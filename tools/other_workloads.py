@@ -57,3 +57,9 @@ prep = ex.prepare_batch(dict(position=walk["position"][:32], yaw=walk["yaw"][:32
                              depth=depth[:32], features=probs))
 ms = timeit(lambda: ex.update_prepared(prep))
 print("exact mode (bitwise), 32 frames 224x224x54: %.2f ms  (%.0f frames/s)" % (ms, 32 / ms * 1e3))
+# one frame per call (the reference's call pattern: NavigationPolicy.process_observations), batched arithmetic
+fast = BaseProjectionLayer(exact=False, **kw).to(dev)
+preps = [fast.prepare_batch(dict(position=walk["position"][t:t + 1], yaw=walk["yaw"][t:t + 1], elevation=walk["elevation"][t:t + 1],
+                                 depth=depth[t:t + 1], features=probs[t:t + 1])) for t in range(32)]
+ms = timeit(lambda: [fast.update_prepared(p) for p in preps])
+print("one frame per call, batched arithmetic, 32 calls 224x224x54: %.2f ms  (%.0f frames/s, %.0f us per call)" % (ms, 32 / ms * 1e3, ms / 32 * 1e3))
