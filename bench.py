@@ -44,8 +44,10 @@ C2_TOUCHED_PER_FRAME = 22243.0
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_cell_accumulate launch on this workload, from the
 # committed ncu --set full capture named below (per launch, like the achieved figure)
-ACCUMULATE_DRAM_BYTES_PER_LAUNCH = 7755.9e6 + 359.3e6
-ACCUMULATE_TRAFFIC_SOURCE = "profiles/r01t_kernels.txt"
+ACCUMULATE_DRAM_BYTES_PER_LAUNCH = 7754.1e6 + 354.3e6
+ACCUMULATE_TRAFFIC_SOURCE = "profiles/r01w_step_traffic.txt"
+# the same two metrics summed over all 40 launches of one step (same capture)
+STEP_DRAM_BYTES = 10228.3e6 + 1653.4e6
 
 
 def algorithmic_bytes_per_frame(h, w, fh, fw, F, touched):
@@ -341,7 +343,8 @@ def main():
     per_gpu_fps = T * args.steps / (ms_total * 1e-3)
     achieved = per_gpu_fps * bpf / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "whole step (all kernels of update_batch)",
+                "traffic": STEP_DRAM_BYTES, "traffic_source": ACCUMULATE_TRAFFIC_SOURCE, "peak_source": peak_src,
+                "kernel": "whole step (all kernels of update_batch)",
                 "algorithmic_bytes_per_frame": bpf, "stage_ms": stages}
     if "accumulate" in stages and stages["accumulate"] > 0:
         # the dominant kernel alone: it streams every feature row once (4*h*w*F per frame) and writes the run rows
