@@ -65,7 +65,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks/throttle reasons sampled every 50 ms while the timed region (and the load phase before it) runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -75,7 +75,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -267,6 +267,12 @@ def main():
     launches0 = L.mb_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
+        # ~0.5 s of untimed steps first, so that nvidia-smi (50 ms period) samples the clocks under this very load
+        # right up to and during the timed region, which itself lasts only a few milliseconds
+        t_load = time.perf_counter() + 0.5
+        while time.perf_counter() < t_load:
+            step_device()
+            torch.cuda.synchronize()
         barrier()
         ev0.record()
         for _ in range(args.steps):
