@@ -43,7 +43,7 @@ extern "C" {
 #define MB_MODE_EXACT 0 /* reference operation order, no FMA: map values bitwise equal to the CPU path;
                            frames are processed one at a time (sort by voxel + one warp per voxel segment)  */
 #define MB_MODE_FAST 1  /* per-voxel affine form new = a*old + b: <= 1e-5 relative, occupancy
-                           still bit-exact; all frames of the call go through the batched brick pipeline    */
+                           still bit-exact; all frames of the call go through the batched cell pipeline     */
 
 const char *mb_last_error(void);
 int mb_version(void);
@@ -80,7 +80,9 @@ int mb_update_feature_map(void *stream, const int64_t *ind0, const int64_t *ind1
 
 /* ---- a6..a9: BaseProjectionLayer.update (mass/nn/base_projection_layer.py:282-343) ---------
  * Fused unproject + voxelise + deterministic voxel reduce for T consecutive frames, applied in
- * frame order (frames do not commute).
+ * frame order (frames do not commute).  MB_MODE_FAST composes the T per-frame affine
+ * updates of every voxel and touches each map row once; nothing synchronises and
+ * nothing is allocated, so the call can be captured in a CUDA graph.
  *   rays      [H*W][3]  camera-frame ray table (the layer's `rays` buffer)
  *   depth     [T][H*W]
  *   features  [T][fh*fw][F], nearest up-sampled to H x W by integer factors H/fh, W/fw
