@@ -155,6 +155,11 @@ int mb_column_summary(void *stream, const float *map, int S0, int S1, int S2, in
  *   it over, or float64): same row order, scan order and tie rule.  Writes
  *   min(n, m) (row, col) pairs sorted by row; *status = 1 if the matrix is infeasible. */
 int mb_pairwise_l2(void *stream, const float *a, int n, const float *b, int m, int d, float *out);
+/* Not on the reference's path (it matches by L2 distance + assignment); an additional op:
+ * best[i] = argmax_j cos(a_i, b_j) (first maximum, torch.argmax's tie rule; -1 if m == 0), best_sim[i] = that
+ * cosine; a zero vector has similarity 0 to everything. */
+int mb_cosine_best_match(void *stream, const float *a, int n, const float *b, int m, int d, int64_t *best,
+                         float *best_sim);
 size_t mb_lsap_workspace_bytes(int n, int m);
 int mb_lsap(void *stream, const float *cost32, const double *cost64, int n, int m, int64_t *rows, int64_t *cols,
             int32_t *status, void *workspace, size_t workspace_bytes);

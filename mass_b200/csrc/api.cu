@@ -361,6 +361,15 @@ MB_API int mb_pairwise_l2(void *stream, const float *a, int n, const float *b, i
     return mbk_pairwise_l2((cudaStream_t)stream, a, n, b, m, d, out);
 }
 
+MB_API int mb_cosine_best_match(void *stream, const float *a, int n, const float *b, int m, int d, int64_t *best,
+                                float *best_sim)
+{
+    MB_REQUIRE(n >= 0 && m >= 0 && d >= 0, "mb_cosine_best_match: negative size");
+    if (n == 0) return MB_OK;
+    MB_REQUIRE(a && best && best_sim && (m == 0 || b), "mb_cosine_best_match: null pointer");
+    return mbk_cosine_best_match((cudaStream_t)stream, a, n, b, m, d, best, best_sim);
+}
+
 MB_API size_t mb_lsap_workspace_bytes(int n, int m)
 {
     if (n <= 0 || m <= 0) return 256;

@@ -297,6 +297,49 @@ k_pairwise_l2(const float *__restrict__ a, int n, const float *__restrict__ b, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// cosine similarity + best match (NOT on the reference's path, which matches by L2 + assignment: SURVEY.md F3;
+// offered because the task statement names it).  One warp per query row i: sim(i, j) = a_i.b_j / (|a_i| |b_j|)
+// with float64 accumulation, best j = the first maximum (torch.argmax's tie rule).  For the instance counts of
+// this path (<= a few hundred rows of 256) this is a latency-sized job; a tcgen05 GEMM would only pay off
+// beyond a few thousand instances.
+__global__ void __launch_bounds__(256)
+k_cosine_best_match(const float *__restrict__ a, int n, const float *__restrict__ b, int m, int d,
+                    int64_t *__restrict__ best, float *__restrict__ best_sim)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (i >= n) return;
+    const float *pa = a + (size_t)i * d;
+    double na = 0;
+    for (int k = lane; k < d; k += 32) na += (double)pa[k] * pa[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) na += __shfl_xor_sync(FULL, na, o);
+    double top = -INFINITY;
+    int arg = 0;
+    for (int j = 0; j < m; ++j) {
+        const float *pb = b + (size_t)j * d;
+        double dot = 0, nb = 0;
+        for (int k = lane; k < d; k += 32) {
+            const double x = pb[k];
+            dot += (double)pa[k] * x;
+            nb += x * x;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dot += __shfl_xor_sync(FULL, dot, o);
+            nb += __shfl_xor_sync(FULL, nb, o);
+        }
+        const double den = sqrt(na) * sqrt(nb);
+        const double sim = den > 0 ? dot / den : 0.0;
+        if (sim > top) { top = sim; arg = j; }
+    }
+    if (lane == 0) {
+        best[i] = m > 0 ? arg : -1;
+        best_sim[i] = m > 0 ? (float)top : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // rectangular linear sum assignment, nr <= nc (the host wrapper transposes otherwise).
 // Follows the scan order and tie rule of SURVEY.md Appendix B: columns are scanned in the order of
 // the `remaining` list (initialised in reverse, swap-removed); among equal shortest path costs the
@@ -480,6 +523,15 @@ int mbk_pairwise_l2(cudaStream_t stream, const float *a, int n, const float *b, 
     if (n <= 0 || m <= 0) return MB_OK;
     const size_t threads = (size_t)n * m * 32;
     k_pairwise_l2<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, n, b, m, d, out);
+    MB_LAUNCHED();
+    return MB_OK;
+}
+
+int mbk_cosine_best_match(cudaStream_t stream, const float *a, int n, const float *b, int m, int d, int64_t *best,
+                          float *best_sim)
+{
+    if (n <= 0) return MB_OK;
+    k_cosine_best_match<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, stream>>>(a, n, b, m, d, best, best_sim);
     MB_LAUNCHED();
     return MB_OK;
 }

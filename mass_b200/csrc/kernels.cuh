@@ -74,6 +74,8 @@ int mbk_column_summary(cudaStream_t stream, const float *map, int S0, int S1, in
 int mbk_instance_pool(cudaStream_t stream, const int *boxes, int nboxes, const float *sem, int S0, int S1, int S2, int F,
                       int c, const float *feat, int FF, const float *mx, const float *my, const float *mz, float *out);
 int mbk_pairwise_l2(cudaStream_t stream, const float *a, int n, const float *b, int m, int d, float *out);
+int mbk_cosine_best_match(cudaStream_t stream, const float *a, int n, const float *b, int m, int d, int64_t *best,
+                          float *best_sim);
 size_t mbk_lsap_workspace_bytes(int n, int m);
 int mbk_lsap(cudaStream_t stream, const float *cost32, const double *cost64, int n, int m, int64_t *rows, int64_t *cols,
              int *status, void *workspace, size_t workspace_bytes);

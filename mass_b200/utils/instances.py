@@ -131,6 +131,22 @@ def pairwise_l2(a, b):
     return out
 
 
+def cosine_best_match(a, b):
+    """(best [n] int64, similarity [n] float32): for every row of a the row of b with the largest cosine
+    similarity, first maximum on ties.  An additional op: the reference matches by L2 distance + assignment
+    (predict_scene_differences), which is what `pairwise_l2` + `linear_sum_assignment` reproduce."""
+    device = _lib.require_cuda(a.device)
+    a = a.to(torch.float32).contiguous()
+    b = b.to(device=device, dtype=torch.float32).contiguous()
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1]:
+        raise ValueError("cosine_best_match needs [n, d] and [m, d], got %s and %s" % (tuple(a.shape), tuple(b.shape)))
+    best = torch.empty(a.shape[0], dtype=torch.int64, device=device)
+    sim = torch.empty(a.shape[0], dtype=torch.float32, device=device)
+    _lib.check(_lib.lib().mb_cosine_best_match(_lib.stream_ptr(device), _lib.ptr(a), a.shape[0], _lib.ptr(b),
+                                               b.shape[0], a.shape[1], _lib.ptr(best), _lib.ptr(sim)))
+    return best, sim
+
+
 def linear_sum_assignment(cost):
     """scipy.optimize.linear_sum_assignment on a CUDA cost matrix (float32 or float64): returns
     (rows, cols) int64 numpy arrays, rows ascending, same tie behaviour as scipy (one CTA runs the

@@ -189,3 +189,25 @@ def test_c3_scale_matching_vs_oracle(dev, oracle):
     assert np.array_equal(rows, r) and np.array_equal(cols, c)
     r2, c2 = oracle.lsap(d_ref)
     assert np.array_equal(rows, r2) and np.array_equal(cols, c2)
+
+
+def test_cosine_best_match(dev):
+    """Additional op (not the reference's matcher): against float64 numpy, ties to the first maximum."""
+    from mass_b200.utils import instances
+    rng = np.random.default_rng(31)
+    a = rng.standard_normal((200, 256)).astype(np.float32)
+    b = np.concatenate([a[rng.permutation(200)[:150]] * rng.uniform(0.5, 2.0, (150, 1)).astype(np.float32)
+                        + 0.05 * rng.standard_normal((150, 256)).astype(np.float32),
+                        rng.standard_normal((40, 256)).astype(np.float32)])
+    b[7] = b[3]                                       # an exact duplicate: the lower index must win
+    b[100] = 0.0                                      # a zero vector never wins against a positive similarity
+    best, sim = instances.cosine_best_match(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev))
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    na, nb = np.linalg.norm(a64, axis=1), np.linalg.norm(b64, axis=1)
+    den = na[:, None] * nb[None, :]
+    ref = np.where(den > 0, (a64 @ b64.T) / np.where(den > 0, den, 1.0), 0.0)
+    assert best.cpu().numpy().tolist() == ref.argmax(axis=1).tolist()
+    np.testing.assert_allclose(sim.cpu().numpy(), ref.max(axis=1), rtol=1e-6)
+    assert 7 not in best.cpu().numpy().tolist() or 3 not in ref.argmax(axis=1).tolist()
+    e_best, e_sim = instances.cosine_best_match(torch.zeros(3, 8, device=dev), torch.zeros(0, 8, device=dev))
+    assert e_best.tolist() == [-1, -1, -1]
