@@ -82,3 +82,21 @@ def test_product_never_imports_oracle():
             if f.endswith(".py") and re.search(r"^\s*(from|import)\s+oracle\b", open(os.path.join(base, f)).read(), re.M):
                 bad.append(f)
     assert not bad, bad
+
+
+def test_new_entry_points_fail_loudly_without_cuda():
+    """column summaries, find() and the sharded fold need the CUDA library: on a CPU layer they raise."""
+    from mass_b200.nn.applications.semantic_projection_layer import SemanticProjectionLayer
+    from mass_b200.nn import sharded
+    from mass_b200.utils import navigation
+    L = SemanticProjectionLayer(camera_height=4, camera_width=4, map_height=8, map_width=8, map_depth=4, feature_size=3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        L.column_summary()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        navigation.navigable_area(L)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        L.find(1, 0.0, 0, 0.0, None)
+    obs = dict(position=np.zeros((1, 3), np.float32), yaw=np.zeros(1, np.float32), elevation=np.zeros(1, np.float32),
+               depth=np.ones((1, 4, 4, 1), np.float32), semantic=np.ones((1, 4, 4, 1), np.int64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sharded.fold_frames(L, obs)
