@@ -218,7 +218,7 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
             torch.cuda.synchronize(self.data.device)
             updates = self._updates
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 self._launch(bufs)
             self._updates = updates                                          # capturing launches nothing
             self._frame_graphs[key] = (graph, bufs, self._last_ws)           # the scratch buffer must outlive the graph
