@@ -148,6 +148,11 @@ int mb_instance_pool(void *stream, const int32_t *boxes, int nboxes, const float
 int mb_column_summary(void *stream, const float *map, int S0, int S1, int S2, int F, int z_lo, int z_hi,
                       float obstacle_threshold, float *amax, uint8_t *blocked);
 
+/* Top-down rendering (mass/nn/base_projection_layer.py:345-379, BaseProjectionLayer.top_down):
+ * out [S0][S1][F] = the feature row of the top-most voxel of [z_lo, z_hi) with any non-zero channel, zeros if the
+ * column is empty in the slice.  A pure selection: bit-exact. */
+int mb_top_down(void *stream, const float *map, int S0, int S1, int S2, int F, int z_lo, int z_hi, float *out);
+
 /* ---- a12: predict_scene_differences (mass/utils/experimentation.py:261-287) ------------------------------
  * mb_pairwise_l2: out[i][j] = ||a[i] - b[j]||_2 from direct differences (torch.linalg.norm of the
  *   broadcast difference), a [n][d], b [m][d], out [n][m].

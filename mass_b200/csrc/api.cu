@@ -338,6 +338,14 @@ MB_API int mb_column_summary(void *stream, const float *map, int S0, int S1, int
     return mbk_column_summary((cudaStream_t)stream, map, S0, S1, S2, F, z_lo, z_hi, obstacle_threshold, amax, blocked);
 }
 
+MB_API int mb_top_down(void *stream, const float *map, int S0, int S1, int S2, int F, int z_lo, int z_hi, float *out)
+{
+    MB_REQUIRE(map && out, "mb_top_down: null pointer");
+    MB_REQUIRE(S0 > 0 && S1 > 0 && S2 > 0 && F > 0, "mb_top_down: bad map shape");
+    MB_REQUIRE(0 <= z_lo && z_lo <= z_hi && z_hi <= S2, "mb_top_down: depth slice [%d, %d) outside [0, %d]", z_lo, z_hi, S2);
+    return mbk_top_down((cudaStream_t)stream, map, S0, S1, S2, F, z_lo, z_hi, out);
+}
+
 MB_API int mb_instance_pool(void *stream, const int32_t *boxes, int nboxes, const float *sem_map, int S0, int S1, int S2,
                             int F, int semantic_category, const float *feat_map, int FF, const float *centres_x,
                             const float *centres_y, const float *centres_z, float *out)

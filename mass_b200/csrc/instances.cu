@@ -158,6 +158,28 @@ k_column_summary(const float *__restrict__ map, size_t ncols, int S2, int F, int
     }
 }
 
+// top-down rendering (mass/nn/base_projection_layer.py:345-379): per (y, x) column the feature row
+// of the top-most voxel of [z_lo, z_hi) that has any non-zero channel, zeros if there is none (the reference's
+// cumsum * mask arg-max picks the last filled voxel, and row z_lo -- all zero -- when none is filled).
+// One warp per column, walking down from the top of the slice and stopping at the first filled voxel.
+__global__ void __launch_bounds__(256)
+k_top_down(const float *__restrict__ map, size_t ncols, int S2, int F, int z_lo, int z_hi, float *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t col = wid; col < ncols; col += nw) {
+        const float *p = map + col * (size_t)S2 * F;
+        int top = -1;
+        for (int z = z_hi - 1; z >= z_lo && top < 0; --z) {
+            bool nz = false;
+            for (int f = lane; f < F; f += 32) nz |= __ldg(p + (size_t)z * F + f) != 0.f;
+            if (__any_sync(FULL, nz)) top = z;
+        }
+        float *o = out + col * F;
+        for (int f = lane; f < F; f += 32) o[f] = top >= 0 ? __ldg(p + (size_t)top * F + f) : 0.f;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // instance pooling: one CTA per bounding box (x, y, w, h) over the full depth of the map.
 //   out row = [confidence, coord_x, coord_y, coord_z, size, feature[FF]]
@@ -503,6 +525,13 @@ int mbk_column_summary(cudaStream_t stream, const float *map, int S0, int S1, in
         k_column_summary<2><<<MB_NUM_SMS * 8, 256, 0, stream>>>(map, ncols, S2, F, z_lo, z_hi, thr, amax, blocked);
     else
         k_column_summary<1><<<MB_NUM_SMS * 8, 256, 0, stream>>>(map, ncols, S2, F, z_lo, z_hi, thr, amax, blocked);
+    MB_LAUNCHED();
+    return MB_OK;
+}
+
+int mbk_top_down(cudaStream_t stream, const float *map, int S0, int S1, int S2, int F, int z_lo, int z_hi, float *out)
+{
+    k_top_down<<<MB_NUM_SMS * 8, 256, 0, stream>>>(map, (size_t)S0 * S1, S2, F, z_lo, z_hi, out);
     MB_LAUNCHED();
     return MB_OK;
 }

@@ -275,10 +275,19 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
     def top_down(self, depth_slice: slice = slice(0, 32)):
         """Features of the top-most non-empty voxel per (y, x) column.
         Reference: base_projection_layer.py:345-379."""
-        vol = self.data if depth_slice is None else self.data[:, :, depth_slice]
-        filled = (vol != 0).any(dim=-1, keepdim=True).to(vol.dtype)
-        top = (filled.cumsum(dim=-2) * filled).argmax(dim=-2, keepdim=True)
-        return torch.gather(vol, -2, top.expand(*vol.shape[:-2], 1, vol.shape[-1])).squeeze(-2)
+        data = self.data
+        S0, S1, S2, F = data.shape
+        z_lo, z_hi, step = (depth_slice or slice(None)).indices(S2)
+        if not data.is_cuda or step != 1 or z_hi <= z_lo:
+            # not the device path (a CPU copy of the layer, a strided or empty slice): the reference's expression
+            vol = data if depth_slice is None else data[:, :, depth_slice]
+            filled = (vol != 0).any(dim=-1, keepdim=True).to(vol.dtype)
+            top = (filled.cumsum(dim=-2) * filled).argmax(dim=-2, keepdim=True)
+            return torch.gather(vol, -2, top.expand(*vol.shape[:-2], 1, vol.shape[-1])).squeeze(-2)
+        out = torch.empty(S0, S1, F, dtype=torch.float32, device=data.device)
+        _lib.check(_lib.lib().mb_top_down(_lib.stream_ptr(data.device), _lib.ptr(data), S0, S1, S2, F, z_lo, z_hi,
+                                          _lib.ptr(out)))
+        return out
 
     def _centre_span(self):
         lo = torch.stack([(b[0] + b[1]) / 2 for b in (self.bins_x, self.bins_y, self.bins_z)])

@@ -37,3 +37,24 @@ def test_column_summary_matches_reference_expressions(F):
     assert torch.equal(blk.cpu()[sure], (l1 > thr).any(dim=2)[sure])
     with pytest.raises(ValueError):
         layer.column_summary(depth_slice=slice(0, 24, 2))
+
+
+@pytest.mark.parametrize("F", [1, 3, 54, 70])
+def test_top_down_matches_reference_expression(F):
+    """BaseProjectionLayer.top_down against the reference's cumsum/arg-max/gather expression on the CPU (bit-exact)."""
+    from mass_b200.nn.base_projection_layer import BaseProjectionLayer
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(100 + F)
+    layer = BaseProjectionLayer(camera_height=8, camera_width=8, map_height=33, map_width=29, map_depth=40,
+                                feature_size=F, grid_resolution=0.1).to(dev)
+    data = (rng.standard_normal((33, 29, 40, F)) * (rng.random((33, 29, 40, 1)) < 0.04)).astype(np.float32)
+    data[0, 0] = 0.0                                  # an empty column
+    data[1, 1, 39] = 1.0                              # filled at the very top
+    layer.data.copy_(torch.from_numpy(data))
+    cpu = torch.from_numpy(data)
+    for sl in (slice(0, 32), slice(4, 32), None, slice(39, 40), slice(0, 1)):
+        vol = cpu if sl is None else cpu[:, :, sl]
+        mask = torch.ne(vol, 0).any(dim=-1, keepdim=True).to(vol.dtype)
+        idx = (mask.cumsum(dim=-2) * mask).argmax(dim=-2, keepdim=True)
+        ref = torch.gather(vol, -2, idx.expand(*vol.shape[:-2], 1, vol.shape[-1])).squeeze(-2)
+        assert torch.equal(layer.top_down(depth_slice=sl).cpu(), ref), sl
