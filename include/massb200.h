@@ -148,6 +148,14 @@ int mb_instance_pool(void *stream, const int32_t *boxes, int nboxes, const float
 int mb_column_summary(void *stream, const float *map, int S0, int S1, int S2, int F, int z_lo, int z_hi,
                       float obstacle_threshold, float *amax, uint8_t *blocked);
 
+/* Perception hand-off (mass/thor/segmentation_config.py:314-334, the Mask R-CNN branch of
+ * SemanticRearrangeSensor.get_segmentation): masks [n][npix] (non-zero = inside), classes [n], scores [n] ->
+ * ids [npix] = arg-max over classes of the number of instances of that class (score >= detection_threshold) whose
+ * mask covers the pixel; first maximum, so 0 where nothing was detected.  The result feeds mb_layer_update's
+ * class_ids directly: no [H][W][54] buffer, no device-host round trip. */
+int mb_masks_to_ids(void *stream, const uint8_t *masks, const int64_t *classes, const float *scores, int n,
+                    int64_t npix, int num_classes, float detection_threshold, int64_t *ids);
+
 /* Top-down rendering (mass/nn/base_projection_layer.py:345-379, BaseProjectionLayer.top_down):
  * out [S0][S1][F] = the feature row of the top-most voxel of [z_lo, z_hi) with any non-zero channel, zeros if the
  * column is empty in the slice.  A pure selection: bit-exact. */

@@ -63,6 +63,7 @@ _SIGNATURES = {
     "mb_class_presence": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _sz]),
     "mb_instance_pool": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "mb_column_summary": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
+    "mb_masks_to_ids": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _f32, _vp]),
     "mb_top_down": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "mb_pairwise_l2": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp]),
     "mb_cosine_best_match": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp]),

@@ -338,6 +338,15 @@ MB_API int mb_column_summary(void *stream, const float *map, int S0, int S1, int
     return mbk_column_summary((cudaStream_t)stream, map, S0, S1, S2, F, z_lo, z_hi, obstacle_threshold, amax, blocked);
 }
 
+MB_API int mb_masks_to_ids(void *stream, const uint8_t *masks, const int64_t *classes, const float *scores, int n,
+                           int64_t npix, int num_classes, float detection_threshold, int64_t *ids)
+{
+    MB_REQUIRE(n >= 0 && npix >= 0, "mb_masks_to_ids: negative size");
+    if (npix == 0) return MB_OK;
+    MB_REQUIRE(ids && (n == 0 || (masks && classes && scores)), "mb_masks_to_ids: null pointer");
+    return mbk_masks_to_ids((cudaStream_t)stream, masks, classes, scores, n, (size_t)npix, num_classes, detection_threshold, ids);
+}
+
 MB_API int mb_top_down(void *stream, const float *map, int S0, int S1, int S2, int F, int z_lo, int z_hi, float *out)
 {
     MB_REQUIRE(map && out, "mb_top_down: null pointer");

@@ -158,6 +158,29 @@ k_column_summary(const float *__restrict__ map, size_t ncols, int S2, int F, int
     }
 }
 
+// perception hand-off (mass/thor/segmentation_config.py:314-334): the detector's instances
+// (mask, class, score) -> per-class mask counts -> arg-max class id per pixel (first maximum: class 0 where
+// nothing was detected), without the [H, W, 54] float buffer and without leaving the device.
+constexpr int IDS_MAX_CLASSES = 128;
+__global__ void __launch_bounds__(128)
+k_masks_to_ids(const uint8_t *__restrict__ masks, const int64_t *__restrict__ classes, const float *__restrict__ scores,
+               int n, size_t npix, int num_classes, float threshold, int64_t *__restrict__ ids)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    unsigned short cnt[IDS_MAX_CLASSES];
+    for (int c = 0; c < num_classes; ++c) cnt[c] = 0;
+    for (int i = 0; i < n; ++i) {
+        if (__ldg(scores + i) < threshold) continue;              // "skip if the model is not confident enough"
+        const int64_t c = __ldg(classes + i);
+        if (c >= 0 && c < num_classes && __ldg(masks + (size_t)i * npix + p)) ++cnt[c];
+    }
+    int best = 0;
+    for (int c = 1; c < num_classes; ++c)
+        if (cnt[c] > cnt[best]) best = c;
+    ids[p] = best;
+}
+
 // top-down rendering (mass/nn/base_projection_layer.py:345-379): per (y, x) column the feature row
 // of the top-most voxel of [z_lo, z_hi) that has any non-zero channel, zeros if there is none (the reference's
 // cumsum * mask arg-max picks the last filled voxel, and row z_lo -- all zero -- when none is filled).
@@ -525,6 +548,17 @@ int mbk_column_summary(cudaStream_t stream, const float *map, int S0, int S1, in
         k_column_summary<2><<<MB_NUM_SMS * 8, 256, 0, stream>>>(map, ncols, S2, F, z_lo, z_hi, thr, amax, blocked);
     else
         k_column_summary<1><<<MB_NUM_SMS * 8, 256, 0, stream>>>(map, ncols, S2, F, z_lo, z_hi, thr, amax, blocked);
+    MB_LAUNCHED();
+    return MB_OK;
+}
+
+int mbk_masks_to_ids(cudaStream_t stream, const uint8_t *masks, const int64_t *classes, const float *scores, int n,
+                     size_t npix, int num_classes, float threshold, int64_t *ids)
+{
+    MB_REQUIRE(num_classes >= 1 && num_classes <= IDS_MAX_CLASSES, "mb_masks_to_ids: between 1 and %d classes", IDS_MAX_CLASSES);
+    MB_REQUIRE(n < 65536, "mb_masks_to_ids: too many instances");
+    k_masks_to_ids<<<(unsigned)((npix + 127) / 128), 128, 0, stream>>>(masks, classes, scores, n, npix, num_classes,
+                                                                      threshold, ids);
     MB_LAUNCHED();
     return MB_OK;
 }

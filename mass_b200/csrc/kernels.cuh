@@ -71,6 +71,8 @@ int mbk_class_presence(cudaStream_t stream, const float *map, int S0, int S1, in
                        uint8_t *image, void *workspace, size_t workspace_bytes);
 int mbk_column_summary(cudaStream_t stream, const float *map, int S0, int S1, int S2, int F, int z_lo, int z_hi, float thr,
                        float *amax, uint8_t *blocked);
+int mbk_masks_to_ids(cudaStream_t stream, const uint8_t *masks, const int64_t *classes, const float *scores, int n,
+                     size_t npix, int num_classes, float threshold, int64_t *ids);
 int mbk_top_down(cudaStream_t stream, const float *map, int S0, int S1, int S2, int F, int z_lo, int z_hi, float *out);
 int mbk_instance_pool(cudaStream_t stream, const int *boxes, int nboxes, const float *sem, int S0, int S1, int S2, int F,
                       int c, const float *feat, int FF, const float *mx, const float *my, const float *mz, float *out);

@@ -58,3 +58,29 @@ def test_top_down_matches_reference_expression(F):
         idx = (mask.cumsum(dim=-2) * mask).argmax(dim=-2, keepdim=True)
         ref = torch.gather(vol, -2, idx.expand(*vol.shape[:-2], 1, vol.shape[-1])).squeeze(-2)
         assert torch.equal(layer.top_down(depth_slice=sl).cpu(), ref), sl
+
+
+def test_detections_to_ids_matches_reference_expression():
+    """mass/thor/segmentation_config.py:314-334 evaluated with torch on the CPU vs the device kernel (bit-exact)."""
+    from mass_b200.utils import perception
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(77)
+    H = W = 224
+    for n in (0, 1, 37):
+        masks = torch.from_numpy(rng.random((n, H, W)) < 0.15)
+        yy, xx = np.mgrid[:H, :W]
+        for i in range(n):                                          # blobs, so that overlaps and ties occur
+            cy, cx, r = rng.integers(0, H), rng.integers(0, W), rng.integers(5, 60)
+            masks[i] &= torch.from_numpy((yy - cy) ** 2 + (xx - cx) ** 2 < r * r)
+        classes = torch.from_numpy(rng.integers(0, 54, n))
+        scores = torch.from_numpy(rng.random(n).astype(np.float32))
+        thr = 0.3
+        seg = torch.zeros(H, W, 54)
+        for i in range(n):
+            if scores[i] < thr:
+                continue
+            seg[:, :, classes[i]] += masks[i].to(torch.float32)
+        ref = seg.argmax(dim=2, keepdim=True)
+        got = perception.detections_to_ids(masks.to(dev), classes.to(dev), scores.to(dev), thr)
+        assert got.dtype == torch.int64 and tuple(got.shape) == (H, W, 1)
+        assert torch.equal(got.cpu(), ref), n
