@@ -128,7 +128,8 @@ int mb_affine_apply_rows(void *stream, float *map, int F, const int64_t *voxel_i
  *   out[box] = {confidence, coord_x, coord_y, coord_z, size, feature[FF]} with
  *   weights = mask / (sum(mask) + 1e-9), confidence = sum(mask*weights), coord = sum(centre*weights),
  *   size = sum(mask), feature = sum(feat_map[box]*weights) (feat_map may be NULL, then FF is ignored and
- *   rows are 5 floats).  centres_* are the per-axis cell-centre tables (y already flipped). */
+ *   rows are 5 floats).  centres_* are the per-axis cell-centre tables (y already flipped).
+ *   semantic_category == -1: boxes are 5 ints (x, y, w, h, class): the boxes of all classes in one launch. */
 size_t mb_class_presence_workspace_bytes(int S0, int S1, int S2, int contour_padding);
 int mb_class_presence(void *stream, const float *map, int S0, int S1, int S2, int F, int semantic_category,
                       int contour_padding, float contour_threshold, uint8_t *image, void *workspace,

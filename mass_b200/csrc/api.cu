@@ -362,7 +362,7 @@ MB_API int mb_instance_pool(void *stream, const int32_t *boxes, int nboxes, cons
     MB_REQUIRE(nboxes >= 0, "mb_instance_pool: negative box count");
     if (nboxes == 0) return MB_OK;
     MB_REQUIRE(boxes && sem_map && centres_x && centres_y && centres_z && out, "mb_instance_pool: null pointer");
-    MB_REQUIRE(S0 > 0 && S1 > 0 && S2 > 0 && F > 0 && semantic_category >= 0 && semantic_category < F,
+    MB_REQUIRE(S0 > 0 && S1 > 0 && S2 > 0 && F > 0 && semantic_category >= -1 && semantic_category < F,
                "mb_instance_pool: bad map shape or category");
     MB_REQUIRE(feat_map == nullptr || FF > 0, "mb_instance_pool: feature map without a feature size");
     return mbk_instance_pool((cudaStream_t)stream, boxes, nboxes, sem_map, S0, S1, S2, F, semantic_category, feat_map,

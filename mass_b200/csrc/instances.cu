@@ -235,8 +235,11 @@ k_instance_pool(const int *__restrict__ boxes, const float *__restrict__ sem, in
     extern __shared__ float s_facc[];          // [POOL_THREADS / 32][FF] per-warp feature sums
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bx = boxes[4 * blockIdx.x], by = boxes[4 * blockIdx.x + 1], bw = boxes[4 * blockIdx.x + 2],
-              bh = boxes[4 * blockIdx.x + 3];
+    // c >= 0: boxes are (x, y, w, h), all of class c; c < 0: boxes are (x, y, w, h, class)
+    const int bstride = c >= 0 ? 4 : 5;
+    const int bx = boxes[bstride * blockIdx.x], by = boxes[bstride * blockIdx.x + 1], bw = boxes[bstride * blockIdx.x + 2],
+              bh = boxes[bstride * blockIdx.x + 3];
+    if (c < 0) c = boxes[bstride * blockIdx.x + 4];
     const uint32_t nvox = (uint32_t)bw * bh * S2;
     float *orow = out + (size_t)blockIdx.x * (5 + FF);
 

@@ -91,29 +91,85 @@ def _presence_image(layer, semantic_category, contour_padding, contour_threshold
     return cache[1][int(semantic_category)]
 
 
-def find_instances(layer, semantic_category, confidence_threshold, contour_padding, contour_threshold,
-                   feature_map):
-    """find() is a pure function of the two maps and its arguments: results are cached until a map changes
-    (the agent's matching loop asks for the same classes again after every rearranged object)."""
-    key = (int(semantic_category), float(confidence_threshold), int(contour_padding), float(contour_threshold),
-           layer.map_state(), None if feature_map is None else (id(feature_map), feature_map.map_state()))
-    memo = getattr(layer, "_find_cache", None)
-    if memo is None or memo[0] != key[4]:
-        memo = (key[4], {})
-        layer._find_cache = memo
-    if key in memo[1]:
-        return memo[1][key]
-    image = _presence_image(layer, semantic_category, contour_padding, contour_threshold)
-    boxes = contour_boxes(image)
-    rows = pool_boxes(layer, semantic_category, boxes, feature_map)
-    keep = (rows[:, 0] > confidence_threshold).cpu().numpy() if len(boxes) else np.zeros(0, bool)
+def _pool_rows(layer, boxes5, feature_map):
+    """[n, 5 + FF] rows for boxes (x, y, w, h, class) of any mix of classes, one launch."""
+    data = layer.data
+    device = _lib.require_cuda(data.device)
+    S0, S1, S2, F = data.shape
+    feat, FF = None, 0
+    if feature_map is not None:
+        feat = feature_map.data
+        if not feat.is_cuda:
+            raise RuntimeError("the instance feature map must live on the GPU (it is %s); the reference keeps "
+                               "it on the host only because 13.5 GiB did not fit its GPU" % feat.device)
+        if feat.device != device or tuple(feat.shape[:3]) != (S0, S1, S2) or feat.dtype != torch.float32:
+            raise ValueError("feature map must be float32 [%d, %d, %d, FF] on %s" % (S0, S1, S2, device))
+        FF = int(feat.shape[3])
+    n = len(boxes5)
+    out = torch.empty(n, 5 + FF, dtype=torch.float32, device=device)
+    if n == 0:
+        return out
+    mx, my, mz = layer.cell_centres()
+    boxes_d = torch.tensor(boxes5, dtype=torch.int32).reshape(n, 5).to(device)
+    _lib.check(_lib.lib().mb_instance_pool(
+        _lib.stream_ptr(device), _lib.ptr(boxes_d), n, _lib.ptr(data), S0, S1, S2, F, -1,
+        _lib.ptr(feat), FF, _lib.ptr(mx.contiguous()), _lib.ptr(my.contiguous()), _lib.ptr(mz.contiguous()),
+        _lib.ptr(out)))
+    return out
+
+
+def _instances_from_rows(boxes, rows, keep, with_features):
     kept = [i for i in range(len(boxes)) if keep[i]]
-    memo[1][key] = found = Instances(
+    return Instances(
         boxes=[boxes[i] for i in kept],
         confidences=[rows[i, 0] for i in kept],
         coordinates=[rows[i, 1:4] for i in kept],
         sizes=[rows[i, 4] for i in kept],
-        features=[rows[i, 5:] for i in kept] if feature_map is not None else None)
+        features=[rows[i, 5:] for i in kept] if with_features else None)
+
+
+def find_instances(layer, semantic_category, confidence_threshold, contour_padding, contour_threshold,
+                   feature_map):
+    """find() is a pure function of the two maps and its arguments: results are cached until a map changes
+    (the agent's matching loop asks for the same classes again after every rearranged object).  Without
+    smoothing (the agent's default) the first query after a map change extracts the instances of ALL classes:
+    one map sweep for the presence images, OpenCV contours per class on the host, one pooling launch and one
+    device-to-host copy for every box of every class."""
+    c = int(semantic_category)
+    params = (float(confidence_threshold), int(contour_padding), float(contour_threshold))
+    maps = (layer.map_state(), None if feature_map is None else (id(feature_map), feature_map.map_state()))
+    memo = getattr(layer, "_find_cache", None)
+    if memo is None or memo[0] != maps[0]:
+        memo = (maps[0], {})
+        layer._find_cache = memo
+    key = (c,) + params + maps
+    if key in memo[1]:
+        return memo[1][key]
+    if contour_padding == 0:
+        num_classes = layer.data.shape[3]
+        if not 0 <= c < num_classes:
+            raise IndexError("semantic_category %d is outside [0, %d)" % (c, num_classes))
+        # classes whose boxes cover a large part of the map (the background class spans the whole room) are
+        # left out of the shared launch and served on demand: one CTA walks a box
+        per_class, boxes5 = {}, []
+        for k in range(num_classes):
+            bk = contour_boxes(_presence_image(layer, k, 0, contour_threshold))
+            if k == c or sum(b[2] * b[3] for b in bk) <= 4096:
+                per_class[k] = bk
+                boxes5.extend(b + (k,) for b in bk)
+        rows = _pool_rows(layer, boxes5, feature_map)
+        keep = (rows[:, 0] > confidence_threshold).cpu().numpy() if boxes5 else np.zeros(0, bool)
+        start = 0
+        for k, bk in per_class.items():
+            sl = slice(start, start + len(bk))
+            memo[1][(k,) + params + maps] = _instances_from_rows(bk, rows[sl], keep[sl], feature_map is not None)
+            start += len(bk)
+        return memo[1][key]
+    image = _presence_image(layer, c, contour_padding, contour_threshold)
+    boxes = contour_boxes(image)
+    rows = pool_boxes(layer, c, boxes, feature_map)
+    keep = (rows[:, 0] > confidence_threshold).cpu().numpy() if len(boxes) else np.zeros(0, bool)
+    memo[1][key] = found = _instances_from_rows(boxes, rows, keep, feature_map is not None)
     return found
 
 
