@@ -20,6 +20,8 @@ class OccupancyProjectionLayer(BaseProjectionLayer):
                                        self.camera_height, self.camera_width, 1)))
 
     def update_batch(self, observations, fold=None):
+        if isinstance(observations, (list, tuple)) and len(observations) == 0:
+            return self
         if isinstance(observations, (list, tuple)):
             observations = {k: torch.stack([torch.as_tensor(o[k]) for o in observations])
                             for k in ("position", "yaw", "elevation", "depth")}

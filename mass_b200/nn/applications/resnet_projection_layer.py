@@ -52,6 +52,8 @@ class ResNetProjectionLayer(BaseProjectionLayer):
                                    depth=self.subsample_depth(depth, features.shape[0]), features=features))
 
     def update_batch(self, observations, fold=None):
+        if isinstance(observations, (list, tuple)) and len(observations) == 0:
+            return self
         if isinstance(observations, (list, tuple)):
             observations = {k: torch.stack([torch.as_tensor(o[k]) for o in observations])
                             for k in observations[0].keys()}

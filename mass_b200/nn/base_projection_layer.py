@@ -242,9 +242,13 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         """Fuse T observations in order (frames do not commute).  `observations` is a
         list of observation dicts or one dict of stacked arrays with a leading T axis."""
         if isinstance(observations, (list, tuple)):
+            if len(observations) == 0:
+                return self                                        # no frames: the map is unchanged
             keys = observations[0].keys()
             observations = {k: torch.stack([torch.as_tensor(o[k]) for o in observations]) for k in keys}
         T = int(torch.as_tensor(observations["yaw"]).reshape(-1).shape[0])
+        if T == 0:
+            return self
         pose = camera_pose(torch.as_tensor(observations["position"]).reshape(T, 3),
                            torch.as_tensor(observations["yaw"]).reshape(T),
                            torch.as_tensor(observations["elevation"]).reshape(T))

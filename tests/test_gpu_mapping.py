@@ -419,6 +419,44 @@ def test_batched_c2_prefix_vs_oracle(dev, oracle):
     assert_close_rel(got.reshape(-1, 54)[idx], ref.data.reshape(-1, 54)[idx])
 
 
+def test_batched_empty_and_all_invalid_batches(dev):
+    """No frames, and frames without a single valid pixel, leave the map untouched."""
+    kw = dict(camera_height=16, camera_width=16, vertical_fov=90.0, map_height=20, map_width=20, map_depth=8,
+              feature_size=3, grid_resolution=0.1, interpolation_weight=0.5)
+    layer = make_layer(kw, dev, exact=False)
+    layer.data.fill_(0.25)
+    before = layer.data.clone()
+    layer.update_batch([])
+    layer.update_batch(dict(position=np.zeros((0, 3), np.float32), yaw=np.zeros(0, np.float32), elevation=np.zeros(0, np.float32),
+                            depth=np.zeros((0, 16, 16, 1), np.float32), features=np.zeros((0, 16, 16, 3), np.float32)))
+    rng = np.random.default_rng(0)
+    frames = _random_frames(rng, 3, 16, 16, 16, 16, 3)
+    frames["depth"][:] = 50.0                          # beyond max_ray_depth: every pixel invalid
+    layer.update_batch(frames).check()
+    frames["depth"][:] = np.nan
+    layer.update_batch(frames).check()
+    assert torch.equal(layer.data, before)
+
+
+def test_batched_720p_frames_vs_oracle(dev, oracle):
+    """BASELINE config 4's frame size (720 x 1280: 90 x 40 tiles, the last tile row is partial)."""
+    H, W, T, F = 720, 1280, 2, 4
+    kw = dict(camera_height=H, camera_width=W, vertical_fov=90.0, map_height=120, map_width=120, map_depth=40,
+              feature_size=F, grid_resolution=0.08, interpolation_weight=0.5, origin_z=1.0)
+    rng = np.random.default_rng(12)
+    frames = _random_frames(rng, T, H, W, H // 8, W // 8, F, depth_lo=0.5, depth_hi=4.0)
+    # smooth depth (a slanted plane + ripples) so that neighbouring pixels share cells, as in a real frame
+    yy, xx = np.mgrid[:H, :W].astype(np.float32)
+    for t in range(T):
+        frames["depth"][t, :, :, 0] = 1.5 + 0.001 * xx + 0.0015 * yy + 0.05 * np.sin(xx / 37.0 + t)
+    ref = _oracle_run(oracle, kw, frames, T)
+    layer = make_layer(kw, dev, exact=False)
+    layer.update_batch(frames).check()
+    got = layer.data.cpu().numpy()
+    assert np.array_equal((got != 0).any(-1), (ref != 0).any(-1))
+    assert_close_rel(got, ref)
+
+
 def test_c2_full_size_properties(dev):
     """BASELINE config 2 at FULL size (500 frames 224x224x54 into 384x384x96) through size-independent
     properties: (1) the batched update is bit-reproducible run to run; (2) fusing the walkthrough as one batch or
