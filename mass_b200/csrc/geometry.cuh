@@ -116,10 +116,16 @@ __device__ __forceinline__ bool bucket_valid(const float *__restrict__ bins, int
     } else if (x < lo) {
         if (k > 0) { --k; hi = lo; lo = __ldg(bins + k); }
     }
-    while (x >= hi && k < n - 2) { ++k; lo = hi; hi = __ldg(bins + k + 1); }
-    while (x < lo && k > 0) { --k; hi = lo; lo = __ldg(bins + k); }
+    bool ok = x >= lo && x < hi;
+    if (!ok && x >= __ldg(bins) && x < __ldg(bins + n - 1)) {
+        // inside the table but more than one bucket from the guess: only tables that are far from uniform
+        // get here; walk to the bucket
+        while (x >= hi && k < n - 2) { ++k; lo = hi; hi = __ldg(bins + k + 1); }
+        while (x < lo && k > 0) { --k; hi = lo; lo = __ldg(bins + k); }
+        ok = x >= lo && x < hi;
+    }
     i = k;
-    return x >= lo && x < hi;
+    return ok;
 }
 
 // bin_point with precomputed spacing: spacing = {b0_x, scale_x, b0_y, scale_y, b0_z, scale_z}.  Indices and
