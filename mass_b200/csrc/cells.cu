@@ -150,6 +150,38 @@ __host__ __device__ inline TileGeom make_tiles(int H, int W)
     return t;
 }
 
+constexpr uint32_t IDX_AGG = 1u << 30, IDX_PREFIX = 2u << 30, IDX_MASK = (1u << 30) - 1u;
+
+// Decoupled look-back over one counter per tile: publishes `total` for `tile` and returns the sum of the totals of
+// all tiles before it.  Tiles take their index from a ticket, so a tile only ever waits for tiles that started
+// before it.  state: one zeroed word per tile (value | flag in the top two bits).  Called by ONE full warp with
+// the same arguments in every lane; the warp inspects 32 predecessors per step.
+__device__ __forceinline__ uint32_t lookback_prefix(uint32_t *state, uint32_t tile, uint32_t total, int lane)
+{
+    uint32_t *mine = state + tile;
+    if (lane == 0) *(volatile uint32_t *)mine = total | (tile == 0 ? IDX_PREFIX : IDX_AGG);
+    uint32_t prefix = 0;
+    if (tile > 0) {
+        int t = (int)tile - 1;                      // nearest predecessor not yet summed
+        for (;;) {
+            const int idx = t - lane;
+            const uint32_t st = idx >= 0 ? *(const volatile uint32_t *)(state + idx) : IDX_PREFIX;
+            const uint32_t flag = st >> 30;
+            const uint32_t pm = __ballot_sync(FULL, flag == 2u), zm = __ballot_sync(FULL, flag == 0u);
+            const int firstp = pm ? __ffs(pm) - 1 : 32, firstz = zm ? __ffs(zm) - 1 : 32;
+            const int take = firstp < firstz ? firstp + 1 : firstz;      // lanes [0, take) are summed now
+            uint32_t v = lane < take ? (st & IDX_MASK) : 0u;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+            prefix += v;
+            if (firstp < firstz) break;
+            t -= take;
+        }
+        if (lane == 0) *(volatile uint32_t *)mine = (prefix + total) | IDX_PREFIX;
+    }
+    return prefix;
+}
+
 // K1a: grid = (pixel blocks, frames): pixel -> {cell key (or >= 0xffffffe0: invalid), 3 in-voxel ratios}, in
 // image order.  Pure per-pixel math at full occupancy; the grouping kernel below re-reads it.
 __global__ void __launch_bounds__(256)
@@ -315,7 +347,6 @@ k_tile_compact(const uint32_t *__restrict__ tkey, const uint32_t *__restrict__ t
 //   (cell, frame); run head: cell head or start of an accumulate task (a multiple of TASK_ITEMS items).
 constexpr int IDX_WORDS = 8;                      // words per warp
 constexpr int IDX_TILE = 256 * IDX_WORDS;         // positions per tile
-constexpr uint32_t IDX_AGG = 1u << 30, IDX_PREFIX = 2u << 30, IDX_MASK = (1u << 30) - 1u;
 
 struct IndexOut {
     uint32_t *smask, *soff, *roff;                // per word of 32 positions: segment-head mask, ranks before the word
@@ -452,27 +483,61 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
     }
 }
 
-// K4: ordered list of touched voxels from the bitmap
-__global__ void __launch_bounds__(256)
-k_vox_count(const uint32_t *__restrict__ bitmap, uint32_t nwords, uint32_t *__restrict__ vcnt)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nwords) vcnt[i] = __popc(bitmap[i]);
-}
+// K4: ordered list of touched voxels from the bitmap, one sweep: a tile is 2048 bitmap words (8 per thread); the
+// position of a tile's first voxel comes from a decoupled look-back over the tiles before it.
+constexpr int VOX_WORDS = 8;
+constexpr int VOX_TILE = 256 * VOX_WORDS;
 
 __global__ void __launch_bounds__(256)
-k_vox_emit(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ voff, uint32_t nwords,
+k_vox_list(const uint32_t *__restrict__ bitmap, uint32_t nwords, uint32_t *state, uint32_t *ticket,
            uint32_t *__restrict__ vlist, uint32_t *__restrict__ counters)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nwords) return;
-    uint32_t m = bitmap[i];
-    uint32_t o = voff[i];
-    if (i == nwords - 1) counters[MB_CNT_VOX] = o + __popc(m);
-    while (m) {
-        const int b = __ffs(m) - 1;
-        vlist[o++] = (i << 5) + (uint32_t)b;
-        m &= m - 1;
+    __shared__ uint32_t s_tile, s_wsum[8], s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * VOX_TILE + tid * VOX_WORDS;
+    uint32_t m[VOX_WORDS];
+    if (base + VOX_WORDS <= nwords) {
+        const uint4 a = __ldg((const uint4 *)(bitmap + base)), b = __ldg((const uint4 *)(bitmap + base) + 1);
+        m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < VOX_WORDS; ++k) m[k] = base + k < nwords ? bitmap[base + k] : 0u;
+    }
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < VOX_WORDS; ++k) cnt += __popc(m[k]);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) total += s_wsum[w];
+        const uint32_t prefix = lookback_prefix(state, tile, total, lane);
+        if (lane == 0) {
+            s_base = prefix;
+            if (tile == gridDim.x - 1) counters[MB_CNT_VOX] = prefix + total;
+        }
+    }
+    __syncthreads();
+    uint32_t o = s_base + inc - cnt;
+    for (int w = 0; w < warp; ++w) o += s_wsum[w];
+#pragma unroll
+    for (int k = 0; k < VOX_WORDS; ++k) {
+        uint32_t mm = m[k];
+        while (mm) {
+            const int bit = __ffs(mm) - 1;
+            vlist[o++] = ((base + k) << 5) + (uint32_t)bit;
+            mm &= mm - 1;
+        }
     }
 }
 
@@ -1134,11 +1199,13 @@ struct CellBuffers {
     uint4 *rec, *pix;
     uint32_t *keys_a, *keys_b, *pids_a, *pids_b;
     uint32_t *tcount, *toff;
-    uint32_t *smask, *soff, *roff, *idx_state;
+    uint32_t *smask, *soff, *roff;
+    uint32_t *idx_state, *vox_state;      // look-back words of K2 and K4; the bitmap follows: zeroed by one memset
+    size_t state_bytes;
     uint32_t *ucell, *cstart, *cseg, *crun, *seg_start, *seg_frame;
     float2 *segws;
     float *gcoef;
-    uint32_t *bitmap, *vcnt, *voff, *vlist;
+    uint32_t *bitmap, *vlist;
     float *vA;
     uint2 *vseg, *vrun;
     int *ctab;                  // dense cell key -> unique cell index (or null: binary search)
@@ -1165,13 +1232,20 @@ size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const Cel
     b.pids_a = a.take<uint32_t>(n); b.pids_b = a.take<uint32_t>(n);
     b.tcount = a.take<uint32_t>(ntiles + 1); b.toff = a.take<uint32_t>(ntiles + 1);
     b.smask = a.take<uint32_t>(words); b.soff = a.take<uint32_t>(words); b.roff = a.take<uint32_t>(words);
-    b.idx_state = a.take<uint32_t>(((size_t)n + IDX_TILE - 1) / IDX_TILE * 3 + 8);
+    {
+        // (sizes are multiples of 4 words: the bitmap behind them is read in 16-byte pieces)
+        const size_t iwords = ((((size_t)n + IDX_TILE - 1) / IDX_TILE * 3 + 8) + 3) & ~(size_t)3;
+        const size_t vxwords = (((vwords + VOX_TILE - 1) / VOX_TILE + 8) + 3) & ~(size_t)3;
+        b.idx_state = a.take<uint32_t>(iwords + vxwords + vwords + VOX_WORDS);
+        b.vox_state = b.idx_state + iwords;
+        b.bitmap = b.vox_state + vxwords;             // touched-voxel bitmap
+        b.state_bytes = (iwords + vxwords + vwords + VOX_WORDS) * sizeof(uint32_t);
+    }
     b.ucell = a.take<uint32_t>(ncap + 1); b.cstart = a.take<uint32_t>(ncap + 1);
     b.cseg = a.take<uint32_t>(ncap + 1); b.crun = a.take<uint32_t>(ncap + 1);
     b.seg_start = a.take<uint32_t>((size_t)n + 1); b.seg_frame = a.take<uint32_t>((size_t)n + 1);
     b.segws = a.take<float2>((size_t)n * 8);
     b.gcoef = a.take<float>((size_t)n * 8);
-    b.bitmap = a.take<uint32_t>(vwords); b.vcnt = a.take<uint32_t>(vwords); b.voff = a.take<uint32_t>(vwords);
     b.vlist = a.take<uint32_t>(vcap + 1);
     b.vA = a.take<float>(vcap + 1);
     b.vseg = a.take<uint2>((vcap + 1) * 8);
@@ -1185,7 +1259,7 @@ size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const Cel
         b.ctab = dense ? a.take<int>((size_t)g.invalid) : nullptr;
         if (!dense) b.ctab = nullptr;
     }
-    const size_t scan_n = ntiles + 1 > vwords ? ntiles + 1 : vwords;
+    const size_t scan_n = ntiles + 1;
     b.scan_bytes = mb_scan_workspace_bytes((uint32_t)scan_n);
     b.scan_ws = a.take<char>(b.scan_bytes);
     b.sort_bytes = mb_sort_workspace_bytes(n);
@@ -1422,11 +1496,10 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
 
     // K2: index sweep over the sorted items
     if ((rc = stage_mark(stream, 2))) return rc;
-    MB_CHECK_CUDA(cudaMemsetAsync(b.bitmap, 0, (size_t)vwords * sizeof(uint32_t), stream));
+    MB_CHECK_CUDA(cudaMemsetAsync(b.idx_state, 0, b.state_bytes, stream));
     if (b.ctab) MB_CHECK_CUDA(cudaMemsetAsync(b.ctab, 0xff, (size_t)g.invalid * sizeof(int), stream));
     {
         const uint32_t itiles = (n + IDX_TILE - 1) / IDX_TILE;
-        MB_CHECK_CUDA(cudaMemsetAsync(b.idx_state, 0, ((size_t)itiles * 3 + 4) * sizeof(uint32_t), stream));
         IndexOut O;
         O.smask = b.smask; O.soff = b.soff; O.roff = b.roff;
         O.ucell = b.ucell; O.cstart = b.cstart; O.cseg = b.cseg; O.crun = b.crun;
@@ -1436,10 +1509,8 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
         MB_LAUNCHED();
     }
     // K4
-    k_vox_count<<<(vwords + 255) / 256, 256, 0, stream>>>(b.bitmap, vwords, b.vcnt);
-    MB_LAUNCHED();
-    if ((rc = mb_exclusive_scan_u32(stream, b.vcnt, b.voff, vwords, b.scan_ws, b.scan_bytes))) return rc;
-    k_vox_emit<<<(vwords + 255) / 256, 256, 0, stream>>>(b.bitmap, b.voff, vwords, b.vlist, b.counters);
+    k_vox_list<<<(vwords + VOX_TILE - 1) / VOX_TILE, 256, 0, stream>>>(b.bitmap, vwords, b.vox_state + 4, b.vox_state, b.vlist,
+                                                                       b.counters);
     MB_LAUNCHED();
     // K5, K6
     if ((rc = stage_mark(stream, 3))) return rc;
