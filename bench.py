@@ -42,12 +42,12 @@ C2_FRAMES = 500
 C2_TOUCHED_PER_FRAME = 22243.0
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_cell_accumulate launch on this workload, from the
-# committed ncu --set full capture named below (per launch, like the achieved figure)
-ACCUMULATE_DRAM_BYTES_PER_LAUNCH = 7754.1e6 + 354.3e6
-ACCUMULATE_TRAFFIC_SOURCE = "profiles/r01w_step_traffic.txt"
-# the same two metrics summed over all 40 launches of one step (same capture)
-STEP_DRAM_BYTES = 10228.3e6 + 1653.4e6
+# dram__bytes_read.sum + dram__bytes_write.sum of the k_cell_accumulate launches of one step on this workload (one
+# working launch + the empty overflow rounds), from the committed ncu launch list named below
+ACCUMULATE_DRAM_BYTES_PER_LAUNCH = 7755.3e6 + 354.2e6
+ACCUMULATE_TRAFFIC_SOURCE = "profiles/r01zz_step_traffic.txt"
+# the same two metrics summed over all 36 launches of one step (same capture)
+STEP_DRAM_BYTES = 10222.6e6 + 1651.0e6
 
 
 def algorithmic_bytes_per_frame(h, w, fh, fw, F, touched):
