@@ -26,6 +26,19 @@ def timeit(fn, reps=3):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
+def stages(fn):
+    """Stage timers of one call (voxelise, sort, index, scalar pass, accumulate, apply), ms."""
+    import ctypes
+    from mass_b200 import _lib
+    L = _lib.lib()
+    L.mb_profile_stages(1)
+    fn()
+    buf = (ctypes.c_float * 8)()
+    n = L.mb_profile_read(buf, 8)
+    L.mb_profile_stages(0)
+    return "stages ms: " + " ".join("%.2f" % buf[i] for i in range(n))
+
+
 kw = dict(bench.C2, **synthetic.MAP_ORIGIN)
 # semantic ids
 ids = torch.from_numpy(walk["probs_low"]).to(dev).argmax(-1).repeat_interleave(8, 1).repeat_interleave(8, 2).contiguous()
@@ -33,6 +46,7 @@ sem = SemanticProjectionLayer(exact=False, **kw).to(dev)
 prep = sem.prepare_batch(dict(base, depth=depth, class_ids=ids))
 ms = timeit(lambda: sem.update_prepared(prep))
 print("semantic map from class ids, %d frames 224x224: %.2f ms  (%.0f frames/s)" % (T, ms, T / ms * 1e3))
+print("   ", stages(lambda: sem.update_prepared(prep)))
 del sem
 # 256-d feature map at 56x56
 kw256 = dict(kw, camera_height=56, camera_width=56, feature_size=256)
@@ -49,6 +63,7 @@ occ = BaseProjectionLayer(exact=False, **kw1).to(dev)
 prep = occ.prepare_batch(dict(base, depth=depth, features=torch.ones(T, 224, 224, 1, device=dev)))
 ms = timeit(lambda: occ.update_prepared(prep))
 print("occupancy map (F = 1), %d frames 224x224: %.2f ms  (%.0f frames/s)" % (T, ms, T / ms * 1e3))
+print("   ", stages(lambda: occ.update_prepared(prep)))
 del occ
 # exact per-frame mode, dense probabilities
 probs = torch.from_numpy(walk["probs_low"][:32]).to(dev).repeat_interleave(8, 1).repeat_interleave(8, 2).contiguous()
