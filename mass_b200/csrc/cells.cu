@@ -757,13 +757,14 @@ struct AccArgs {
     const uint32_t *smask, *soff, *roff;
     const float *gcoef;         // [8 slots][cap] coefficient per (slot, segment)
     size_t cap;
-    const uint32_t *counters;
+    uint32_t *counters;            // read; the two work-queue heads are written
     MbFeatIndex fi;             // np = pixels per frame
     uint32_t fhw;               // feature rows per frame
     const float *features;      // [T][fhw][F] or null
     const int64_t *class_ids;   // [T][np] or null (one-hot features)
     int F;
     float *P;                   // [run][8][F]
+    uint32_t round;             // launch index inside the chunk (which work-queue head to use)
     uint32_t run_base, run_cap; // runs of this round: [run_base, run_base + run_cap)
 };
 
@@ -840,15 +841,27 @@ k_cell_accumulate(const AccArgs A)
     __shared__ uint8_t s_p2i[NW][TASK_ITEMS * ITEM_MAX];          // item of every pixel of the task
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nitems = A.counters[MB_CNT_NVALID], nruns = A.counters[MB_CNT_RUNS];
+    // Work queue: a unit is (task, channel block); warps take the next unit from a counter when they finish one, so
+    // the tasks' very different pixel counts (64 items of 1..16 pixels) do not leave SMs idle at the end.  The
+    // launches of a chunk use the two queue heads in turn; each launch clears the one the next launch will use.
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.counters[MB_CNT_TASKQ + ((A.round + 1) & 1)] = 0;
     if (A.run_base >= nruns) return;
+    uint32_t *queue = A.counters + MB_CNT_TASKQ + (A.round & 1);
     const uint32_t run_end = A.run_base + A.run_cap;
     const int F = A.F;
-    const int ch0 = (int)blockIdx.y * (32 * VEC * IT) + lane * VEC;     // first channel of this lane
     const uint32_t ntasks = (nitems + TASK_ITEMS - 1) / TASK_ITEMS;
+    const uint32_t ny = (uint32_t)(F + 32 * VEC * IT - 1) / (uint32_t)(32 * VEC * IT), nunits = ntasks * ny;
     const uint32_t np = A.fi.np;
     const uint32_t lemask = lane == 31 ? 0xffffffffu : ((2u << lane) - 1u);
+    auto next_unit = [&]() {
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(queue, 1u);
+        return __shfl_sync(FULL, u, 0);
+    };
 
-    for (uint32_t task = blockIdx.x * NW + warp; task < ntasks; task += gridDim.x * NW) {
+    for (uint32_t unit = next_unit(); unit < nunits; unit = next_unit()) {
+        const uint32_t task = unit / ny;
+        const int ch0 = (int)(unit - task * ny) * (32 * VEC * IT) + lane * VEC;     // first channel of this lane
         const uint32_t base = task * TASK_ITEMS, end = min(base + (uint32_t)TASK_ITEMS, nitems);
         uint32_t e = A.roff[base >> 5];                                  // rank of the task's first run
         {
@@ -1295,9 +1308,7 @@ int launch_accumulate(cudaStream_t stream, const AccArgs &A)
     int per_sm = 1;
     MB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ACC_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
-    const int cblocks = (A.F + 32 * VEC * IT - 1) / (32 * VEC * IT);
-    dim3 grid(MB_NUM_SMS * per_sm, cblocks);
-    kern<<<grid, ACC_THREADS, 0, stream>>>(A);
+    kern<<<MB_NUM_SMS * per_sm, ACC_THREADS, 0, stream>>>(A);      // persistent: the kernel walks (task, channel block) units
     MB_LAUNCHED();
     return MB_OK;
 }
@@ -1541,6 +1552,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     Y.g = g; Y.F = F; Y.map = map; Y.affine_a = affine_a; Y.run_cap = run_cap;
     for (int r = 0; r < rounds; ++r) {
         A.run_base = Y.run_base = (uint32_t)r * run_cap;
+        A.round = (uint32_t)r;
         if (r == 0 && (rc = stage_mark(stream, 4))) return rc;
         if ((rc = dispatch_accumulate(stream, A, vec, it))) return rc;
         if (r == 0 && (rc = stage_mark(stream, 5))) return rc;
