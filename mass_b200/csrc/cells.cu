@@ -613,17 +613,23 @@ k_voxel_sources(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__
 __global__ void __launch_bounds__(256, 4)
 k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vseg, const uint32_t *__restrict__ seg_frame,
                 const float2 *__restrict__ segws, size_t cap, CellGrid g, float alpha, int T,
-                float *__restrict__ gcoef, float *__restrict__ vA, const uint32_t *__restrict__ counters)
+                float *__restrict__ gcoef, float *__restrict__ vA, uint32_t *__restrict__ counters)
 {
     extern __shared__ float s_tab[];                  // [warps][2][Tp]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Tp = (T + 31) & ~31;
     float *tW = s_tab + (size_t)warp * 2 * Tp, *tS = tW + Tp;
     const uint32_t nvox = counters[MB_CNT_VOX];
-    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (int f = lane; f < Tp; f += 32) { tW[f] = 0.f; tS[f] = 0.f; }
     __syncwarp();
-    for (uint32_t j = wid; j < nvox; j += nw) {
+    // voxels are handed out by a work queue: a voxel's cost goes with the number of frames that saw it
+    uint32_t *queue = counters + MB_CNT_TASKQ + 2;
+    auto next_voxel = [&]() {
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(queue, 1u);
+        return __shfl_sync(FULL, u, 0);
+    };
+    for (uint32_t j = next_voxel(); j < nvox; j = next_voxel()) {
         const uint32_t v = vlist[j];
         uint2 mine = make_uint2(0u, 0u);
         if (lane < 8) mine = vseg[(size_t)j * 8 + lane];
@@ -1054,10 +1060,11 @@ struct ApplyArgs {
     const uint32_t *vlist;
     const uint2 *vrun;          // [voxel][8] run range of each source cell (from K6a)
     const float *vA, *P;
-    const uint32_t *counters;
+    uint32_t *counters;         // read; the two work-queue heads of this kernel are written
     CellGrid g;
     int F;
     float *map, *affine_a;
+    uint32_t round;             // launch index inside the chunk (which work-queue head to use)
     uint32_t run_base, run_cap;
 };
 
@@ -1067,12 +1074,21 @@ k_voxel_apply(const ApplyArgs A)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t nvox = A.counters[MB_CNT_VOX], nruns = A.counters[MB_CNT_RUNS];
+    // work queue over (voxel, channel block) units, as in the accumulate kernel: two heads used in turn by the launches
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.counters[MB_CNT_TASKQ + 3 + ((A.round + 1) & 1)] = 0;
     if (A.run_base >= nruns && A.run_base > 0) return;
+    uint32_t *queue = A.counters + MB_CNT_TASKQ + 3 + (A.round & 1);
     const uint32_t run_end = A.run_base + A.run_cap;
     const int F = A.F;
-    const int ch0 = (int)blockIdx.y * (32 * VEC * IT) + lane * VEC;
-    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t j = wid; j < nvox; j += nw) {
+    const uint32_t ny = (uint32_t)(F + 32 * VEC * IT - 1) / (uint32_t)(32 * VEC * IT), nunits = nvox * ny;
+    auto next_unit = [&]() {
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(queue, 1u);
+        return __shfl_sync(0xffffffffu, u, 0);
+    };
+    for (uint32_t unit = next_unit(); unit < nunits; unit = next_unit()) {
+        const uint32_t j = unit / ny;
+        const int ch0 = (int)(unit - j * ny) * (32 * VEC * IT) + lane * VEC;
         const uint32_t v = A.vlist[j];
         uint32_t lo = 0, hi = 0;
         if (lane < 8) {
@@ -1328,9 +1344,7 @@ int dispatch_accumulate(cudaStream_t stream, const AccArgs &A, int vec, int it)
 template <int VEC, int IT>
 int launch_apply(cudaStream_t stream, const ApplyArgs &A)
 {
-    const int cblocks = (A.F + 32 * VEC * IT - 1) / (32 * VEC * IT);
-    dim3 grid(MB_NUM_SMS * 8, cblocks);
-    k_voxel_apply<VEC, IT><<<grid, 256, 0, stream>>>(A);
+    k_voxel_apply<VEC, IT><<<MB_NUM_SMS * 8, 256, 0, stream>>>(A);
     MB_LAUNCHED();
     return MB_OK;
 }
@@ -1525,8 +1539,14 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     MB_LAUNCHED();
     // K5, K6
     if ((rc = stage_mark(stream, 3))) return rc;
-    k_seg_sums<<<MB_NUM_SMS * 8, 256, 0, stream>>>(ival, b.rec, b.seg_start, b.segws, (size_t)n, b.counters);
-    MB_LAUNCHED();
+    {
+        // one full wave: every CTA takes an equal share of the segments, so a partial second wave would idle SMs
+        int per_sm = 1;
+        MB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seg_sums, 256, 0));
+        if (per_sm < 1) per_sm = 1;
+        k_seg_sums<<<MB_NUM_SMS * per_sm, 256, 0, stream>>>(ival, b.rec, b.seg_start, b.segws, (size_t)n, b.counters);
+        MB_LAUNCHED();
+    }
     {
         const size_t smem = (size_t)8 * 2 * ((T + 31) & ~31) * sizeof(float);
         MB_CHECK_CUDA(cudaFuncSetAttribute(k_voxel_scalars, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1552,7 +1572,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     Y.g = g; Y.F = F; Y.map = map; Y.affine_a = affine_a; Y.run_cap = run_cap;
     for (int r = 0; r < rounds; ++r) {
         A.run_base = Y.run_base = (uint32_t)r * run_cap;
-        A.round = (uint32_t)r;
+        A.round = Y.round = (uint32_t)r;
         if (r == 0 && (rc = stage_mark(stream, 4))) return rc;
         if ((rc = dispatch_accumulate(stream, A, vec, it))) return rc;
         if (r == 0 && (rc = stage_mark(stream, 5))) return rc;
