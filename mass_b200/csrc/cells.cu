@@ -545,10 +545,19 @@ k_vox_list(const uint32_t *__restrict__ bitmap, uint32_t nwords, uint32_t *state
 // order, pixel order inside the item).  One thread per segment; an item's records are contiguous.
 __global__ void __launch_bounds__(256)
 k_seg_sums(const uint32_t *__restrict__ ival, const uint4 *__restrict__ rec, const uint32_t *__restrict__ seg_start,
-           float2 *__restrict__ segws, size_t cap, const uint32_t *__restrict__ counters)
+           float2 *__restrict__ segws, size_t cap, uint32_t *__restrict__ counters)
 {
     const uint32_t nsegs = counters[MB_CNT_SEGS];
-    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nsegs; s += gridDim.x * blockDim.x) {
+    // warps take 32 consecutive segments at a time from a work queue (segments differ a lot in pixel count)
+    uint32_t *queue = counters + MB_CNT_TASKQ + 5;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t s0 = 0;
+        if (lane == 0) s0 = atomicAdd(queue, 32u);
+        s0 = __shfl_sync(FULL, s0, 0);
+        if (s0 >= nsegs) break;
+        const uint32_t s = s0 + lane;
+        if (s >= nsegs) continue;
         const uint32_t beg = seg_start[s], end = seg_start[s + 1];
         float W[8], S2[8];
 #pragma unroll
