@@ -545,19 +545,10 @@ k_vox_list(const uint32_t *__restrict__ bitmap, uint32_t nwords, uint32_t *state
 // order, pixel order inside the item).  One thread per segment; an item's records are contiguous.
 __global__ void __launch_bounds__(256)
 k_seg_sums(const uint32_t *__restrict__ ival, const uint4 *__restrict__ rec, const uint32_t *__restrict__ seg_start,
-           float2 *__restrict__ segws, size_t cap, uint32_t *__restrict__ counters)
+           float2 *__restrict__ segws, size_t cap, const uint32_t *__restrict__ counters)
 {
     const uint32_t nsegs = counters[MB_CNT_SEGS];
-    // warps take 32 consecutive segments at a time from a work queue (segments differ a lot in pixel count)
-    uint32_t *queue = counters + MB_CNT_TASKQ + 5;
-    const int lane = threadIdx.x & 31;
-    for (;;) {
-        uint32_t s0 = 0;
-        if (lane == 0) s0 = atomicAdd(queue, 32u);
-        s0 = __shfl_sync(FULL, s0, 0);
-        if (s0 >= nsegs) break;
-        const uint32_t s = s0 + lane;
-        if (s >= nsegs) continue;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nsegs; s += gridDim.x * blockDim.x) {
         const uint32_t beg = seg_start[s], end = seg_start[s + 1];
         float W[8], S2[8];
 #pragma unroll
@@ -1069,11 +1060,10 @@ struct ApplyArgs {
     const uint32_t *vlist;
     const uint2 *vrun;          // [voxel][8] run range of each source cell (from K6a)
     const float *vA, *P;
-    uint32_t *counters;         // read; the two work-queue heads of this kernel are written
+    const uint32_t *counters;
     CellGrid g;
     int F;
     float *map, *affine_a;
-    uint32_t round;             // launch index inside the chunk (which work-queue head to use)
     uint32_t run_base, run_cap;
 };
 
@@ -1083,21 +1073,12 @@ k_voxel_apply(const ApplyArgs A)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t nvox = A.counters[MB_CNT_VOX], nruns = A.counters[MB_CNT_RUNS];
-    // work queue over (voxel, channel block) units, as in the accumulate kernel: two heads used in turn by the launches
-    if (blockIdx.x == 0 && threadIdx.x == 0) A.counters[MB_CNT_TASKQ + 3 + ((A.round + 1) & 1)] = 0;
     if (A.run_base >= nruns && A.run_base > 0) return;
-    uint32_t *queue = A.counters + MB_CNT_TASKQ + 3 + (A.round & 1);
     const uint32_t run_end = A.run_base + A.run_cap;
     const int F = A.F;
-    const uint32_t ny = (uint32_t)(F + 32 * VEC * IT - 1) / (uint32_t)(32 * VEC * IT), nunits = nvox * ny;
-    auto next_unit = [&]() {
-        uint32_t u = 0;
-        if (lane == 0) u = atomicAdd(queue, 1u);
-        return __shfl_sync(0xffffffffu, u, 0);
-    };
-    for (uint32_t unit = next_unit(); unit < nunits; unit = next_unit()) {
-        const uint32_t j = unit / ny;
-        const int ch0 = (int)(unit - j * ny) * (32 * VEC * IT) + lane * VEC;
+    const int ch0 = (int)blockIdx.y * (32 * VEC * IT) + lane * VEC;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j = wid; j < nvox; j += nw) {
         const uint32_t v = A.vlist[j];
         uint32_t lo = 0, hi = 0;
         if (lane < 8) {
@@ -1353,7 +1334,9 @@ int dispatch_accumulate(cudaStream_t stream, const AccArgs &A, int vec, int it)
 template <int VEC, int IT>
 int launch_apply(cudaStream_t stream, const ApplyArgs &A)
 {
-    k_voxel_apply<VEC, IT><<<MB_NUM_SMS * 8, 256, 0, stream>>>(A);
+    const int cblocks = (A.F + 32 * VEC * IT - 1) / (32 * VEC * IT);
+    dim3 grid(MB_NUM_SMS * 8, cblocks);
+    k_voxel_apply<VEC, IT><<<grid, 256, 0, stream>>>(A);
     MB_LAUNCHED();
     return MB_OK;
 }
@@ -1581,7 +1564,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     Y.g = g; Y.F = F; Y.map = map; Y.affine_a = affine_a; Y.run_cap = run_cap;
     for (int r = 0; r < rounds; ++r) {
         A.run_base = Y.run_base = (uint32_t)r * run_cap;
-        A.round = Y.round = (uint32_t)r;
+        A.round = (uint32_t)r;
         if (r == 0 && (rc = stage_mark(stream, 4))) return rc;
         if ((rc = dispatch_accumulate(stream, A, vec, it))) return rc;
         if (r == 0 && (rc = stage_mark(stream, 5))) return rc;
