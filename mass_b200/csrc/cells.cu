@@ -129,7 +129,8 @@ constexpr int TILE_W = 32, TILE_H = 8, TILE_PIX = TILE_W * TILE_H;
 constexpr int WHASH = 512;                       // hash slots per warp (>= 2 x pixels of a tile)
 constexpr int ITEM_MAX = 16;                     // pixels per item
 constexpr uint32_t HASH_EMPTY = 0xffffffffu;
-constexpr int TASK_ITEMS = 64;                   // items per accumulate task; runs never cross a task
+constexpr int TASK_ITEMS = 128;                  // items per accumulate task; runs never cross a task
+constexpr int TASK_WORDS = TASK_ITEMS / 32;      // items per lane when a warp loads a task
 constexpr uint32_t MAX_TILES = 1u << 20;         // tile ids are 20 bits of the item value
 
 __device__ __forceinline__ uint32_t item_tile(uint32_t v) { return v >> 12; }
@@ -848,7 +849,7 @@ k_cell_accumulate(const AccArgs A)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nitems = A.counters[MB_CNT_NVALID], nruns = A.counters[MB_CNT_RUNS];
     // Work queue: a unit is (task, channel block); warps take the next unit from a counter when they finish one, so
-    // the tasks' very different pixel counts (64 items of 1..16 pixels) do not leave SMs idle at the end.  The
+    // the tasks' very different pixel counts (TASK_ITEMS items of 1..16 pixels each) do not leave SMs idle at the end.  The
     // launches of a chunk use the two queue heads in turn; each launch clears the one the next launch will use.
     if (blockIdx.x == 0 && threadIdx.x == 0) A.counters[MB_CNT_TASKQ + ((A.round + 1) & 1)] = 0;
     if (A.run_base >= nruns) return;
@@ -874,14 +875,14 @@ k_cell_accumulate(const AccArgs A)
             const uint32_t e_after = end == nitems ? nruns : A.roff[end >> 5];
             if (e_after <= A.run_base || e >= run_end) continue;         // no run of this round in the task
         }
-        // ---- the task's items: pixel prefix, run heads, segment ranks (two items per lane) -----------------
-        uint32_t ihead[2];                                                // run-head masks of items 0-31, 32-63
+        // ---- the task's items: pixel prefix, run heads, segment ranks (TASK_WORDS items per lane) --------
+        uint32_t ihead[TASK_WORDS];                                       // run-head masks of items 0-31, 32-63, ...
         uint32_t npixels;
         {
-            uint32_t key[2], len[2];
+            uint32_t key[TASK_WORDS], len[TASK_WORDS];
             __syncwarp();
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < TASK_WORDS; ++h) {
                 const uint32_t i = base + 32 * h + lane;
                 key[h] = 0xfffffffeu;
                 len[h] = 0;
@@ -896,7 +897,7 @@ k_cell_accumulate(const AccArgs A)
             }
             uint32_t carry = 0, lastkey = 0xffffffffu;                    // != any key: item 0 is a run head
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < TASK_WORDS; ++h) {
                 uint32_t inc = len[h];
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -1289,7 +1290,7 @@ size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const Cel
     return used;
 }
 
-// most runs a call can produce: every cell starts one, every task start (64 items) may split one
+// most runs a call can produce: every cell starts one, every task start (TASK_ITEMS items) may split one
 size_t worst_runs(uint32_t n, const CellGrid &g)
 {
     const size_t ncap = (size_t)n < (size_t)g.invalid ? (size_t)n : (size_t)g.invalid;
