@@ -222,14 +222,14 @@ k_cell_voxelise(const float *__restrict__ rays, const float *__restrict__ depth,
     pix[pid] = out;
 }
 
-struct WarpTile {
+struct __align__(16) WarpTile {
     uint32_t hkey[WHASH];
     uint16_t cnt[WHASH], start[WHASH];
 };
 
 // K1b: one warp per 32 x 8 tile groups the tile's pixels by cell (see above) and writes the grouped records
 // and the tile's items.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_tile_group(const uint4 *__restrict__ pix, TileGeom tg, uint32_t ntiles, uint4 *__restrict__ rec,
              uint32_t *__restrict__ tkey, uint32_t *__restrict__ tval, uint32_t *__restrict__ tcount)
 {
@@ -240,7 +240,15 @@ k_tile_group(const uint4 *__restrict__ pix, TileGeom tg, uint32_t ntiles, uint4 
     WarpTile &S = s_w[warp];
     const uint32_t frame = tile / (uint32_t)tg.tpf, tif = tile - frame * (uint32_t)tg.tpf;
     const int y0 = (int)(tif / (uint32_t)tg.tiles_x) * TILE_H, x0 = (int)(tif % (uint32_t)tg.tiles_x) * TILE_W;
-    for (int i = lane; i < WHASH; i += 32) { S.hkey[i] = HASH_EMPTY; S.cnt[i] = 0; }
+    {
+        // clear the table with 16-byte stores (WHASH keys = WHASH / 4 pieces, WHASH counters = WHASH / 8 pieces)
+        uint4 *hk = reinterpret_cast<uint4 *>(S.hkey), *ct = reinterpret_cast<uint4 *>(S.cnt);
+        const uint4 e4 = make_uint4(HASH_EMPTY, HASH_EMPTY, HASH_EMPTY, HASH_EMPTY), z4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int i = lane; i < WHASH / 4; i += 32) hk[i] = e4;
+#pragma unroll
+        for (int i = lane; i < WHASH / 8; i += 32) ct[i] = z4;
+    }
     const uint32_t ltmask = (1u << lane) - 1u;
     const size_t fbase = (size_t)frame * tg.H * tg.W;
     const int x = x0 + lane;
@@ -299,9 +307,14 @@ k_tile_group(const uint4 *__restrict__ pix, TileGeom tg, uint32_t ntiles, uint4 
         S.start[sl] = (uint16_t)(base & 0xffffu);
         if (c) {
             const uint32_t k = S.hkey[sl], gs = base & 0xffffu, is = base >> 16;
-            for (uint32_t o = 0, n = 0; o < c; o += ITEM_MAX, ++n) {
-                tkey[tbase + is + n] = k;
-                tval[tbase + is + n] = (tile << 12) | ((gs + o) << 4) | (min((uint32_t)ITEM_MAX, c - o) - 1u);
+            // nearly every group is one item (<= ITEM_MAX pixels): no loop on that path
+            tkey[tbase + is] = k;
+            tval[tbase + is] = (tile << 12) | (gs << 4) | (min((uint32_t)ITEM_MAX, c) - 1u);
+            if (c > ITEM_MAX) {
+                for (uint32_t o = ITEM_MAX, n = 1; o < c; o += ITEM_MAX, ++n) {
+                    tkey[tbase + is + n] = k;
+                    tval[tbase + is + n] = (tile << 12) | ((gs + o) << 4) | (min((uint32_t)ITEM_MAX, c - o) - 1u);
+                }
             }
         }
         base += c | (((c + ITEM_MAX - 1) / ITEM_MAX) << 16);
