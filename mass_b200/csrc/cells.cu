@@ -183,6 +183,8 @@ __device__ __forceinline__ uint32_t lookback_prefix(uint32_t *state, uint32_t ti
     return prefix;
 }
 
+constexpr int VOX_PPT = 4;                       // pixels per thread of k_cell_voxelise
+
 // K1a: grid = (pixel blocks, frames): pixel -> {cell key (or >= 0xffffffe0: invalid), 3 in-voxel ratios}, in
 // image order.  Pure per-pixel math at full occupancy; the grouping kernel below re-reads it.
 __global__ void __launch_bounds__(256)
@@ -203,23 +205,39 @@ k_cell_voxelise(const float *__restrict__ rays, const float *__restrict__ depth,
     }
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < MB_NUM_COUNTERS) counters[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npix) return;
-    const size_t pid = (size_t)t * npix + p;
-    float r0, r1, r2;
-    orient(P, rays[3 * (size_t)p], rays[3 * (size_t)p + 1], rays[3 * (size_t)p + 2], r0, r1, r2);
-    const BinResult b = bin_point_fast(bins_x, nx, bins_y, ny, bins_z, nz, spacing, P[9], P[10], P[11], r0, r1, r2,
-                                       depth[pid], min_d, max_d);
-    uint4 out = make_uint4(0xffffffffu, 0u, 0u, 0u);
-    if (b.ok) {
-        // map axes are (y flipped, x, z) = input axes (1, 0, 2): base_projection_layer.py:339
-        const float q0 = b.q1, q1 = b.q0, q2 = b.q2;
-        const int e0 = q0 < 0.5f ? b.i1 : b.i1 + 1;       // lower corner + 1
-        const int e1 = q1 < 0.5f ? b.i0 : b.i0 + 1;
-        const int e2 = q2 < 0.5f ? b.i2 : b.i2 + 1;
-        out = make_uint4(cell_key(g, e0, e1, e2), __float_as_uint(q0), __float_as_uint(q1), __float_as_uint(q2));
+    // VOX_PPT pixels per thread (a CTA covers 256 * VOX_PPT consecutive pixels of one frame): the loads of all of them
+    // are issued before the first is used, and the per-CTA prologue above is paid once for all of them
+    float ray[VOX_PPT][3], dep[VOX_PPT];
+    const uint32_t p0 = blockIdx.x * (256u * VOX_PPT) + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < VOX_PPT; ++i) {
+        const uint32_t p = p0 + 256u * i;
+        if (p < npix) {
+            ray[i][0] = __ldg(rays + 3 * (size_t)p);
+            ray[i][1] = __ldg(rays + 3 * (size_t)p + 1);
+            ray[i][2] = __ldg(rays + 3 * (size_t)p + 2);
+            dep[i] = __ldg(depth + (size_t)t * npix + p);
+        }
     }
-    pix[pid] = out;
+#pragma unroll
+    for (int i = 0; i < VOX_PPT; ++i) {
+        const uint32_t p = p0 + 256u * i;
+        if (p >= npix) break;
+        float r0, r1, r2;
+        orient(P, ray[i][0], ray[i][1], ray[i][2], r0, r1, r2);
+        const BinResult b = bin_point_fast(bins_x, nx, bins_y, ny, bins_z, nz, spacing, P[9], P[10], P[11], r0, r1, r2,
+                                           dep[i], min_d, max_d);
+        uint4 out = make_uint4(0xffffffffu, 0u, 0u, 0u);
+        if (b.ok) {
+            // map axes are (y flipped, x, z) = input axes (1, 0, 2): base_projection_layer.py:339
+            const float q0 = b.q1, q1 = b.q0, q2 = b.q2;
+            const int e0 = q0 < 0.5f ? b.i1 : b.i1 + 1;       // lower corner + 1
+            const int e1 = q1 < 0.5f ? b.i0 : b.i0 + 1;
+            const int e2 = q2 < 0.5f ? b.i2 : b.i2 + 1;
+            out = make_uint4(cell_key(g, e0, e1, e2), __float_as_uint(q0), __float_as_uint(q1), __float_as_uint(q2));
+        }
+        pix[(size_t)t * npix + p] = out;
+    }
 }
 
 struct __align__(16) WarpTile {
@@ -1506,7 +1524,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     int rc;
     if ((rc = stage_mark(stream, 0))) return rc;
     uint32_t *tkey = b.keys_b, *tval = b.pids_b;          // tile-local item lists live in the sort's second buffers
-    dim3 vgrid((npix + 255) / 256, (unsigned)T);
+    dim3 vgrid((npix + 256 * VOX_PPT - 1) / (256 * VOX_PPT), (unsigned)T);
     k_cell_voxelise<<<vgrid, 256, 0, stream>>>(rays, depth, pose, npix, bins_x, nx, bins_y, ny, bins_z, nz, g, min_d, max_d,
                                                b.pix, b.counters);
     MB_LAUNCHED();
