@@ -179,9 +179,25 @@ int mb_lsap(void *stream, const float *cost32, const double *cost64, int n, int 
             int32_t *status, void *workspace, size_t workspace_bytes);
 
 /* Synchronises `stream` and returns the sticky error bits the batched kernels left in the workspace of
- * the last MB_MODE_FAST call: 0 = fine, bit 0 = an in-order row update gave up waiting for its
- * predecessor (never expected; the map is then not trustworthy). */
+ * the last MB_MODE_FAST call: 0 = fine; bit 0 = more accumulate runs than the planned rounds hold (an
+ * internal invariant: never expected, the map is then not trustworthy); bit 1 = a class id outside
+ * [0, F) in `class_ids` (torch.nn.functional.one_hot raises on it in the reference,
+ * mass/nn/applications/semantic_projection_layer.py:203-214; the kernel adds nothing for that pixel). */
 int mb_layer_update_status(void *stream, const void *workspace, uint32_t *error_bits_host);
+
+/* Synchronises `stream` and copies the counters the last MB_MODE_FAST chunk left in its workspace to
+ * counters_host[0 .. min(capacity, 16)): measurement aid (bench.py derives SURVEY.md 8d's bytes per frame from
+ * them instead of hard-coding it).  Indices: */
+#define MB_COUNTER_ITEMS 1      /* (cell, tile) items sorted */
+#define MB_COUNTER_CELLS 2      /* distinct cells */
+#define MB_COUNTER_SEGMENTS 3   /* (cell, frame) segments */
+#define MB_COUNTER_RUNS 4       /* accumulate runs */
+#define MB_COUNTER_ERROR 5      /* the bits of mb_layer_update_status */
+#define MB_COUNTER_VOXELS 6     /* distinct voxels touched by the chunk */
+#define MB_COUNTER_VOXEL_FRAMES 7 /* (voxel, frame) pairs: the sum over the chunk's frames of U_f, the voxels one
+                                     frame touches (the reference rewrites each of them once per frame,
+                                     mass/utils/projection.py:335-351) */
+int mb_layer_update_counters(void *stream, const void *workspace, uint32_t *counters_host, int capacity);
 
 /* ---- measurement aid (bench.py) -------------------------------------------------------------------------
  * mb_profile_stages(1) makes MB_MODE_FAST calls record CUDA events on their stream between the stages of

@@ -5,6 +5,8 @@ missing it is built in-tree with nvcc for sm_100a, and if that is impossible the
 import of any hot-path function fails loudly.
 """
 import ctypes
+import fcntl
+import hashlib
 import os
 import subprocess
 
@@ -13,6 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libmassb200.so")
+STAMP_PATH = SO_PATH + ".srchash"
 
 MODE_EXACT = 0
 MODE_FAST = 1
@@ -26,17 +29,47 @@ _f32 = ctypes.c_float
 _sz = ctypes.c_size_t
 
 
-def build(force=False):
-    """Compile every CUDA source for sm_100a (see csrc/Makefile)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+def _sources():
+    srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")) or f == "Makefile")
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "massb200.h"))
-    stale = (not os.path.exists(SO_PATH) or
-             any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs))
-    if force or stale:
-        cmd = ["make", "-C", CSRC, "-j8"] + (["-B"] if force else [])
-        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        if proc.returncode != 0:
-            raise RuntimeError("building libmassb200.so failed:\n" + proc.stdout[-4000:])
+    return srcs
+
+
+def source_hash():
+    """sha256 over every source the library is built from.  Compared with the stamp written next to the .so, so a
+    stale binary is never loaded (file times do not survive a snapshot copy; contents do)."""
+    h = hashlib.sha256()
+    for path in _sources():
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def is_stale():
+    if not os.path.exists(SO_PATH) or not os.path.exists(STAMP_PATH):
+        return True
+    with open(STAMP_PATH) as f:
+        return f.read().strip() != source_hash()
+
+
+def build(force=False):
+    """Compile every CUDA source for sm_100a (see csrc/Makefile); a no-op when the library matches the sources.
+    Concurrent callers (one process per GPU) serialise on a lock file."""
+    if not force and not is_stale():
+        return SO_PATH
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or is_stale():
+                proc = subprocess.run(["make", "-C", CSRC, "-j8", "-B"], stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True)
+                if proc.returncode != 0:
+                    raise RuntimeError("building libmassb200.so failed:\n" + proc.stdout[-4000:])
+                with open(STAMP_PATH, "w") as f:
+                    f.write(source_hash())
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO_PATH
 
 
@@ -59,6 +92,7 @@ _SIGNATURES = {
     "mb_profile_stages": (_i32, [_i32]),
     "mb_profile_read": (_i32, [_vp, _i32]),
     "mb_layer_update_status": (_i32, [_vp, _vp, _vp]),
+    "mb_layer_update_counters": (_i32, [_vp, _vp, _vp, _i32]),
     "mb_class_presence_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "mb_class_presence": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _sz]),
     "mb_instance_pool": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
@@ -78,8 +112,7 @@ def lib():
     """Loads (building first if needed) the shared library; raises if impossible."""
     global _lib
     if _lib is None:
-        if not os.path.exists(SO_PATH):
-            build()
+        build()                            # no-op unless a source changed since the library was built
         L = ctypes.CDLL(SO_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError here = header/library mismatch
@@ -135,6 +168,20 @@ class Workspace:
         return self.buf
 
 
+_ws_uses = {}
+
+
+def note_workspace_use(buf):
+    """Counts the library calls that were handed `buf` as scratch (its counters are overwritten by each)."""
+    key = buf.data_ptr()
+    _ws_uses[key] = _ws_uses.get(key, 0) + 1
+    return _ws_uses[key]
+
+
+def workspace_uses(buf):
+    return _ws_uses.get(buf.data_ptr(), 0)
+
+
 _shared = {}
 
 
@@ -149,3 +196,37 @@ def shared_workspace(device):
     if key not in _shared:
         _shared[key] = Workspace()
     return _shared[key]
+
+
+
+class HostStaging:
+    """Two sets of device staging buffers, a copy stream and the events that order them: what update_batch needs to
+    overlap the host->device copy of chunk i+1 with the fusion of chunk i when it is handed HOST frames."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.slots = [dict(bufs={}, ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+
+    def buffer(self, slot, name, shape, dtype):
+        """Grow-only device tensor `name` of slot `slot`, viewed as `shape`."""
+        need = 1
+        for d in shape:
+            need *= int(d)
+        cur = self.slots[slot]["bufs"].get(name)
+        if cur is None or cur.dtype != dtype or cur.numel() < need:
+            cur = torch.empty(need, dtype=dtype, device=self.device)
+            self.slots[slot]["bufs"][name] = cur
+        return cur[:need].view(*shape)
+
+
+_staging = {}
+
+
+def host_staging(device):
+    key = torch.device(device)
+    if key.type == "cuda" and key.index is None:
+        key = torch.device("cuda", torch.cuda.current_device())
+    if key not in _staging:
+        _staging[key] = HostStaging(key)
+    return _staging[key]

@@ -164,13 +164,26 @@ MB_API int mb_update_feature_map(void *stream_, const int64_t *ind0, const int64
 }
 
 // Waits for `stream` and reports the sticky error bits the batched kernels left in the workspace
-// of the last MB_MODE_FAST call (0 = fine; bit 0: an in-order update wait timed out).
+// of the last MB_MODE_FAST call (0 = fine; bit 0: more accumulate runs than the planned rounds hold -- an internal
+// invariant; bit 1: a class id outside [0, F) in the class_ids image, where functional.one_hot would raise).
 MB_API int mb_layer_update_status(void *stream_, const void *workspace, uint32_t *error_bits_host)
 {
     MB_REQUIRE(workspace && error_bits_host, "mb_layer_update_status: null pointer");
     cudaStream_t stream = (cudaStream_t)stream_;
     MB_CHECK_CUDA(cudaMemcpyAsync(error_bits_host, (const uint32_t *)workspace + MB_CNT_ERROR, sizeof(uint32_t),
                                   cudaMemcpyDeviceToHost, stream));
+    MB_CHECK_CUDA(cudaStreamSynchronize(stream));
+    return MB_OK;
+}
+
+// Waits for `stream` and copies the device counters the last MB_MODE_FAST chunk left in its workspace
+// (MB_COUNTER_* indices of massb200.h) to the host: what bench.py derives its bytes-per-frame figure from.
+MB_API int mb_layer_update_counters(void *stream_, const void *workspace, uint32_t *counters_host, int capacity)
+{
+    MB_REQUIRE(workspace && counters_host && capacity > 0, "mb_layer_update_counters: null pointer");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int n = capacity < MB_NUM_COUNTERS ? capacity : MB_NUM_COUNTERS;
+    MB_CHECK_CUDA(cudaMemcpyAsync(counters_host, workspace, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     MB_CHECK_CUDA(cudaStreamSynchronize(stream));
     return MB_OK;
 }

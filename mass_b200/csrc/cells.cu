@@ -389,6 +389,7 @@ struct IndexOut {
     uint32_t *counters;
     uint32_t *state;                              // [tiles][3] look-back words, zeroed
     uint32_t *ticket;                             // zeroed
+    uint32_t run_limit;                           // runs the planned accumulate rounds can hold
 };
 
 __global__ void __launch_bounds__(256)
@@ -505,6 +506,7 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
                 O.counters[MB_CNT_CELLS] = nc;
                 O.counters[MB_CNT_SEGS] = ns;
                 O.counters[MB_CNT_RUNS] = nr;
+                if (nr > O.run_limit) atomicOr(&O.counters[MB_CNT_ERROR], 1u);     // never expected: worst_runs() bounds nr
                 O.cstart[nc] = i + 1;
                 O.cseg[nc] = ns;
                 O.crun[nc] = nr;
@@ -661,6 +663,7 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vs
         if (lane == 0) u = atomicAdd(queue, 1u);
         return __shfl_sync(FULL, u, 0);
     };
+    uint32_t nvt = 0;                                 // (voxel, frame) pairs this warp has seen: sum over frames of U_f
     for (uint32_t j = next_voxel(); j < nvox; j = next_voxel()) {
         const uint32_t v = vlist[j];
         uint2 mine = make_uint2(0u, 0u);
@@ -735,6 +738,7 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vs
             const float W = tW[base + lane], S2 = tS[base + lane];
             float r = 0.f, a = 1.0f;
             if (W > 0.f) { r = alpha / W; a = 1.0f - r * S2; }
+            nvt += __popc(__ballot_sync(FULL, W > 0.f));
             float inc = a;                             // inclusive product over lanes >= lane
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -780,6 +784,7 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vs
         if (lane == 0) vA[j] = carry;
         __syncwarp();
     }
+    if (lane == 0 && nvt) atomicAdd(&counters[MB_CNT_VOXFRAMES], nvt);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1001,7 +1006,12 @@ k_cell_accumulate(const AccArgs A)
                     const uint32_t tyo = tif / (uint32_t)A.tg.tiles_x, txo = tif - tyo * (uint32_t)A.tg.tiles_x;
                     const uint32_t y = tyo * TILE_H + (r.w >> 5), x = txo * TILE_W + (r.w & 31u);
                     if (ONEHOT) {
-                        src = (uint32_t)A.class_ids[(size_t)frame * np + y * A.fi.W + x];
+                        const int64_t id = A.class_ids[(size_t)frame * np + y * A.fi.W + x];
+                        src = (uint32_t)id;
+                        if ((uint64_t)id >= (uint64_t)F) {      // functional.one_hot raises here: flag it, add nothing
+                            src = 0xffffffffu;
+                            atomicOr(&A.counters[MB_CNT_ERROR], 2u);
+                        }
                     } else {
                         src = frame * A.fhw + (y / A.fi.ky) * A.fi.fw + x / A.fi.kx;
                     }
@@ -1554,6 +1564,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
         O.ucell = b.ucell; O.cstart = b.cstart; O.cseg = b.cseg; O.crun = b.crun;
         O.seg_start = b.seg_start; O.seg_frame = b.seg_frame; O.bitmap = b.bitmap; O.ctab = b.ctab;
         O.counters = b.counters; O.state = b.idx_state + 4; O.ticket = b.idx_state;
+        O.run_limit = (uint32_t)((uint64_t)rounds * run_cap < 0xffffffffull ? (uint64_t)rounds * run_cap : 0xffffffffull);
         k_cell_index<<<itiles, 256, 0, stream>>>(ikey, ival, n_items, (uint32_t)tg.tpf, g, O);
         MB_LAUNCHED();
     }

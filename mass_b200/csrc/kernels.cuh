@@ -10,6 +10,7 @@ constexpr int MB_CNT_SEGS = 3;       // batched path: (cell, frame) segments
 constexpr int MB_CNT_RUNS = 4;       // batched path: accumulate runs
 constexpr int MB_CNT_ERROR = 5;      // sticky error bits (read by mb_layer_update_status)
 constexpr int MB_CNT_VOX = 6;        // batched path: touched voxels
+constexpr int MB_CNT_VOXFRAMES = 7;  // batched path: (touched voxel, frame) pairs = sum over the chunk's frames of U_f
 constexpr int MB_CNT_TASKQ = 8;      // batched path: work-queue heads: +0/+1 accumulate (used in turn by its launches), +2 voxel scalars
 constexpr int MB_NUM_COUNTERS = 16;
 constexpr int MB_MAX_CHUNK_FRAMES = 1024;   // frames fused per batched chunk (per-voxel frame table in shared memory)

@@ -43,13 +43,19 @@ class SemanticProjectionLayer(BaseProjectionLayer):
         ids = torch.as_tensor(semantic).to(torch.int64)
         return ids[..., 0] if ids.dim() >= 3 and ids.shape[-1] == 1 else ids
 
+    def _validate(self, ids):
+        """functional.one_hot raises on ids outside [0, feature_size) (semantic_projection_layer.py:203-214).  A host
+        image (what the agent passes: numpy from the detector) is checked here, on the host, for free.  A DEVICE
+        image is not read back -- that would stall the stream on every frame; the kernel flags the bad id, adds
+        nothing for that pixel, and `check()` raises the same error."""
+        if not ids.is_cuda and ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= self.feature_size):
+            raise RuntimeError("Class values must be in [0, %d)" % self.feature_size)
+
     def update(self, observation: Dict[str, Any]):
         """observation["semantic"]: [H, W, 1] integer class ids
         (semantic_projection_layer.py:203-214: one_hot(ids, feature_size).float())."""
         ids = self._ids(observation["semantic"])
-        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= self.feature_size):
-            # functional.one_hot raises on the same input
-            raise RuntimeError("Class values must be in [0, %d)" % self.feature_size)
+        self._validate(ids)
         return super().update(dict(position=observation["position"], yaw=observation["yaw"],
                                    elevation=observation["elevation"], depth=observation["depth"],
                                    class_ids=ids))
@@ -60,10 +66,11 @@ class SemanticProjectionLayer(BaseProjectionLayer):
         if isinstance(observations, (list, tuple)):
             observations = {k: torch.stack([torch.as_tensor(o[k]) for o in observations])
                             for k in observations[0].keys()}
-        ids = torch.as_tensor(observations["semantic"]).to(torch.int64)
+        ids = torch.as_tensor(observations["semantic"])
+        if ids.is_cuda or ids.dtype not in (torch.int32, torch.int16, torch.uint8, torch.int8):
+            ids = ids.to(torch.int64)           # (narrow host ids cross PCIe as they are and widen on the device)
         ids = ids.reshape(-1, self.camera_height, self.camera_width)
-        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= self.feature_size):
-            raise RuntimeError("Class values must be in [0, %d)" % self.feature_size)
+        self._validate(ids)
         return super().update_batch(dict(position=observations["position"], yaw=observations["yaw"],
                                          elevation=observations["elevation"], depth=observations["depth"],
                                          class_ids=ids), fold=fold)

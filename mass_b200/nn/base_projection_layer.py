@@ -23,6 +23,14 @@ from mass_b200.nn.projection_layer import ProjectionLayer
 from mass_b200.utils.projection import camera_pose, project_camera_rays
 
 
+def _on_device(x):
+    return torch.is_tensor(x) and x.is_cuda
+
+
+def _as_host_tensor(x):
+    return x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x))
+
+
 def _edges(origin, cells, resolution):
     # base_projection_layer.py:164-181: the edge table is whatever ATen's CPU
     # arange produces for these float64 bounds; the kernels only ever read it.
@@ -118,6 +126,14 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         `data`.  Derived results (find()'s instance lists) are cached against it."""
         return (self._updates, self.data._version, self.data.data_ptr())
 
+    def mark_dirty(self):
+        """Tell the layer its map changed behind its back: a write through `data.data_ptr()` (the free function
+        `update_feature_map`, `mb_affine_apply_rows`, any other raw-pointer kernel) or a replay of a CUDA graph the
+        CALLER captured around `update_prepared` -- a replay runs no Python, so only the capture bumped the counter.
+        Invalidates everything memoised against `map_state()` (find(), predict_scene_differences)."""
+        self._updates += 1
+        return self
+
     def _launch(self, prep, fold=None):
         """Device side of an update: enqueues the kernels on the current stream.  No host work besides the
         launches, no allocation once the scratch buffer exists: a call with the same `prep` can be captured
@@ -135,7 +151,7 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
             # rounds of the feature pass); below the one-frame minimum the call fails
             want = min(want, int(self.workspace_limit))
         ws = (self._ws or _lib.shared_workspace(device)).get(want, device)
-        self._last_ws = ws
+        self._last_ws, self._last_ws_use = ws, _lib.note_workspace_use(ws)
         if fold is not None:
             partial_b, partial_a = fold
             _lib.check(L.mb_layer_fold(
@@ -177,18 +193,37 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         return self._launch(prep)
 
     def check(self):
-        """Synchronises and raises if the batched kernels flagged an error during the last
-        non-exact update (an in-order row update that timed out: never expected)."""
-        if self.exact or getattr(self, "_last_ws", None) is None:
+        """Synchronises and raises if the batched kernels of this layer's last non-exact update flagged an error:
+        bit 0 = more accumulate runs than the planned rounds hold (an internal invariant), bit 1 = a class id
+        outside [0, feature_size) in a `class_ids` image that was given as a DEVICE tensor (host images are checked
+        on the host before the launch; functional.one_hot raises on the same input in the reference).  The bits
+        live in the scratch buffer: if another layer has used the device's shared buffer since, they are gone and
+        only the synchronisation happens."""
+        ws = getattr(self, "_last_ws", None)
+        if self.exact or ws is None or getattr(self, "_last_ws_use", None) != _lib.workspace_uses(ws):
             torch.cuda.synchronize(self.data.device)
             return self
         import ctypes
         bits = ctypes.c_uint32(0)
-        _lib.check(_lib.lib().mb_layer_update_status(_lib.stream_ptr(self.data.device), _lib.ptr(self._last_ws),
+        _lib.check(_lib.lib().mb_layer_update_status(_lib.stream_ptr(self.data.device), _lib.ptr(ws),
                                                      ctypes.byref(bits)))
+        if bits.value & 2:
+            raise RuntimeError("Class values must be in [0, %d)" % self.feature_size)
         if bits.value:
             raise RuntimeError("libmassb200: batched update reported error bits 0x%x" % bits.value)
         return self
+
+    def counters(self):
+        """Synchronises and returns the device counters of this layer's last batched (non-exact) chunk as a dict:
+        items, cells, segments, runs, voxels (distinct voxels touched) and voxel_frames (sum over the chunk's frames
+        of the voxels each frame touches).  None if the scratch buffer has been used by another call since."""
+        ws = getattr(self, "_last_ws", None)
+        if ws is None or getattr(self, "_last_ws_use", None) != _lib.workspace_uses(ws):
+            return None
+        import ctypes
+        c = (ctypes.c_uint32 * 16)()
+        _lib.check(_lib.lib().mb_layer_update_counters(_lib.stream_ptr(self.data.device), _lib.ptr(ws), c, 16))
+        return dict(items=c[1], cells=c[2], segments=c[3], runs=c[4], error=c[5], voxels=c[6], voxel_frames=c[7])
 
     def update(self, observation: Dict[str, Any]):
         """Fuse one observation into the map; returns self.
@@ -198,7 +233,8 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         pose = camera_pose(observation["position"], observation["yaw"], observation["elevation"])
         features = observation.get("features")
         class_ids = None if features is not None else observation["class_ids"]
-        if self.frame_graphs and self.data.is_cuda:
+        if self.frame_graphs and self.data.is_cuda and not torch.cuda.is_current_stream_capturing():
+            # (a caller who is capturing gets the plain launches: they land in the caller's graph)
             return self._update_replayed(pose, observation["depth"], features, class_ids)
         return self._fuse(pose, observation["depth"], features, class_ids, 1)
 
@@ -207,7 +243,11 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         frame is copied into persistent device buffers and the captured launch sequence is replayed."""
         H, W, F = self.camera_height, self.camera_width, self.feature_size
         shape = None if features is None else tuple(torch.as_tensor(features).shape[-3:-1])
-        key = (shape, self.exact, self.workspace_limit, self.data.data_ptr(), torch.cuda.current_stream(self.data.device).cuda_stream)
+        # everything the captured launches bake in as by-value arguments: the reference reads these attributes on
+        # every update() (base_projection_layer.py:334-341), so changing one must not replay a stale graph
+        key = (shape, self.exact, self.workspace_limit, self.data.data_ptr(),
+               torch.cuda.current_stream(self.data.device).cuda_stream, float(self.interpolation_weight),
+               float(self.min_ray_depth), float(self.max_ray_depth))
         entry = self._frame_graphs.get(key)
         if entry is None:
             if len(self._frame_graphs) >= 4:
@@ -252,9 +292,63 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         pose = camera_pose(torch.as_tensor(observations["position"]).reshape(T, 3),
                            torch.as_tensor(observations["yaw"]).reshape(T),
                            torch.as_tensor(observations["elevation"]).reshape(T))
-        if "features" in observations:
-            return self._fuse(pose, observations["depth"], observations["features"], None, T, fold=fold)
-        return self._fuse(pose, observations["depth"], None, observations["class_ids"], T, fold=fold)
+        features = observations.get("features")
+        class_ids = None if features is not None else observations["class_ids"]
+        if T > 1 and self.data.is_cuda and not _on_device(observations["depth"]) \
+                and not _on_device(features if features is not None else class_ids):
+            return self._fuse_from_host(pose, observations["depth"], features, class_ids, T, fold)
+        return self._fuse(pose, observations["depth"], features, class_ids, T, fold=fold)
+
+    host_chunk_bytes = 256 << 20     # staging per chunk when update_batch is handed frames in HOST memory
+
+    def _fuse_from_host(self, pose, depth, features, class_ids, T, fold=None):
+        """T frames that live in host memory (numpy arrays or CPU tensors; pinned memory makes the copies
+        asynchronous): the call is cut into chunks of ~host_chunk_bytes, chunk i+1 is copied to one of two device
+        staging sets on a copy stream while chunk i is being fused, so the caller sees the PCIe rate of its inputs
+        instead of copy + fusion back to back.  Frames still enter the map strictly in order (batches compose)."""
+        device = _lib.require_cuda(self.data.device)
+        H, W = self.camera_height, self.camera_width
+        depth = _as_host_tensor(depth).reshape(T, H, W)
+        if depth.dtype != torch.float32:
+            depth = depth.to(torch.float32)
+        if features is not None:
+            feats = _as_host_tensor(features)
+            if feats.dim() == 3:
+                feats = feats[None]
+            if feats.dtype != torch.float32:
+                feats = feats.to(torch.float32)
+            if feats.shape[0] != T or feats.shape[-1] != self.feature_size:
+                raise ValueError("features must be [%d, h, w, %d], got %s" % (T, self.feature_size, tuple(feats.shape)))
+            other, name = feats, "features"
+        else:
+            ids = _as_host_tensor(class_ids).reshape(T, H, W)
+            if ids.dtype not in (torch.int64, torch.int32, torch.int16, torch.uint8, torch.int8):
+                ids = ids.to(torch.int64)
+            other, name = ids, "class_ids"
+        per_frame = depth[0].numel() * depth.element_size() + other[0].numel() * other.element_size()
+        chunk = int(max(1, min(T, self.host_chunk_bytes // max(per_frame, 1))))
+        st = _lib.host_staging(device)
+        main = torch.cuda.current_stream(device)
+        for slot in st.slots:
+            slot["free"].record(main)                  # staging sets may be overwritten once earlier work is done
+        for i, s in enumerate(range(0, T, chunk)):
+            e = min(s + chunk, T)
+            slot = st.slots[i % 2]
+            d_buf = st.buffer(i % 2, "depth", (e - s, H, W), torch.float32)
+            o_buf = st.buffer(i % 2, name, (e - s,) + tuple(other.shape[1:]), other.dtype)
+            with torch.cuda.stream(st.stream):
+                st.stream.wait_event(slot["free"])
+                d_buf.copy_(depth[s:e], non_blocking=True)
+                o_buf.copy_(other[s:e], non_blocking=True)
+                slot["ready"].record(st.stream)
+            main.wait_event(slot["ready"])
+            if name == "features":
+                self._fuse(pose[s:e], d_buf, o_buf, None, e - s, fold=fold)
+            else:
+                self._fuse(pose[s:e], d_buf, None, o_buf if o_buf.dtype == torch.int64 else o_buf.to(torch.int64),
+                           e - s, fold=fold)
+            slot["free"].record(main)
+        return self
 
     # -- whole-map readers next to the path (SURVEY.md 8f rank 1) ------------------------------------------------
     def column_summary(self, depth_slice: slice = None, obstacle_threshold: float = 0.0,

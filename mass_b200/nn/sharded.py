@@ -54,6 +54,7 @@ def apply_partial(layer, idx, a, b):
     _lib.check(_lib.lib().mb_affine_apply_rows(
         _lib.stream_ptr(device), _lib.ptr(data), int(data.shape[3]), _lib.ptr(idx.to(torch.int64).contiguous()),
         _lib.ptr(a.to(torch.float32).contiguous()), _lib.ptr(b.to(torch.float32).contiguous()), n))
+    layer.mark_dirty()            # a raw-pointer write: results memoised against map_state() are stale now
 
 
 def exchange_partials(idx, a, b, group=None):

@@ -98,8 +98,8 @@ def test_episode_pair_maps_find_and_match(oracle, exact):
             break
         found_any = True
         assert len(a0) == len(r0) and len(a1) == len(r1)
-        np.testing.assert_allclose(torch.stack(a0).cpu().numpy(), np.stack(r0), rtol=1e-4, atol=1e-5)
-        np.testing.assert_allclose(torch.stack(a1).cpu().numpy(), np.stack(r1), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(torch.stack(a0).cpu().numpy(), np.stack(r0), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(torch.stack(a1).cpu().numpy(), np.stack(r1), rtol=1e-5, atol=1e-5)
         moved.add(obj)
     assert found_any
     # per class: same instances (count, order, boxes) and pooled statistics in both maps
@@ -109,6 +109,6 @@ def test_episode_pair_maps_find_and_match(oracle, exact):
             rconf, rcoord, rsize, rfeats, rboxes = oracle.find(os_, cls, 0.0, 0, 0.0, of)
             assert [tuple(b) for b in gs.boxes] == [tuple(b) for b in rboxes]
             if rconf:
-                np.testing.assert_allclose(torch.stack(conf).cpu().numpy(), np.stack(rconf), rtol=1e-4)
-                np.testing.assert_allclose(torch.stack(size).cpu().numpy(), np.stack(rsize), rtol=1e-4)
-                np.testing.assert_allclose(torch.stack(feats).cpu().numpy(), np.stack(rfeats), rtol=1e-4, atol=1e-6)
+                np.testing.assert_allclose(torch.stack(conf).cpu().numpy(), np.stack(rconf), rtol=1e-5)
+                np.testing.assert_allclose(torch.stack(size).cpu().numpy(), np.stack(rsize), rtol=1e-5)
+                np.testing.assert_allclose(torch.stack(feats).cpu().numpy(), np.stack(rfeats), rtol=1e-5, atol=1e-6)

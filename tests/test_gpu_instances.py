@@ -116,6 +116,50 @@ def test_find_cache_follows_the_map(block_layers, dev):
         f.data.copy_(saved_f)
 
 
+def test_find_cache_follows_raw_pointer_writers(block_layers, dev):
+    """Writers that bypass update(): the ordered affine apply of a sharded partial bumps the map state itself; a
+    CUDA graph the CALLER captured around update_prepared runs no Python on replay, so the caller says
+    mark_dirty() -- after which find() sees the new map."""
+    from mass_b200.nn import sharded
+    g, layers = block_layers
+    s, f = layers[1]
+    saved = s.data.clone()
+    try:
+        before = s.find(7, 0.0, 0, 0.0, f)
+        assert len(before[0]) > 0
+        occ = (s.data[..., 7] != 0).nonzero()
+        idx = ((occ[:, 0] * s.data.shape[1] + occ[:, 1]) * s.data.shape[2] + occ[:, 2]).to(torch.int64)
+        state = s.map_state()
+        sharded.apply_partial(s, idx, torch.zeros(idx.numel(), device=dev),
+                              torch.zeros(idx.numel(), s.data.shape[3], device=dev))     # wipes class 7's voxels
+        assert s.map_state() != state
+        assert len(s.find(7, 0.0, 0, 0.0, f)[0]) == 0
+        # caller-captured graph: one frame that paints class 7 back in
+        s.exact = False
+        H, W = s.camera_height, s.camera_width
+        prep = s.prepare_batch(dict(position=np.array([[0.3, -0.1, 0.9]], np.float32), yaw=np.array([0.3], np.float32),
+                                    elevation=np.array([-0.4], np.float32),
+                                    depth=torch.full((1, H, W, 1), 0.6, device=dev),
+                                    class_ids=torch.full((1, H, W), 7, dtype=torch.int64, device=dev)))
+        s.update_prepared(prep)
+        s.data.copy_(saved)
+        sharded.apply_partial(s, idx, torch.zeros(idx.numel(), device=dev), torch.zeros(idx.numel(), s.data.shape[3], device=dev))
+        assert len(s.find(7, 0.0, 0, 0.0, f)[0]) == 0
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            s.update_prepared(prep)
+        state = s.map_state()
+        graph.replay()
+        assert s.map_state() == state                         # a replay runs no Python: the layer cannot know
+        s.mark_dirty()
+        assert len(s.find(7, 0.0, 0, 0.0, f)[0]) > 0
+    finally:
+        s.exact = True
+        s.data.copy_(saved)
+        s.mark_dirty()
+
+
 def test_pairwise_l2_golden(dev):
     from mass_b200.utils import instances
     g = golden("pairwise.npz")

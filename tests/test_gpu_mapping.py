@@ -512,6 +512,114 @@ def test_c2_full_size_properties(dev):
     assert bool(((d.data - e.data).abs() <= 1e-6 * d.data.abs()).all())
 
 
+def test_c2_full_size_values_vs_oracle(dev, oracle):
+    """The BENCHED workload itself against the oracle: all 500 frames of BASELINE config 2, fused in the batched
+    (affine) mode as one batch and as 5 x 100, compared with the threaded CPU oracle run frame by frame
+    (reference: mass/utils/projection.py:335-351).  Occupancy bit-exact, every element within 1e-5 relative --
+    including voxels driven towards the fp32 denormal range by hundreds of consecutive frames."""
+    import os
+    import bench
+    from mass_b200.utils import synthetic
+    T = 500
+    walk = bench.make_walkthrough(T)
+    kw = dict(bench.C2, **synthetic.MAP_ORIGIN)
+    ref = oracle.OracleLayer(nthreads=os.cpu_count() or 8, **kw)
+    for t in range(T):
+        ref.update(dict(position=walk["position"][t], yaw=walk["yaw"][t], elevation=walk["elevation"][t],
+                        depth=walk["depth"][t], features=synthetic.upsample(walk["probs_low"][t], 8)))
+    ref_d = torch.from_numpy(ref.data).to(dev)
+    del ref
+    ref_occ = (ref_d != 0).any(-1)
+    depth = torch.from_numpy(walk["depth"]).to(dev)
+    probs = torch.from_numpy(walk["probs_low"]).to(dev).repeat_interleave(8, 1).repeat_interleave(8, 2).contiguous()
+    obs = dict(position=walk["position"], yaw=walk["yaw"], elevation=walk["elevation"], depth=depth, features=probs)
+
+    def compare(layer, what):
+        got = layer.data
+        assert torch.equal((got != 0).any(-1), ref_occ), what + ": occupancy differs from the oracle"
+        # element-wise |got - ref| <= 1e-5 |ref| in float64, slab by slab (the map is 2.85 GiB)
+        worst = 0.0
+        for y in range(0, got.shape[0], 48):
+            g, r = got[y:y + 48].double(), ref_d[y:y + 48].double()
+            bad = (g - r).abs() > 1e-5 * r.abs()
+            assert not bool(bad.any()), "%s: %d elements out of tolerance in rows %d..%d" % (what, int(bad.sum()), y, y + 48)
+            nz = r != 0
+            if bool(nz.any()):
+                worst = max(worst, float(((g - r).abs()[nz] / r.abs()[nz]).max()))
+        return worst
+
+    one = make_layer(kw, dev, exact=False).update_batch(obs)
+    w1 = compare(one, "one batch of 500")
+    del one
+    five = make_layer(kw, dev, exact=False)
+    for s in range(0, T, 100):
+        five.update_batch({k: v[s:s + 100] for k, v in obs.items()})
+    w5 = compare(five, "5 x 100")
+    print("c2 full size vs oracle: worst relative error %.3g (one batch), %.3g (5 x 100); %d touched voxels"
+          % (w1, w5, int(ref_occ.sum())))
+
+
+def test_frame_graph_follows_layer_attributes(dev, oracle):
+    """update() replays a captured CUDA graph per frame; interpolation_weight / min_ray_depth / max_ray_depth are
+    read on every update() by the reference (base_projection_layer.py:334-341), so changing them after the first
+    frame must not replay launches that baked the old values in."""
+    kw = dict(camera_height=24, camera_width=24, vertical_fov=90.0, map_height=40, map_width=40, map_depth=16,
+              feature_size=3, grid_resolution=0.1, interpolation_weight=0.5)
+    rng = np.random.default_rng(5)
+    frames = _random_frames(rng, 3, 24, 24, 24, 24, 3, depth_lo=0.5, depth_hi=1.5)
+    ref = oracle.OracleLayer(**kw)
+    layer = make_layer(kw, dev, exact=True)
+    for t, alpha in enumerate((0.5, 0.25, 0.5)):
+        f = {k: v[t] for k, v in frames.items()}
+        ref.interpolation_weight = alpha
+        layer.interpolation_weight = alpha
+        ref.update(f)
+        layer.update(f)
+        assert np.array_equal(layer.data.cpu().numpy(), ref.data), t
+
+
+def test_device_class_ids_out_of_range_are_flagged(dev):
+    """functional.one_hot raises on ids outside [0, F) (semantic_projection_layer.py:203-214).  Host images raise
+    before the launch; a DEVICE image is not read back (no per-frame stall): the kernel flags it and check() raises."""
+    from mass_b200.nn.applications.semantic_projection_layer import SemanticProjectionLayer
+    kw = dict(camera_height=16, camera_width=16, vertical_fov=90.0, map_height=20, map_width=20, map_depth=8,
+              feature_size=5, grid_resolution=0.1, interpolation_weight=0.5)
+    layer = SemanticProjectionLayer(exact=False, **kw).to(dev)
+    obs = dict(position=np.zeros((2, 3), np.float32), yaw=np.zeros(2, np.float32), elevation=np.zeros(2, np.float32),
+               depth=np.full((2, 16, 16, 1), 0.5, np.float32), semantic=np.full((2, 16, 16, 1), 2, np.int64))
+    layer.update_batch(obs).check()
+    bad = dict(obs, semantic=np.full((2, 16, 16, 1), 5, np.int64))
+    with pytest.raises(RuntimeError, match="Class values"):
+        layer.update_batch(bad)
+    bad_dev = dict(obs, depth=torch.from_numpy(obs["depth"]).to(dev), semantic=torch.full((2, 16, 16, 1), 7, device=dev))
+    layer.update_batch(bad_dev)
+    with pytest.raises(RuntimeError, match="Class values"):
+        layer.check()
+    layer.update_batch(dict(obs, depth=torch.from_numpy(obs["depth"]).to(dev), semantic=torch.full((2, 16, 16, 1), 1, device=dev))).check()
+
+
+def test_update_batch_from_host_memory_is_pipelined_and_equal(dev):
+    """Frames handed over in HOST memory go through the chunked copy/fuse pipeline inside update_batch; the map must
+    equal fusing the same chunks from device memory (bitwise: same kernels, same batches)."""
+    kw = dict(camera_height=32, camera_width=32, vertical_fov=90.0, map_height=48, map_width=48, map_depth=16,
+              feature_size=6, grid_resolution=0.1, interpolation_weight=0.5)
+    rng = np.random.default_rng(8)
+    frames = _random_frames(rng, 11, 32, 32, 32, 32, 6, depth_lo=0.5, depth_hi=2.0)
+    a = make_layer(kw, dev, exact=False)
+    a.host_chunk_bytes = 3 * (32 * 32 * 4 * 7)                      # 3 frames per chunk: 4 chunks, the last partial
+    pinned = {k: (torch.from_numpy(v).pin_memory() if k in ("depth", "features") else v) for k, v in frames.items()}
+    a.update_batch(pinned)
+    b = make_layer(kw, dev, exact=False)
+    for s in range(0, 11, 3):
+        b.update_batch({k: (torch.from_numpy(v[s:s + 3]).to(dev) if k in ("depth", "features") else v[s:s + 3])
+                        for k, v in frames.items()})
+    assert torch.equal(a.data, b.data)
+    c = make_layer(kw, dev, exact=False)
+    c.host_chunk_bytes = 3 * (32 * 32 * 4 * 7)
+    c.update_batch(frames)                                            # pageable numpy arrays take the same path
+    assert torch.equal(c.data, b.data)
+
+
 # ---- frame-sharded scenes (SURVEY.md 8e) -----------------------------------------------------------
 def test_fold_and_ordered_apply_equal_sequential(dev, oracle):
     """One GPU standing in for three ranks: contiguous frame chunks folded into sparse partials from the
