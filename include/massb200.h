@@ -120,6 +120,34 @@ int mb_layer_fold(void *stream, const float *rays, const float *depth, const flo
 int mb_affine_apply_rows(void *stream, float *map, int F, const int64_t *voxel_index, const float *a,
                          const float *b, int64_t n);
 
+/* Sparse partials: the same fold without a second dense map.  A partial buffer holds
+ *   {count u32 | index int64[capacity] | a f32[capacity] | b f32[capacity][F]}   (offsets: mb_partial_buffer_layout,
+ *   in that order) -- ONE allocation, so that a peer GPU can map it and read it over NVLink;
+ * slot_table int32[S0*S1*S2] (-1 = no row yet) finds a voxel's row while the chunks of a rank are folded in, in frame
+ * order: mb_layer_fold_sparse composes each chunk onto the rows (a <- a_chunk * a, b <- a_chunk * b + b_chunk).
+ * mb_partial_reset empties table and buffer with memsets (first use); mb_partial_clear empties them by walking the
+ * rows in use.  mb_affine_apply_partial: map[index[i]] = a[i] * map[index[i]] + b[i] for i < count, with count read
+ * ON THE DEVICE (no host round trip) and `partial_buffer` allowed to live on a peer GPU: transfer and application
+ * are then one kernel.  A full partial sets error bit 2 (value 4) of mb_layer_update_status and drops the row. */
+size_t mb_partial_buffer_bytes(uint32_t capacity, int F);
+int mb_partial_buffer_layout(uint32_t capacity, int F, size_t *offsets_host /* [4]: count, index, a, b */);
+int mb_partial_reset(void *stream, int32_t *slot_table, int64_t voxels, void *partial_buffer);
+int mb_partial_clear(void *stream, int32_t *slot_table, void *partial_buffer, uint32_t capacity, int F);
+int mb_layer_fold_sparse(void *stream, const float *rays, const float *depth, const float *features,
+                         const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw, int F,
+                         const float *bins_x, int nx, const float *bins_y, int ny, const float *bins_z, int nz,
+                         int32_t *slot_table, void *partial_buffer, uint32_t capacity, float interpolation_weight,
+                         float min_ray_depth, float max_ray_depth, void *workspace, size_t workspace_bytes);
+int mb_affine_apply_partial(void *stream, float *map, int F, const void *partial_buffer, uint32_t capacity);
+
+/* Peer memory for partial buffers (CUDA IPC: another process of the box -- another GPU over NVLink -- maps the
+ * allocation).  The one exception to "the library owns no memory": an IPC handle names a whole allocation. */
+int mb_peer_alloc(size_t bytes, void **ptr_host);
+int mb_peer_free(void *ptr);
+int mb_peer_export(const void *ptr, void *handle64_host /* 64 bytes */);
+int mb_peer_open(const void *handle64_host, void **ptr_host);
+int mb_peer_close(void *ptr);
+
 /* ---- a11: SemanticProjectionLayer.find (mass/nn/applications/semantic_projection_layer.py:257-362) ----
  * Step 1, lines 309-317: image[y][x] = any over z of (box mean of map[..., category] with kernel
  * 2*contour_padding+1, zero padded, divisor k^3) > contour_threshold; uint8 [S0][S1].

@@ -89,6 +89,18 @@ _SIGNATURES = {
     "mb_layer_fold": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32,
                              _vp, _i32, _vp, _i32, _vp, _vp, _f32, _f32, _f32, _vp, _sz]),
     "mb_affine_apply_rows": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64]),
+    "mb_partial_buffer_bytes": (_sz, [ctypes.c_uint32, _i32]),
+    "mb_partial_buffer_layout": (_i32, [ctypes.c_uint32, _i32, _vp]),
+    "mb_partial_reset": (_i32, [_vp, _vp, _i64, _vp]),
+    "mb_partial_clear": (_i32, [_vp, _vp, _vp, ctypes.c_uint32, _i32]),
+    "mb_layer_fold_sparse": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32,
+                                    _vp, _i32, _vp, _i32, _vp, _vp, ctypes.c_uint32, _f32, _f32, _f32, _vp, _sz]),
+    "mb_affine_apply_partial": (_i32, [_vp, _vp, _i32, _vp, ctypes.c_uint32]),
+    "mb_peer_alloc": (_i32, [_sz, _vp]),
+    "mb_peer_free": (_i32, [_vp]),
+    "mb_peer_export": (_i32, [_vp, _vp]),
+    "mb_peer_open": (_i32, [_vp, _vp]),
+    "mb_peer_close": (_i32, [_vp]),
     "mb_profile_stages": (_i32, [_i32]),
     "mb_profile_read": (_i32, [_vp, _i32]),
     "mb_layer_update_status": (_i32, [_vp, _vp, _vp]),

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <string.h>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -224,12 +225,12 @@ static int layer_update(void *stream_, const float *rays, const float *depth, co
                         int F, const float *bins_x, int nx, const float *bins_y, int ny,
                         const float *bins_z, int nz, float *map, float *affine_a, float interpolation_weight,
                         float min_ray_depth, float max_ray_depth, int mode, void *workspace,
-                        size_t workspace_bytes)
+                        size_t workspace_bytes, const MbSparseFold *sparse = nullptr)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     MB_REQUIRE(T >= 0 && H > 0 && W > 0 && F > 0, "mb_layer_update: bad sizes");
     if (T == 0) return MB_OK;
-    MB_REQUIRE(rays && depth && pose && bins_x && bins_y && bins_z && map, "mb_layer_update: null pointer");
+    MB_REQUIRE(rays && depth && pose && bins_x && bins_y && bins_z && (map || sparse), "mb_layer_update: null pointer");
     MB_REQUIRE((features != nullptr) != (class_ids != nullptr),
                "mb_layer_update: pass exactly one of features / class_ids");
     MB_REQUIRE(nx >= 2 && ny >= 2 && nz >= 2, "mb_layer_update: every edge table needs >= 2 entries");
@@ -254,7 +255,8 @@ static int layer_update(void *stream_, const float *rays, const float *depth, co
                                       features ? features + (size_t)t * feat_stride : nullptr,
                                       class_ids ? class_ids + (size_t)t * npix : nullptr, pose + (size_t)t * 12, n,
                                       H, W, fh, fw, F, bins_x, nx, bins_y, ny, bins_z, nz, map, affine_a,
-                                      interpolation_weight, min_ray_depth, max_ray_depth, workspace, workspace_bytes);
+                                      interpolation_weight, min_ray_depth, max_ray_depth, workspace, workspace_bytes,
+                                      sparse);
             if (rc) return rc;
         }
         return MB_OK;
@@ -302,6 +304,91 @@ MB_API int mb_layer_fold(void *stream, const float *rays, const float *depth, co
     return layer_update(stream, rays, depth, features, class_ids, pose, T, H, W, fh, fw, F, bins_x, nx, bins_y, ny,
                         bins_z, nz, partial_b, partial_a, interpolation_weight, min_ray_depth, max_ray_depth,
                         MB_MODE_FAST, workspace, workspace_bytes);
+}
+
+// ---- sparse partials + peer memory (frame-sharded scenes over NVLink) -------------------------------------------------
+MB_API size_t mb_partial_buffer_bytes(uint32_t capacity, int F)
+{
+    return F > 0 ? mbk_partial_buffer_layout(capacity, F, nullptr) : 0;
+}
+
+MB_API int mb_partial_buffer_layout(uint32_t capacity, int F, size_t *offsets_host)
+{
+    MB_REQUIRE(offsets_host && F > 0, "mb_partial_buffer_layout: bad arguments");
+    mbk_partial_buffer_layout(capacity, F, offsets_host);
+    return MB_OK;
+}
+
+MB_API int mb_partial_reset(void *stream, int32_t *slot_table, int64_t voxels, void *partial_buffer)
+{
+    MB_REQUIRE(slot_table && partial_buffer && voxels > 0, "mb_partial_reset: bad arguments");
+    return mbk_partial_reset((cudaStream_t)stream, slot_table, voxels, partial_buffer);
+}
+
+MB_API int mb_partial_clear(void *stream, int32_t *slot_table, void *partial_buffer, uint32_t capacity, int F)
+{
+    MB_REQUIRE(slot_table && partial_buffer && F > 0, "mb_partial_clear: bad arguments");
+    return mbk_partial_clear((cudaStream_t)stream, slot_table, partial_buffer, capacity, F);
+}
+
+MB_API int mb_layer_fold_sparse(void *stream, const float *rays, const float *depth, const float *features,
+                                const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw, int F,
+                                const float *bins_x, int nx, const float *bins_y, int ny, const float *bins_z, int nz,
+                                int32_t *slot_table, void *partial_buffer, uint32_t capacity, float interpolation_weight,
+                                float min_ray_depth, float max_ray_depth, void *workspace, size_t workspace_bytes)
+{
+    MB_REQUIRE(slot_table && partial_buffer && capacity > 0, "mb_layer_fold_sparse: null pointer");
+    MB_REQUIRE(capacity < 0x7fffffffu, "mb_layer_fold_sparse: capacity too large");
+    const MbSparseFold sp = { slot_table, partial_buffer, capacity };
+    return layer_update(stream, rays, depth, features, class_ids, pose, T, H, W, fh, fw, F, bins_x, nx, bins_y, ny,
+                        bins_z, nz, nullptr, nullptr, interpolation_weight, min_ray_depth, max_ray_depth, MB_MODE_FAST,
+                        workspace, workspace_bytes, &sp);
+}
+
+MB_API int mb_affine_apply_partial(void *stream, float *map, int F, const void *partial_buffer, uint32_t capacity)
+{
+    MB_REQUIRE(map && partial_buffer && F > 0, "mb_affine_apply_partial: bad arguments");
+    return mbk_affine_apply_partial((cudaStream_t)stream, map, F, partial_buffer, capacity);
+}
+
+// Peer memory: a partial buffer another process / GPU of the box can map (CUDA IPC; over NVLink between GPUs).
+// This is the one place where the library allocates: an IPC handle names a whole cudaMalloc allocation, so the
+// buffer must be its own allocation rather than a slice of the caller's caching allocator.
+MB_API int mb_peer_alloc(size_t bytes, void **ptr_host)
+{
+    MB_REQUIRE(ptr_host && bytes > 0, "mb_peer_alloc: bad arguments");
+    MB_CHECK_CUDA(cudaMalloc(ptr_host, bytes));
+    MB_CHECK_CUDA(cudaMemset(*ptr_host, 0, bytes));
+    return MB_OK;
+}
+
+MB_API int mb_peer_free(void *ptr)
+{
+    if (ptr) MB_CHECK_CUDA(cudaFree(ptr));
+    return MB_OK;
+}
+
+MB_API int mb_peer_export(const void *ptr, void *handle64_host)
+{
+    MB_REQUIRE(ptr && handle64_host, "mb_peer_export: null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    MB_CHECK_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64_host, const_cast<void *>(ptr)));
+    return MB_OK;
+}
+
+MB_API int mb_peer_open(const void *handle64_host, void **ptr_host)
+{
+    MB_REQUIRE(handle64_host && ptr_host, "mb_peer_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, sizeof(h));
+    MB_CHECK_CUDA(cudaIpcOpenMemHandle(ptr_host, h, cudaIpcMemLazyEnablePeerAccess));
+    return MB_OK;
+}
+
+MB_API int mb_peer_close(void *ptr)
+{
+    if (ptr) MB_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+    return MB_OK;
 }
 
 MB_API int mb_affine_apply_rows(void *stream, float *map, int F, const int64_t *voxel_index, const float *a,

@@ -381,22 +381,21 @@ constexpr int IDX_WORDS = 8;                      // words per warp
 constexpr int IDX_TILE = 256 * IDX_WORDS;         // positions per tile
 
 struct IndexOut {
-    uint32_t *smask, *soff, *roff;                // per word of 32 positions: segment-head mask, ranks before the word
-    uint32_t *ucell, *cstart, *cseg, *crun;       // per unique cell (+ sentinel)
+    uint32_t *smask, *soff;                       // per word of 32 positions: segment-head mask, segment rank before the word
+    uint32_t *ucell, *cstart, *cseg;              // per unique cell (+ sentinel)
     uint32_t *seg_start, *seg_frame;              // per segment (+ sentinel)
     uint32_t *bitmap;                             // touched voxels
     int *ctab;                                    // dense cell key -> unique index, or null
     uint32_t *counters;
     uint32_t *state;                              // [tiles][3] look-back words, zeroed
     uint32_t *ticket;                             // zeroed
-    uint32_t run_limit;                           // runs the planned accumulate rounds can hold
 };
 
 __global__ void __launch_bounds__(256)
 k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sval, const uint32_t *__restrict__ n_dev,
              uint32_t tpf, CellGrid g, const IndexOut O)
 {
-    __shared__ uint32_t s_tile, s_wsum[8][3], s_base[3];
+    __shared__ uint32_t s_tile, s_wsum[8][2], s_base[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n = *n_dev;                    // number of items
     if (tid == 0) s_tile = atomicAdd(O.ticket, 1u);
@@ -406,7 +405,7 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
     const uint32_t wbase = tile * IDX_TILE + warp * (32 * IDX_WORDS);
     const uint32_t lt = (1u << lane) - 1u;
 
-    uint32_t key[IDX_WORDS], val[IDX_WORDS], cm[IDX_WORDS], sm[IDX_WORDS], rm[IDX_WORDS];
+    uint32_t key[IDX_WORDS], val[IDX_WORDS], cm[IDX_WORDS], sm[IDX_WORDS];
     uint32_t pk = 0xffffffffu, pv = 0;            // element before the warp's first one
     if (lane == 0 && wbase > 0 && wbase <= n) { pk = skey[wbase - 1]; pv = sval[wbase - 1]; }
 #pragma unroll
@@ -415,7 +414,7 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
         key[r] = i < n ? skey[i] : 0xffffffffu;
         val[r] = i < n ? sval[i] : 0u;
     }
-    uint32_t cw = 0, sw = 0, rw = 0;              // heads in this warp's 8 words
+    uint32_t cw = 0, sw = 0;                      // heads in this warp's 8 words
 #pragma unroll
     for (int r = 0; r < IDX_WORDS; ++r) {
         const uint32_t i = wbase + r * 32 + lane;
@@ -426,19 +425,17 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
         const bool valid = i < n;
         const bool chead = valid && (i == 0 || kprev != key[r]);
         const bool shead = valid && (chead || item_tile(vprev) / tpf != item_tile(val[r]) / tpf);
-        const bool rhead = valid && (chead || (i % TASK_ITEMS) == 0);
         cm[r] = __ballot_sync(FULL, chead);
         sm[r] = __ballot_sync(FULL, shead);
-        rm[r] = __ballot_sync(FULL, rhead);
-        cw += __popc(cm[r]); sw += __popc(sm[r]); rw += __popc(rm[r]);
+        cw += __popc(cm[r]); sw += __popc(sm[r]);
     }
-    if (lane == 0) { s_wsum[warp][0] = cw; s_wsum[warp][1] = sw; s_wsum[warp][2] = rw; }
+    if (lane == 0) { s_wsum[warp][0] = cw; s_wsum[warp][1] = sw; }
     __syncthreads();
-    if (tid < 3) {
+    if (tid < 2) {
         // tile total of counter `tid`, published; then the look-back for the tile's base rank
         uint32_t total = 0;
         for (int w = 0; w < 8; ++w) total += s_wsum[w][tid];
-        uint32_t *mine = O.state + (size_t)tile * 3 + tid;
+        uint32_t *mine = O.state + (size_t)tile * 2 + tid;
         *(volatile uint32_t *)mine = total | (tile == 0 ? IDX_PREFIX : IDX_AGG);
         uint32_t prefix = 0;
         if (tile > 0) {
@@ -447,7 +444,7 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
             while (!done) {
                 uint32_t st[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) st[q] = t - q >= 0 ? *(const volatile uint32_t *)(O.state + (size_t)(t - q) * 3 + tid) : IDX_PREFIX;
+                for (int q = 0; q < 4; ++q) st[q] = t - q >= 0 ? *(const volatile uint32_t *)(O.state + (size_t)(t - q) * 2 + tid) : IDX_PREFIX;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (done) break;
@@ -462,17 +459,17 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
         s_base[tid] = prefix;
     }
     __syncthreads();
-    uint32_t cb = s_base[0], sb = s_base[1], rb = s_base[2];      // ranks before this warp's first word
-    for (int w = 0; w < warp; ++w) { cb += s_wsum[w][0]; sb += s_wsum[w][1]; rb += s_wsum[w][2]; }
+    uint32_t cb = s_base[0], sb = s_base[1];                      // ranks before this warp's first word
+    for (int w = 0; w < warp; ++w) { cb += s_wsum[w][0]; sb += s_wsum[w][1]; }
 
 #pragma unroll
     for (int r = 0; r < IDX_WORDS; ++r) {
         const uint32_t i = wbase + r * 32 + lane;
         const uint32_t w = i >> 5;
-        if (lane == 0 && w <= (n >> 5)) { O.smask[w] = sm[r]; O.soff[w] = sb; O.roff[w] = rb; }
+        if (lane == 0 && w <= (n >> 5)) { O.smask[w] = sm[r]; O.soff[w] = sb; }
         const bool valid = i < n;
         if (valid) {
-            const uint32_t crank = cb + __popc(cm[r] & lt), srank = sb + __popc(sm[r] & lt), rrank = rb + __popc(rm[r] & lt);
+            const uint32_t crank = cb + __popc(cm[r] & lt), srank = sb + __popc(sm[r] & lt);
             if ((sm[r] >> lane) & 1u) {
                 O.seg_start[srank] = i;
                 O.seg_frame[srank] = item_tile(val[r]) / tpf;
@@ -483,7 +480,6 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
                 if (O.ctab != nullptr) O.ctab[k] = (int)crank;
                 O.cstart[crank] = i;
                 O.cseg[crank] = srank;
-                O.crun[crank] = rrank;
                 const int e2 = (int)(k % (uint32_t)g.E2);
                 const uint32_t t = k / (uint32_t)g.E2;
                 const int e1 = (int)(t % (uint32_t)g.E1), e0 = (int)(t / (uint32_t)g.E1);
@@ -501,19 +497,77 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
             const bool is_last = valid && i + 1 == n;
             if (is_last) {
                 const uint32_t le = lane == 31 ? 0xffffffffu : ((2u << lane) - 1u);
-                const uint32_t nc = cb + __popc(cm[r] & le), ns = sb + __popc(sm[r] & le), nr = rb + __popc(rm[r] & le);
+                const uint32_t nc = cb + __popc(cm[r] & le), ns = sb + __popc(sm[r] & le);
                 O.counters[MB_CNT_NVALID] = i + 1;
                 O.counters[MB_CNT_CELLS] = nc;
                 O.counters[MB_CNT_SEGS] = ns;
-                O.counters[MB_CNT_RUNS] = nr;
-                if (nr > O.run_limit) atomicOr(&O.counters[MB_CNT_ERROR], 1u);     // never expected: worst_runs() bounds nr
                 O.cstart[nc] = i + 1;
                 O.cseg[nc] = ns;
-                O.crun[nc] = nr;
                 O.seg_start[ns] = i + 1;
             }
         }
-        cb += __popc(cm[r]); sb += __popc(sm[r]); rb += __popc(rm[r]);
+        cb += __popc(cm[r]); sb += __popc(sm[r]);
+    }
+}
+
+// K3: accumulate runs.  A run is a piece of ONE cell's item list, at most TASK_ITEMS items long, cut at the cell's own
+// multiples of TASK_ITEMS: it is the accumulate kernel's unit of work (one warp, one set of 8 partial rows).  Runs
+// start on cell heads, so the warps that work on neighbouring cells at the same moment are also at the same place
+// in those cells' frame-ordered lists -- the feature rows of one frame that share a DRAM atom across a cell border
+// then meet in L2 instead of being fetched twice.  One thread per cell; run ranks by a decoupled look-back over
+// CTAs of 256 cells.
+__global__ void __launch_bounds__(256)
+k_cell_runs(const uint32_t *__restrict__ cstart, uint32_t *__restrict__ counters, uint32_t *state, uint32_t *ticket,
+            uint32_t *__restrict__ crun, uint32_t *__restrict__ rstart, uint32_t run_limit)
+{
+    __shared__ uint32_t s_tile, s_wsum[8], s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t ncells = counters[MB_CNT_CELLS];
+    // persistent CTAs take tiles of 256 cells from a ticket counter (a tile only ever waits for lower tickets)
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile * 256u >= ncells) {
+            if (tile == 0 && tid == 0) { crun[0] = 0; rstart[0] = 0; counters[MB_CNT_RUNS] = 0; }  // nothing valid at all
+            return;
+        }
+        const uint32_t u = tile * 256u + tid;
+        uint32_t beg = 0, nr = 0;
+        if (u < ncells) {
+            beg = cstart[u];
+            nr = (cstart[u + 1] - beg + TASK_ITEMS - 1) / TASK_ITEMS;
+        }
+        uint32_t inc = nr;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) s_wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) total += s_wsum[w];
+            const uint32_t prefix = lookback_prefix(state, tile, total, lane);
+            if (lane == 0) s_base = prefix;
+        }
+        __syncthreads();
+        uint32_t r0 = s_base + inc - nr;
+        for (int w = 0; w < warp; ++w) r0 += s_wsum[w];
+        if (u < ncells) {
+            crun[u] = r0;
+            for (uint32_t j = 0; j < nr; ++j) rstart[r0 + j] = beg + j * TASK_ITEMS;
+            if (u == ncells - 1) {
+                const uint32_t total = r0 + nr;
+                crun[ncells] = total;
+                rstart[total] = cstart[ncells];
+                counters[MB_CNT_RUNS] = total;
+                if (total > run_limit) atomicOr(&counters[MB_CNT_ERROR], 1u);      // never expected: worst_runs() bounds it
+            }
+        }
     }
 }
 
@@ -797,7 +851,8 @@ struct AccArgs {
     const uint32_t *ikey, *ival;   // sorted item list
     TileGeom tg;
     const uint4 *rec;              // pixel records in tile-grouped order
-    const uint32_t *smask, *soff, *roff;
+    const uint32_t *smask, *soff;
+    const uint32_t *rstart;        // first item of every run (+ sentinel)
     const float *gcoef;         // [8 slots][cap] coefficient per (slot, segment)
     size_t cap;
     uint32_t *counters;            // read; the two work-queue heads are written
@@ -810,6 +865,16 @@ struct AccArgs {
     uint32_t round;             // launch index inside the chunk (which work-queue head to use)
     uint32_t run_base, run_cap; // runs of this round: [run_base, run_base + run_cap)
 };
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem_dst, const void *gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // acc += c * f on VEC floats; pairs go through the packed fp32x2 FMA of sm_100
 __device__ __forceinline__ void ffma2(float &a0, float &a1, float c, float f0, float f1)
@@ -866,6 +931,17 @@ __device__ __forceinline__ void row_load(float (&dst)[VEC], const float *p)
 }
 
 template <int VEC>
+__device__ __forceinline__ void plain_load(float (&dst)[VEC], const float *p)
+{
+    if (VEC == 1) dst[0] = *p;
+    if (VEC == 2) { const float2 v = *(const float2 *)p; dst[0] = v.x; dst[VEC > 1 ? 1 : 0] = v.y; }
+    if (VEC == 4) {
+        const float4 v = *(const float4 *)p;
+        dst[0] = v.x; dst[VEC > 1 ? 1 : 0] = v.y; dst[VEC > 2 ? 2 : 0] = v.z; dst[VEC > 2 ? 3 : 0] = v.w;
+    }
+}
+
+template <int VEC>
 __device__ __forceinline__ void row_store(float *p, const float (&src)[VEC])
 {
     if (VEC == 1) *p = src[0];
@@ -873,29 +949,36 @@ __device__ __forceinline__ void row_store(float *p, const float (&src)[VEC])
     if (VEC == 4) *(float4 *)p = make_float4(src[0], src[VEC > 1 ? 1 : 0], src[VEC > 2 ? 2 : 0], src[VEC > 2 ? 3 : 0]);
 }
 
+// shared memory of k_cell_accumulate (dynamic: ~37 KB per CTA of 8 warps)
+struct AccSmem {
+    static constexpr int NW = ACC_THREADS / 32;
+    float coef[NW][32][8];                          // 8 splat coefficients of every pixel of the batch being walked
+    uint32_t src[NW][32];                           // feature row (or class id) of every pixel of the batch
+    uint32_t pre[NW][TASK_ITEMS + 1], ival[NW][TASK_ITEMS], seg[NW][TASK_ITEMS];
+    uint8_t p2i[NW][TASK_ITEMS * ITEM_MAX];         // item of every pixel of the run
+};
+
 template <int VEC, int IT, bool ONEHOT, int U>
 __global__ void __launch_bounds__(ACC_THREADS, (VEC * IT <= 2 ? 4 : 1))
 k_cell_accumulate(const AccArgs A)
 {
-    constexpr int NW = ACC_THREADS / 32;
-    __shared__ __align__(16) float s_coef[NW][32][8];
-    __shared__ uint32_t s_src[NW][32];
-    __shared__ uint32_t s_pre[NW][TASK_ITEMS + 1], s_ival[NW][TASK_ITEMS], s_seg[NW][TASK_ITEMS];
-    __shared__ uint8_t s_p2i[NW][TASK_ITEMS * ITEM_MAX];          // item of every pixel of the task
+    extern __shared__ __align__(16) unsigned char acc_smem_raw[];
+    AccSmem &SM = *reinterpret_cast<AccSmem *>(acc_smem_raw);
+    auto &s_coef = SM.coef; auto &s_src = SM.src; auto &s_pre = SM.pre; auto &s_ival = SM.ival; auto &s_seg = SM.seg;
+    auto &s_p2i = SM.p2i;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nitems = A.counters[MB_CNT_NVALID], nruns = A.counters[MB_CNT_RUNS];
-    // Work queue: a unit is (task, channel block); warps take the next unit from a counter when they finish one, so
-    // the tasks' very different pixel counts (TASK_ITEMS items of 1..16 pixels each) do not leave SMs idle at the end.  The
-    // launches of a chunk use the two queue heads in turn; each launch clears the one the next launch will use.
+    const uint32_t nruns = A.counters[MB_CNT_RUNS];
+    // Work queue: a unit is (run, channel block); warps take the next unit from a counter when they finish one, so
+    // the runs' very different pixel counts (1 .. TASK_ITEMS items of 1 .. 16 pixels each) do not leave SMs idle at the
+    // end, and the runs in flight at any moment are neighbours in the sorted order.  The launches of a chunk use the
+    // two queue heads in turn; each launch clears the one the next launch will use.
     if (blockIdx.x == 0 && threadIdx.x == 0) A.counters[MB_CNT_TASKQ + ((A.round + 1) & 1)] = 0;
     if (A.run_base >= nruns) return;
     uint32_t *queue = A.counters + MB_CNT_TASKQ + (A.round & 1);
-    const uint32_t run_end = A.run_base + A.run_cap;
     const int F = A.F;
-    const uint32_t ntasks = (nitems + TASK_ITEMS - 1) / TASK_ITEMS;
-    const uint32_t ny = (uint32_t)(F + 32 * VEC * IT - 1) / (uint32_t)(32 * VEC * IT), nunits = ntasks * ny;
+    const uint32_t ny = (uint32_t)(F + 32 * VEC * IT - 1) / (uint32_t)(32 * VEC * IT);
+    const uint32_t nunits = min(nruns - A.run_base, A.run_cap) * ny;
     const uint32_t np = A.fi.np;
-    const uint32_t lemask = lane == 31 ? 0xffffffffu : ((2u << lane) - 1u);
     auto next_unit = [&]() {
         uint32_t u = 0;
         if (lane == 0) u = atomicAdd(queue, 1u);
@@ -903,56 +986,35 @@ k_cell_accumulate(const AccArgs A)
     };
 
     for (uint32_t unit = next_unit(); unit < nunits; unit = next_unit()) {
-        const uint32_t task = unit / ny;
-        const int ch0 = (int)(unit - task * ny) * (32 * VEC * IT) + lane * VEC;     // first channel of this lane
-        const uint32_t base = task * TASK_ITEMS, end = min(base + (uint32_t)TASK_ITEMS, nitems);
-        uint32_t e = A.roff[base >> 5];                                  // rank of the task's first run
-        {
-            const uint32_t e_after = end == nitems ? nruns : A.roff[end >> 5];
-            if (e_after <= A.run_base || e >= run_end) continue;         // no run of this round in the task
-        }
-        // ---- the task's items: pixel prefix, run heads, segment ranks (TASK_WORDS items per lane) --------
-        uint32_t ihead[TASK_WORDS];                                       // run-head masks of items 0-31, 32-63, ...
-        uint32_t npixels;
-        {
-            uint32_t key[TASK_WORDS], len[TASK_WORDS];
-            __syncwarp();
-#pragma unroll
-            for (int h = 0; h < TASK_WORDS; ++h) {
-                const uint32_t i = base + 32 * h + lane;
-                key[h] = 0xfffffffeu;
-                len[h] = 0;
-                if (i < end) {
-                    const uint32_t v = A.ival[i];
-                    key[h] = A.ikey[i];
-                    len[h] = item_len(v);
-                    const uint32_t w = i >> 5;
-                    s_ival[warp][32 * h + lane] = v;
-                    s_seg[warp][32 * h + lane] = A.soff[w] + __popc(A.smask[w] & lemask) - 1u;
-                }
+        const uint32_t rr = unit / ny;                                   // run of this round
+        const int ch0 = (int)(unit - rr * ny) * (32 * VEC * IT) + lane * VEC;       // first channel of this lane
+        const uint32_t base = __ldg(A.rstart + A.run_base + rr), end = __ldg(A.rstart + A.run_base + rr + 1);
+        // ---- the run's items: pixel prefix, segment ranks (32 items per round of lanes) -----------------------
+        uint32_t npixels = 0;
+        __syncwarp();
+        for (uint32_t h0 = 0; base + h0 < end; h0 += 32) {
+            const uint32_t i = base + h0 + lane;
+            uint32_t len = 0;
+            if (i < end) {
+                const uint32_t v = A.ival[i];
+                len = item_len(v);
+                const uint32_t w = i >> 5, bit = i & 31u;
+                const uint32_t le = bit == 31u ? 0xffffffffu : ((2u << bit) - 1u);
+                s_ival[warp][h0 + lane] = v;
+                s_seg[warp][h0 + lane] = A.soff[w] + __popc(A.smask[w] & le) - 1u;
             }
-            uint32_t carry = 0, lastkey = 0xffffffffu;                    // != any key: item 0 is a run head
+            uint32_t inc = len;
 #pragma unroll
-            for (int h = 0; h < TASK_WORDS; ++h) {
-                uint32_t inc = len[h];
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(FULL, inc, d);
-                    if (lane >= d) inc += o;
-                }
-                const uint32_t pre = carry + inc - len[h];
-                s_pre[warp][32 * h + lane] = pre;
-                for (uint32_t o = 0; o < len[h]; ++o) s_p2i[warp][pre + o] = (uint8_t)(32 * h + lane);
-                carry += __shfl_sync(FULL, inc, 31);
-                uint32_t prevkey = __shfl_up_sync(FULL, key[h], 1);
-                if (lane == 0) prevkey = lastkey;
-                lastkey = __shfl_sync(FULL, key[h], 31);
-                ihead[h] = __ballot_sync(FULL, len[h] != 0 && key[h] != prevkey);
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(FULL, inc, d);
+                if (lane >= d) inc += o;
             }
-            npixels = carry;
-            if (lane == 0) s_pre[warp][TASK_ITEMS] = carry;
-            __syncwarp();
+            const uint32_t pre = npixels + inc - len;
+            if (i < end) s_pre[warp][h0 + lane] = pre;
+            for (uint32_t o = 0; o < len; ++o) s_p2i[warp][pre + o] = (uint8_t)(h0 + lane);
+            npixels += __shfl_sync(FULL, inc, 31);
         }
+        __syncwarp();
         float acc[8][IT][VEC];
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -961,44 +1023,21 @@ k_cell_accumulate(const AccArgs A)
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) acc[k][it][j] = 0.f;
 
-        auto flush = [&]() {
-            if (e >= A.run_base && e < run_end) {
-                float *prow = A.P + (size_t)(e - A.run_base) * 8 * F;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-#pragma unroll
-                    for (int it = 0; it < IT; ++it) {
-                        const int ch = ch0 + it * 32 * VEC;
-                        if (ch < F) row_store<VEC>(prow + (size_t)k * F + ch, acc[k][it]);
-                    }
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-#pragma unroll
-                for (int it = 0; it < IT; ++it)
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) acc[k][it][j] = 0.f;
-            ++e;
-        };
-
         for (uint32_t b0 = 0; b0 < npixels; b0 += 32) {
             // ---- lanes = pixels: coefficients of the batch ------------------------------------------------
-            const uint32_t qp = b0 + lane;                                // pixel of the task
-            const bool ok = qp < npixels;
-            bool phead = false;
+            const uint32_t qp = b0 + lane;                                // pixel of the run
             {
                 float c[8];
                 uint32_t src = 0;
-                if (ok) {
+                if (qp < npixels) {
                     const int lo = s_p2i[warp][qp];
                     const uint32_t v = s_ival[warp][lo], off = qp - s_pre[warp][lo];
-                    phead = off == 0 && ((ihead[lo >> 5] >> (lo & 31)) & 1u);
                     const uint32_t tile = item_tile(v);
                     const uint4 r = __ldg(A.rec + (size_t)tile * TILE_PIX + item_pos(v) + off);
-                    const uint32_t s = s_seg[warp][lo];
+                    const uint32_t sg = s_seg[warp][lo];
                     float gk[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) gk[k] = __ldg(A.gcoef + (size_t)k * A.cap + s);
+                    for (int k = 0; k < 8; ++k) gk[k] = __ldg(A.gcoef + (size_t)k * A.cap + sg);
                     splat_weights(r, c);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) c[k] = c[k] * c[k] * gk[k];
@@ -1019,79 +1058,60 @@ k_cell_accumulate(const AccArgs A)
 #pragma unroll
                     for (int k = 0; k < 8; ++k) c[k] = 0.f;
                 }
+                {
+                    const uint32_t src0 = __shfl_sync(FULL, src, 0);      // lane 0's pixel always exists
+                    if (qp >= npixels) src = ONEHOT ? 0xffffffffu : src0;
+                }
                 __syncwarp();
                 *(float4 *)&s_coef[warp][lane][0] = make_float4(c[0], c[1], c[2], c[3]);
                 *(float4 *)&s_coef[warp][lane][4] = make_float4(c[4], c[5], c[6], c[7]);
                 s_src[warp][lane] = src;
                 __syncwarp();
             }
-            const uint32_t hm = __ballot_sync(FULL, phead);
-
-            // ---- lanes = channels: walk the batch ---------------------------------------------------------
+            // ---- lanes = channels: walk the batch, U rows in flight ---------------------------------------
+            // (always whole groups of U: the pixels past the end of the run carry zero coefficients and the row of
+            // the batch's first pixel, so a short last batch costs a few spare loads instead of a one-row-at-a-time tail)
             const int nb = (int)min(32u, npixels - b0);
-            int jj = 0;
-            while (jj < nb) {
-                if (((hm >> jj) & 1u) && !(b0 == 0 && jj == 0)) flush();
-                const uint32_t rest = jj < 31 ? (hm >> (jj + 1)) : 0u;
-                int jend = rest ? jj + __ffs(rest) : nb;            // next head (exclusive end of this stretch)
-                if (jend > nb) jend = nb;
-                for (; jj + U <= jend; jj += U) {
-                    float f[U][IT][VEC];
+            for (int jj = 0; jj < nb; jj += U) {
+                float f[U][IT][VEC];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const uint32_t src = s_src[warp][jj + u];
-#pragma unroll
-                        for (int it = 0; it < IT; ++it) {
-                            const int ch = ch0 + it * 32 * VEC;
-                            if (ONEHOT) {
-#pragma unroll
-                                for (int j = 0; j < VEC; ++j) f[u][it][j] = (uint32_t)(ch + j) == src ? 1.0f : 0.0f;
-                            } else if (ch < F) {
-                                feat_load<VEC>(f[u][it], A.features + (size_t)src * F + ch);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < VEC; ++j) f[u][it][j] = 0.f;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const float4 c0 = *(const float4 *)&s_coef[warp][jj + u][0];
-                        const float4 c1 = *(const float4 *)&s_coef[warp][jj + u][4];
-                        const float c[8] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w };
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-#pragma unroll
-                            for (int it = 0; it < IT; ++it) vec_fma<VEC>(acc[k][it], c[k], f[u][it]);
-                    }
-                }
-                for (; jj < jend; ++jj) {
-                    float f[IT][VEC];
-                    const uint32_t src = s_src[warp][jj];
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t src = s_src[warp][jj + u];
 #pragma unroll
                     for (int it = 0; it < IT; ++it) {
                         const int ch = ch0 + it * 32 * VEC;
                         if (ONEHOT) {
 #pragma unroll
-                            for (int j = 0; j < VEC; ++j) f[it][j] = (uint32_t)(ch + j) == src ? 1.0f : 0.0f;
+                            for (int j = 0; j < VEC; ++j) f[u][it][j] = (uint32_t)(ch + j) == src ? 1.0f : 0.0f;
                         } else if (ch < F) {
-                            feat_load<VEC>(f[it], A.features + (size_t)src * F + ch);
+                            feat_load<VEC>(f[u][it], A.features + (size_t)src * F + ch);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < VEC; ++j) f[it][j] = 0.f;
+                            for (int j = 0; j < VEC; ++j) f[u][it][j] = 0.f;
                         }
                     }
-                    const float4 c0 = *(const float4 *)&s_coef[warp][jj][0];
-                    const float4 c1 = *(const float4 *)&s_coef[warp][jj][4];
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float4 c0 = *(const float4 *)&s_coef[warp][jj + u][0];
+                    const float4 c1 = *(const float4 *)&s_coef[warp][jj + u][4];
                     const float c[8] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w };
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
 #pragma unroll
-                        for (int it = 0; it < IT; ++it) vec_fma<VEC>(acc[k][it], c[k], f[it]);
+                        for (int it = 0; it < IT; ++it) vec_fma<VEC>(acc[k][it], c[k], f[u][it]);
                 }
             }
         }
-        flush();
+        // ---- the run's 8 partial rows ----------------------------------------------------------------------
+        float *prow = A.P + (size_t)rr * 8 * F;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int it = 0; it < IT; ++it) {
+                const int ch = ch0 + it * 32 * VEC;
+                if (ch < F) row_store<VEC>(prow + (size_t)k * F + ch, acc[k][it]);
+            }
     }
 }
 
@@ -1107,6 +1127,10 @@ struct ApplyArgs {
     int F;
     float *map, *affine_a;
     uint32_t run_base, run_cap;
+    // fold into a sparse partial instead of the map (frame-sharded scenes): row slot of every touched voxel
+    // (top bit: the row is new in this chunk; 0xffffffff: no room, skipped), rows and their coefficients
+    const uint32_t *vslot;
+    float *part_a, *part_b;
 };
 
 template <int VEC, int IT>
@@ -1130,13 +1154,22 @@ k_voxel_apply(const ApplyArgs A)
         }
         const float a = A.run_base == 0 ? A.vA[j] : 1.0f;
         float *grow = A.map + (size_t)v * F;
+        bool fresh = false;                            // sparse partial: the row starts from the identity (A = 1, B = 0)
+        uint32_t slot = 0;
+        if (A.vslot != nullptr) {
+            slot = A.vslot[j];
+            if (slot == 0xffffffffu) continue;
+            fresh = (slot >> 31) != 0u && A.run_base == 0;
+            slot &= 0x7fffffffu;
+            grow = A.part_b + (size_t)slot * F;
+        }
         float old[IT][VEC];
 #pragma unroll
         for (int it = 0; it < IT; ++it) {
             const int ch = ch0 + it * 32 * VEC;
 #pragma unroll
             for (int q = 0; q < VEC; ++q) old[it][q] = 0.f;
-            if (ch < F) {
+            if (ch < F && !fresh) {
                 if (VEC == 1) old[it][0] = grow[ch];
                 if (VEC == 2) { const float2 o = *(const float2 *)(grow + ch); old[it][0] = o.x; old[it][VEC > 1 ? 1 : 0] = o.y; }
                 if (VEC == 4) { const float4 o = *(const float4 *)(grow + ch); old[it][0] = o.x; old[it][VEC > 1 ? 1 : 0] = o.y; old[it][VEC > 2 ? 2 : 0] = o.z; old[it][VEC > 2 ? 3 : 0] = o.w; }
@@ -1235,6 +1268,8 @@ k_voxel_apply(const ApplyArgs A)
             const float prev = A.affine_a[v];
             A.affine_a[v] = (prev == 2.0f ? 1.0f : prev) * a;
         }
+        if (A.vslot != nullptr && A.run_base == 0 && blockIdx.y == 0 && lane == 0)
+            A.part_a[slot] = fresh ? a : A.part_a[slot] * a;
     }
 }
 
@@ -1254,13 +1289,120 @@ k_affine_apply_rows(float *__restrict__ map, int F, const int64_t *__restrict__ 
     }
 }
 
+// ---- sparse partials of frame-sharded scenes ---------------------------------------------------------
+// A partial is the action of a contiguous run of frames on ANY map: M[v] <- a[v] * M[v] + b[v] for the voxels the
+// frames touched.  It lives in one buffer {count | index[cap] | a[cap] | b[cap][F]} (offsets: partial_layout) so that a
+// peer GPU can read it through ONE mapped pointer; slot_table[V] (-1 = no row) finds a voxel's row while chunks are
+// being folded in.
+struct PartialView {
+    uint32_t *count;
+    int64_t *index;
+    float *a, *b;
+};
+
+__host__ __device__ inline void partial_layout(uint32_t capacity, int F, size_t off[4], size_t *total)
+{
+    off[0] = 0;                                                        // count (+ padding)
+    off[1] = 256;                                                      // index
+    off[2] = off[1] + (((size_t)capacity * sizeof(int64_t) + 255) / 256) * 256;     // a
+    off[3] = off[2] + (((size_t)capacity * sizeof(float) + 255) / 256) * 256;       // b
+    if (total) *total = off[3] + (((size_t)capacity * F * sizeof(float) + 255) / 256) * 256;
+}
+
+__host__ __device__ inline PartialView partial_view(void *buffer, uint32_t capacity, int F)
+{
+    size_t off[4];
+    partial_layout(capacity, F, off, nullptr);
+    char *p = (char *)buffer;
+    PartialView v;
+    v.count = (uint32_t *)(p + off[0]);
+    v.index = (int64_t *)(p + off[1]);
+    v.a = (float *)(p + off[2]);
+    v.b = (float *)(p + off[3]);
+    return v;
+}
+
+// one thread per touched voxel of the chunk: find or create its row
+__global__ void __launch_bounds__(256)
+k_partial_slots(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__ counters, int32_t *__restrict__ slot_table,
+                PartialView P, uint32_t capacity, uint32_t *__restrict__ vslot, uint32_t *__restrict__ errors)
+{
+    const uint32_t nvox = counters[MB_CNT_VOX];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nvox; j += gridDim.x * blockDim.x) {
+        const uint32_t v = vlist[j];
+        int32_t s = slot_table[v];
+        uint32_t out;
+        if (s >= 0) {
+            out = (uint32_t)s;
+        } else {
+            const uint32_t n = atomicAdd(P.count, 1u);
+            if (n < capacity) {
+                slot_table[v] = (int32_t)n;
+                P.index[n] = (int64_t)v;
+                out = n | 0x80000000u;
+            } else {
+                atomicOr(errors, 4u);                                   // partial full: the row is dropped, check() raises
+                out = 0xffffffffu;
+            }
+        }
+        vslot[j] = out;
+    }
+}
+
+// slot_table[index[i]] = -1 for the rows in use (the sparse way back to an empty partial); count is zeroed by the caller
+__global__ void __launch_bounds__(256)
+k_partial_clear(int32_t *__restrict__ slot_table, PartialView P, uint32_t capacity)
+{
+    const uint32_t n = min(*P.count, capacity);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        slot_table[P.index[i]] = -1;
+}
+
+// map[index[i]] = a[i] * map[index[i]] + b[i] for the rows of a partial; the row count is read on the device.
+// `P` may point into a PEER GPU's memory (mapped over NVLink): the rows then cross the link inside this kernel,
+// overlapped row by row with their application -- there is no separate exchange step.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_affine_apply_partial(float *__restrict__ map, int F, PartialView P, uint32_t capacity)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = min(*(const volatile uint32_t *)P.count, capacity);
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    // two rows per warp and iteration: both rows' loads are in flight before either is used
+    for (uint32_t i = 2 * wid; i < n; i += 2 * nw) {
+        const bool two = i + 1 < n;
+        const int64_t v0 = P.index[i], v1 = two ? P.index[i + 1] : 0;
+        const float a0 = P.a[i], a1 = two ? P.a[i + 1] : 0.f;
+        float *r0 = map + (size_t)v0 * F, *r1 = map + (size_t)v1 * F;
+        const float *b0 = P.b + (size_t)i * F, *b1 = b0 + F;
+        for (int ch = lane * VEC; ch < F; ch += 32 * VEC) {
+            float x0[VEC], x1[VEC], m0[VEC], m1[VEC];
+            plain_load<VEC>(x0, b0 + ch);                   // (coherent loads: the rows may have been written by a peer)
+            if (two) plain_load<VEC>(x1, b1 + ch);
+            plain_load<VEC>(m0, r0 + ch);
+            if (two) plain_load<VEC>(m1, r1 + ch);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) m0[q] = fmaf(a0, m0[q], x0[q]);
+            row_store<VEC>(r0 + ch, m0);
+            if (two) {
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) m1[q] = fmaf(a1, m1[q], x1[q]);
+                row_store<VEC>(r1 + ch, m1);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 struct CellBuffers {
     uint32_t *counters;
     uint4 *rec, *pix;
     uint32_t *keys_a, *keys_b, *pids_a, *pids_b;
     uint32_t *tcount, *toff;
-    uint32_t *smask, *soff, *roff;
+    uint32_t *smask, *soff;
+    uint32_t *rstart;                     // first item of every accumulate run (+ sentinel)
+    uint32_t *run_state;                  // look-back words of K3
+    uint32_t *scan_state;                 // look-back words of the tile-count scan
     uint32_t *idx_state, *vox_state;      // look-back words of K2 and K4; the bitmap follows: zeroed by one memset
     size_t state_bytes;
     uint32_t *ucell, *cstart, *cseg, *crun, *seg_start, *seg_frame;
@@ -1269,6 +1411,7 @@ struct CellBuffers {
     uint32_t *bitmap, *vlist;
     float *vA;
     uint2 *vseg, *vrun;
+    uint32_t *vslot;            // sparse-partial row of every touched voxel (fold into a partial)
     int *ctab;                  // dense cell key -> unique cell index (or null: binary search)
     char *scan_ws, *sort_ws;
     size_t scan_bytes, sort_bytes;
@@ -1292,18 +1435,23 @@ size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const Cel
     b.keys_a = a.take<uint32_t>(n); b.keys_b = a.take<uint32_t>(n);
     b.pids_a = a.take<uint32_t>(n); b.pids_b = a.take<uint32_t>(n);
     b.tcount = a.take<uint32_t>(ntiles + 1); b.toff = a.take<uint32_t>(ntiles + 1);
-    b.smask = a.take<uint32_t>(words); b.soff = a.take<uint32_t>(words); b.roff = a.take<uint32_t>(words);
+    b.smask = a.take<uint32_t>(words); b.soff = a.take<uint32_t>(words);
     {
         // (sizes are multiples of 4 words: the bitmap behind them is read in 16-byte pieces)
-        const size_t iwords = ((((size_t)n + IDX_TILE - 1) / IDX_TILE * 3 + 8) + 3) & ~(size_t)3;
+        const size_t iwords = ((((size_t)n + IDX_TILE - 1) / IDX_TILE * 2 + 8) + 3) & ~(size_t)3;
+        const size_t rwords = (((ncap + 255) / 256 + 8) + 3) & ~(size_t)3;
         const size_t vxwords = (((vwords + VOX_TILE - 1) / VOX_TILE + 8) + 3) & ~(size_t)3;
-        b.idx_state = a.take<uint32_t>(iwords + vxwords + vwords + VOX_WORDS);
-        b.vox_state = b.idx_state + iwords;
+        const size_t swords = (mb_scan_state_words((uint32_t)ntiles + 1) + 3) & ~(size_t)3;
+        b.idx_state = a.take<uint32_t>(iwords + rwords + swords + vxwords + vwords + VOX_WORDS);
+        b.run_state = b.idx_state + iwords;
+        b.scan_state = b.run_state + rwords;
+        b.vox_state = b.scan_state + swords;
         b.bitmap = b.vox_state + vxwords;             // touched-voxel bitmap
-        b.state_bytes = (iwords + vxwords + vwords + VOX_WORDS) * sizeof(uint32_t);
+        b.state_bytes = (iwords + rwords + swords + vxwords + vwords + VOX_WORDS) * sizeof(uint32_t);
     }
     b.ucell = a.take<uint32_t>(ncap + 1); b.cstart = a.take<uint32_t>(ncap + 1);
     b.cseg = a.take<uint32_t>(ncap + 1); b.crun = a.take<uint32_t>(ncap + 1);
+    b.rstart = a.take<uint32_t>(ncap + ((size_t)n + TASK_ITEMS - 1) / TASK_ITEMS + 2);     // worst_runs() + sentinel
     b.seg_start = a.take<uint32_t>((size_t)n + 1); b.seg_frame = a.take<uint32_t>((size_t)n + 1);
     b.segws = a.take<float2>((size_t)n * 8);
     b.gcoef = a.take<float>((size_t)n * 8);
@@ -1311,6 +1459,7 @@ size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const Cel
     b.vA = a.take<float>(vcap + 1);
     b.vseg = a.take<uint2>((vcap + 1) * 8);
     b.vrun = a.take<uint2>((vcap + 1) * 8);
+    b.vslot = a.take<uint32_t>(vcap + 1);
     {
         // dense lookup table over the extended grid when it is not out of proportion to the batch
         // (it is re-initialised by every call: 4 bytes per cell of the extended grid; a one-frame call on a large
@@ -1354,9 +1503,10 @@ int launch_accumulate(cudaStream_t stream, const AccArgs &A)
 {
     auto kern = k_cell_accumulate<VEC, IT, ONEHOT, U>;
     int per_sm = 1;
-    MB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ACC_THREADS, 0));
+    MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccSmem)));
+    MB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ACC_THREADS, sizeof(AccSmem)));
     if (per_sm < 1) per_sm = 1;
-    kern<<<MB_NUM_SMS * per_sm, ACC_THREADS, 0, stream>>>(A);      // persistent: the kernel walks (task, channel block) units
+    kern<<<MB_NUM_SMS * per_sm, ACC_THREADS, sizeof(AccSmem), stream>>>(A);      // persistent: the kernel walks (run, channel block) units
     MB_LAUNCHED();
     return MB_OK;
 }
@@ -1436,6 +1586,40 @@ int mbk_affine_apply_rows(cudaStream_t stream, float *map, int F, const int64_t 
     return MB_OK;
 }
 
+size_t mbk_partial_buffer_layout(uint32_t capacity, int F, size_t *offsets)
+{
+    size_t off[4], total;
+    partial_layout(capacity, F, off, &total);
+    if (offsets) for (int i = 0; i < 4; ++i) offsets[i] = off[i];
+    return total;
+}
+
+int mbk_partial_reset(cudaStream_t stream, int32_t *slot_table, int64_t voxels, void *buffer)
+{
+    MB_CHECK_CUDA(cudaMemsetAsync(slot_table, 0xff, (size_t)voxels * sizeof(int32_t), stream));
+    MB_CHECK_CUDA(cudaMemsetAsync(buffer, 0, 256, stream));
+    return MB_OK;
+}
+
+int mbk_partial_clear(cudaStream_t stream, int32_t *slot_table, void *buffer, uint32_t capacity, int F)
+{
+    k_partial_clear<<<MB_NUM_SMS * 4, 256, 0, stream>>>(slot_table, partial_view(buffer, capacity, F), capacity);
+    MB_LAUNCHED();
+    MB_CHECK_CUDA(cudaMemsetAsync(buffer, 0, 256, stream));
+    return MB_OK;
+}
+
+int mbk_affine_apply_partial(cudaStream_t stream, float *map, int F, const void *buffer, uint32_t capacity)
+{
+    const PartialView pv = partial_view(const_cast<void *>(buffer), capacity, F);
+    const uintptr_t al = (uintptr_t)map | (uintptr_t)pv.b;
+    if (F % 4 == 0 && al % 16 == 0) k_affine_apply_partial<4><<<MB_NUM_SMS * 8, 256, 0, stream>>>(map, F, pv, capacity);
+    else if (F % 2 == 0 && al % 8 == 0) k_affine_apply_partial<2><<<MB_NUM_SMS * 8, 256, 0, stream>>>(map, F, pv, capacity);
+    else k_affine_apply_partial<1><<<MB_NUM_SMS * 8, 256, 0, stream>>>(map, F, pv, capacity);
+    MB_LAUNCHED();
+    return MB_OK;
+}
+
 // bytes per P run (8 rows of F floats)
 static size_t run_bytes(int F) { return (size_t)8 * F * sizeof(float); }
 
@@ -1507,7 +1691,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
                      const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw, int F,
                      const float *bins_x, int nx, const float *bins_y, int ny, const float *bins_z, int nz,
                      float *map, float *affine_a, float alpha, float min_d, float max_d, void *workspace,
-                     size_t workspace_bytes)
+                     size_t workspace_bytes, const MbSparseFold *sparse)
 {
     const uint32_t npix = (uint32_t)H * (uint32_t)W;
     const TileGeom tg = make_tiles(H, W);
@@ -1522,7 +1706,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     const size_t V = (size_t)g.S0 * g.S1 * g.S2;
     const uint32_t vwords = (uint32_t)(V / 32 + 1);
     int vec, it;
-    pick_vec(features, map, b.P, F, vec, it);
+    pick_vec(features, sparse ? partial_view(sparse->buffer, sparse->capacity, F).b : map, b.P, F, vec, it);
     const size_t run_cap_sz = b.P_floats / ((size_t)8 * F);
     const size_t wruns = worst_runs(n, g);
     MB_REQUIRE(run_cap_sz >= (wruns < 512 ? wruns : 512), "batch workspace too small for the run buffer");
@@ -1533,6 +1717,8 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     // K1: voxelise + group inside tiles, compact the items; then sort the items by cell
     int rc;
     if ((rc = stage_mark(stream, 0))) return rc;
+    // every look-back word of the call and the touched-voxel bitmap: one memset up front
+    MB_CHECK_CUDA(cudaMemsetAsync(b.idx_state, 0, b.state_bytes, stream));
     uint32_t *tkey = b.keys_b, *tval = b.pids_b;          // tile-local item lists live in the sort's second buffers
     dim3 vgrid((npix + 256 * VOX_PPT - 1) / (256 * VOX_PPT), (unsigned)T);
     k_cell_voxelise<<<vgrid, 256, 0, stream>>>(rays, depth, pose, npix, bins_x, nx, bins_y, ny, bins_z, nz, g, min_d, max_d,
@@ -1540,7 +1726,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     MB_LAUNCHED();
     k_tile_group<<<(ntiles + 7) / 8, 256, 0, stream>>>(b.pix, tg, ntiles, b.rec, tkey, tval, b.tcount);
     MB_LAUNCHED();
-    if ((rc = mb_exclusive_scan_u32(stream, b.tcount, b.toff, ntiles, b.scan_ws, b.scan_bytes))) return rc;
+    if ((rc = mb_exclusive_scan_small(stream, b.tcount, b.toff, ntiles, b.scan_state))) return rc;
     k_tile_compact<<<(ntiles + 7) / 8, 256, 0, stream>>>(tkey, tval, b.tcount, b.toff, ntiles, b.keys_a, b.pids_a,
                                                          b.counters);
     MB_LAUNCHED();
@@ -1555,17 +1741,22 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
 
     // K2: index sweep over the sorted items
     if ((rc = stage_mark(stream, 2))) return rc;
-    MB_CHECK_CUDA(cudaMemsetAsync(b.idx_state, 0, b.state_bytes, stream));
     if (b.ctab) MB_CHECK_CUDA(cudaMemsetAsync(b.ctab, 0xff, (size_t)g.invalid * sizeof(int), stream));
     {
         const uint32_t itiles = (n + IDX_TILE - 1) / IDX_TILE;
         IndexOut O;
-        O.smask = b.smask; O.soff = b.soff; O.roff = b.roff;
-        O.ucell = b.ucell; O.cstart = b.cstart; O.cseg = b.cseg; O.crun = b.crun;
+        O.smask = b.smask; O.soff = b.soff;
+        O.ucell = b.ucell; O.cstart = b.cstart; O.cseg = b.cseg;
         O.seg_start = b.seg_start; O.seg_frame = b.seg_frame; O.bitmap = b.bitmap; O.ctab = b.ctab;
         O.counters = b.counters; O.state = b.idx_state + 4; O.ticket = b.idx_state;
-        O.run_limit = (uint32_t)((uint64_t)rounds * run_cap < 0xffffffffull ? (uint64_t)rounds * run_cap : 0xffffffffull);
         k_cell_index<<<itiles, 256, 0, stream>>>(ikey, ival, n_items, (uint32_t)tg.tpf, g, O);
+        MB_LAUNCHED();
+    }
+    // K3: accumulate runs (cell-aligned pieces of <= TASK_ITEMS items)
+    {
+        const uint64_t lim = (uint64_t)rounds * run_cap;
+        k_cell_runs<<<MB_NUM_SMS * 4, 256, 0, stream>>>(b.cstart, b.counters, b.run_state + 4, b.run_state, b.crun, b.rstart,
+                                                        (uint32_t)(lim < 0xffffffffull ? lim : 0xffffffffull));
         MB_LAUNCHED();
     }
     // K4
@@ -1597,7 +1788,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     }
     // K7, K8 (one round unless the runs outgrow the P buffer)
     AccArgs A;
-    A.ikey = ikey; A.ival = ival; A.tg = tg; A.rec = b.rec; A.smask = b.smask; A.soff = b.soff; A.roff = b.roff;
+    A.ikey = ikey; A.ival = ival; A.tg = tg; A.rec = b.rec; A.smask = b.smask; A.soff = b.soff; A.rstart = b.rstart;
     A.gcoef = b.gcoef; A.cap = (size_t)n; A.counters = b.counters;
     A.fi = MbFeatIndex{ npix, (uint32_t)W, (uint32_t)(H / fh), (uint32_t)(W / fw), (uint32_t)fw };
     A.fhw = (uint32_t)fh * (uint32_t)fw;
@@ -1605,6 +1796,15 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     ApplyArgs Y;
     Y.vlist = b.vlist; Y.vrun = b.vrun; Y.vA = b.vA; Y.P = b.P; Y.counters = b.counters;
     Y.g = g; Y.F = F; Y.map = map; Y.affine_a = affine_a; Y.run_cap = run_cap;
+    Y.vslot = nullptr; Y.part_a = Y.part_b = nullptr;
+    if (sparse != nullptr) {
+        // fold into a sparse partial: rows are found / created per touched voxel, then the apply kernel writes them
+        const PartialView pv = partial_view(sparse->buffer, sparse->capacity, F);
+        k_partial_slots<<<MB_NUM_SMS * 4, 256, 0, stream>>>(b.vlist, b.counters, sparse->slot_table, pv, sparse->capacity,
+                                                            b.vslot, b.counters + MB_CNT_ERROR);
+        MB_LAUNCHED();
+        Y.vslot = b.vslot; Y.part_a = pv.a; Y.part_b = pv.b; Y.map = pv.b;
+    }
     for (int r = 0; r < rounds; ++r) {
         A.run_base = Y.run_base = (uint32_t)r * run_cap;
         A.round = (uint32_t)r;

@@ -112,6 +112,10 @@ int mb_sort_pairs(cudaStream_t stream, uint32_t *keys_a, uint32_t *vals_a, uint3
                   uint32_t *vals_b, uint32_t n, const uint32_t *n_dev, int key_bits, bool vals_a_is_iota,
                   void *workspace, size_t workspace_bytes, uint32_t **keys_out, uint32_t **vals_out);
 
+// one-launch exclusive scan of n <= 2^20 values whose sum stays below 2^30 (in place allowed); zeroed_state:
+// mb_scan_state_words(n) words the caller has zeroed
+size_t mb_scan_state_words(uint32_t n);
+int mb_exclusive_scan_small(cudaStream_t stream, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *zeroed_state);
 // exclusive prefix sum of n u32 values (in place allowed)
 size_t mb_scan_workspace_bytes(uint32_t n);
 int mb_exclusive_scan_u32(cudaStream_t stream, const uint32_t *in, uint32_t *out, uint32_t n,

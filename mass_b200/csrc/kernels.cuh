@@ -56,11 +56,21 @@ int mbk_batch_frames_that_fit(int H, int W, int nx, int ny, int nz, int F, size_
 int mbk_batch_max_chunk_frames(int H, int W);
 size_t mbk_batch_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int F);
 size_t mbk_batch_min_workspace_bytes(int H, int W, int nx, int ny, int nz, int T, int F);
+// fold target of frame-sharded scenes: a sparse partial instead of the map (cells.cu, "sparse partials")
+struct MbSparseFold {
+    int32_t *slot_table;        // [voxels] row of a voxel, -1 = none yet
+    void *buffer;               // {count | index | a | b}, mbk_partial_buffer_layout
+    uint32_t capacity;          // rows the buffer holds
+};
 int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth, const float *features,
                      const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw, int F,
                      const float *bins_x, int nx, const float *bins_y, int ny, const float *bins_z, int nz,
                      float *map, float *affine_a, float alpha, float min_d, float max_d, void *workspace,
-                     size_t workspace_bytes);
+                     size_t workspace_bytes, const MbSparseFold *sparse = nullptr);
+size_t mbk_partial_buffer_layout(uint32_t capacity, int F, size_t *offsets);
+int mbk_partial_reset(cudaStream_t stream, int32_t *slot_table, int64_t voxels, void *buffer);
+int mbk_partial_clear(cudaStream_t stream, int32_t *slot_table, void *buffer, uint32_t capacity, int F);
+int mbk_affine_apply_partial(cudaStream_t stream, float *map, int F, const void *buffer, uint32_t capacity);
 
 int mbk_affine_apply_rows(cudaStream_t stream, float *map, int F, const int64_t *idx, const float *a, const float *b,
                           int64_t n);

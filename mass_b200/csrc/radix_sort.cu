@@ -100,6 +100,74 @@ k_scan_apply(const uint32_t *in, uint32_t *out, uint32_t n, const uint32_t *__re
     }
 }
 
+// Small inputs (digit tables, per-tile item counts: <= 2^20 values) in ONE launch: tiles of 2048 values, the
+// prefix of a tile by a decoupled look-back over the tiles before it (one zeroed word per tile: value | flag in the
+// top two bits).  At most 512 CTAs, all resident at once, so a tile never waits for a CTA that has not started.
+constexpr uint32_t SCAN1_MAX = 1u << 20;
+constexpr uint32_t LB_AGG = 1u << 30, LB_PREFIX = 2u << 30, LB_MASK = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_lookback(const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *state)
+{
+    __shared__ uint32_t s_prefix;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t base = tile * SCAN_TILE + tid * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    if (base + SCAN_ITEMS <= n && ((uintptr_t)in % 16 == 0)) {
+        const uint4 a = *(const uint4 *)(in + base), b = *(const uint4 *)(in + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = base + i < n ? in[base + i] : 0u;
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) s += v[i];
+    uint32_t total;
+    const uint32_t excl = block_exclusive_scan(s, &total);
+    if (tid < 32) {
+        // warp 0: publish the tile total, then sum the totals of the tiles before (32 per step)
+        uint32_t *mine = state + tile;
+        if (lane == 0) *(volatile uint32_t *)mine = total | (tile == 0 ? LB_PREFIX : LB_AGG);
+        uint32_t prefix = 0;
+        if (tile > 0) {
+            int t = (int)tile - 1;
+            for (;;) {
+                const int idx = t - lane;
+                const uint32_t st = idx >= 0 ? *(const volatile uint32_t *)(state + idx) : LB_PREFIX;
+                const uint32_t flag = st >> 30;
+                const uint32_t pm = __ballot_sync(0xffffffffu, flag == 2u), zm = __ballot_sync(0xffffffffu, flag == 0u);
+                const int firstp = pm ? __ffs(pm) - 1 : 32, firstz = zm ? __ffs(zm) - 1 : 32;
+                const int take = firstp < firstz ? firstp + 1 : firstz;
+                uint32_t x = lane < take ? (st & LB_MASK) : 0u;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+                prefix += x;
+                if (firstp < firstz) break;
+                t -= take;
+            }
+            if (lane == 0) *(volatile uint32_t *)mine = (prefix + total) | LB_PREFIX;
+        }
+        if (lane == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    uint32_t run = s_prefix + excl;
+    if (base + SCAN_ITEMS <= n && ((uintptr_t)out % 16 == 0)) {
+        uint4 a, b;
+        a.x = run; a.y = a.x + v[0]; a.z = a.y + v[1]; a.w = a.z + v[2];
+        b.x = a.w + v[3]; b.y = b.x + v[4]; b.z = b.y + v[5]; b.w = b.z + v[6];
+        *(uint4 *)(out + base) = a;
+        *(uint4 *)(out + base + 4) = b;
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            if (base + i < n) out[base + i] = run;
+            run += v[i];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Radix sort, 8 bits per pass.  The input is cut into one contiguous block per resident CTA (148 SMs x 4);
 // per pass:
@@ -302,11 +370,24 @@ int mb_exclusive_scan_u32(cudaStream_t stream, const uint32_t *in, uint32_t *out
     return MB_OK;
 }
 
+// values of [0, 2^30) only (tile totals carry two flag bits): n <= 2^20 values whose sum stays below 2^30.  `state`:
+// mb_scan_state_words(n) words the caller has zeroed (they are left non-zero).
+size_t mb_scan_state_words(uint32_t n) { return ((size_t)n + SCAN_TILE - 1) / SCAN_TILE + 4; }
+
+int mb_exclusive_scan_small(cudaStream_t stream, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *zeroed_state)
+{
+    if (n == 0) return MB_OK;
+    MB_REQUIRE(n <= SCAN1_MAX, "mb_exclusive_scan_small: too many values");
+    k_scan_lookback<<<(n + SCAN_TILE - 1) / SCAN_TILE, SCAN_THREADS, 0, stream>>>(in, out, n, zeroed_state);
+    MB_LAUNCHED();
+    return MB_OK;
+}
+
 size_t mb_sort_workspace_bytes(uint32_t n)
 {
     (void)n;
     const size_t table = (size_t)256 * OS_BLOCKS;
-    return mb_align_up(table * sizeof(uint32_t)) + mb_scan_workspace_bytes((uint32_t)table) + 256;
+    return mb_align_up(table * sizeof(uint32_t)) + mb_align_up(4 * mb_scan_state_words((uint32_t)table) * sizeof(uint32_t)) + 256;
 }
 
 int mb_sort_pairs(cudaStream_t stream, uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b,
@@ -328,15 +409,18 @@ int mb_sort_pairs(cudaStream_t stream, uint32_t *keys_a, uint32_t *vals_a, uint3
     MbArena arena(workspace, workspace_bytes);
     const uint32_t table_n = 256u * (uint32_t)blocks;
     uint32_t *table = arena.take<uint32_t>((size_t)256 * OS_BLOCKS);
-    const size_t scan_bytes = mb_scan_workspace_bytes(256u * OS_BLOCKS);
-    char *scan_ws = arena.take<char>(scan_bytes);
+    // look-back words of the table scans, one set per pass, zeroed by ONE memset (the sum of a table is n < 2^30)
+    const size_t state_words = mb_scan_state_words(256u * OS_BLOCKS);
+    uint32_t *state = arena.take<uint32_t>(4 * state_words);
+    MB_REQUIRE(n < (1u << 30), "mb_sort_pairs: too many pairs");
+    MB_CHECK_CUDA(cudaMemsetAsync(state, 0, 4 * state_words * sizeof(uint32_t), stream));
 
     uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
     bool iota = vals_a_is_iota;
     for (int p = 0; p < passes; ++p) {
         k_radix_block_hist<<<blocks, 256, 0, stream>>>(kin, n, n_dev, per_block, 8 * p, table);
         MB_LAUNCHED();
-        int rc = mb_exclusive_scan_u32(stream, table, table, table_n, scan_ws, scan_bytes);
+        int rc = mb_exclusive_scan_small(stream, table, table, table_n, state + (size_t)p * state_words);
         if (rc) return rc;
         k_radix_block_scatter<<<blocks, OS_THREADS, sizeof(ScatterSmem), stream>>>(kin, vin, kout, vout, n, n_dev,
                                                                                    per_block, 8 * p, table, iota ? 1 : 0);

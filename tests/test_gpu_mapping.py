@@ -578,6 +578,30 @@ def test_frame_graph_follows_layer_attributes(dev, oracle):
         assert np.array_equal(layer.data.cpu().numpy(), ref.data), t
 
 
+def test_counters_equal_the_oracles_touched_voxels(dev, oracle):
+    """bench.py takes U_f (voxels one frame touches) from the pipeline's own counters: they must equal the oracle's
+    per-frame touched-voxel counts ('computed by the oracle's indices'), and `voxels` the union."""
+    kw = dict(camera_height=40, camera_width=48, vertical_fov=90.0, map_height=60, map_width=60, map_depth=20,
+              feature_size=4, grid_resolution=0.1, interpolation_weight=0.5, origin_z=0.5)
+    rng = np.random.default_rng(31)
+    T = 7
+    frames = _random_frames(rng, T, 40, 48, 40, 48, 4, depth_lo=0.5, depth_hi=2.5)
+    frames["yaw"][:] = frames["yaw"][0] + 0.05 * np.arange(T, dtype=np.float32)          # overlapping views
+    frames["elevation"][:] = -0.3
+    frames["position"][:] = frames["position"][0]
+    ref = oracle.OracleLayer(**kw)
+    per_frame = []
+    for t in range(T):
+        ref.update({k: v[t] for k, v in frames.items()})
+        per_frame.append(int(ref.n_touched))
+    layer = make_layer(kw, dev, exact=False)
+    layer.update_batch({k: (torch.from_numpy(v).to(dev) if k in ("depth", "features") else v) for k, v in frames.items()})
+    c = layer.counters()
+    assert c["voxel_frames"] == sum(per_frame), (c, per_frame)
+    assert c["voxels"] == int((ref.data != 0).any(-1).sum())
+    assert c["error"] == 0
+
+
 def test_device_class_ids_out_of_range_are_flagged(dev):
     """functional.one_hot raises on ids outside [0, F) (semantic_projection_layer.py:203-214).  Host images raise
     before the launch; a DEVICE image is not read back (no per-frame stall): the kernel flags it and check() raises."""
