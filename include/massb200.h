@@ -190,6 +190,31 @@ int mb_masks_to_ids(void *stream, const uint8_t *masks, const int64_t *classes, 
  * column is empty in the slice.  A pure selection: bit-exact. */
 int mb_top_down(void *stream, const float *map, int S0, int S1, int S2, int F, int z_lo, int z_hi, float *out);
 
+/* ---- next to the path: coordinate transforms and the navigation graph's traversability tests ----
+ * mb_world_to_map  mass/nn/base_projection_layer.py:513-547 (with clamp_to_world, :381-413): coords [n][k] (k = 2 or 3,
+ *                  xyz order) -> int64 map cells [n][k]; clamp to the span of the voxel mid-points,
+ *                  bucketize(right=True) - 1, y index flipped.
+ * mb_map_to_world  mass/nn/base_projection_layer.py:452-511 (with clamp_to_map, :415-450): float map coordinates
+ *                  [n][k] -> world [n][k]: left + (right - left) * frac between neighbouring voxel mid-points, every
+ *                  operation rounded on its own as the ATen CPU ops are.
+ * mb_navigable_area  mass/navigation_policy.py:219-221: 1 - max_pool2d(blocked, 2*padding+1, stride 1, padding) as float
+ *                  [S0][S1] from the uint8 `blocked` image mb_column_summary produces.
+ * mb_nav_graph_lattice  mass/navigation_policy.py:253-285 (reset_navigation_graph): nodes at rows offset_y + a*step,
+ *                  columns offset_x + b*step; node_ok [ny][nx] (the node's cell is navigable), edge_ok [ny][nx][2]
+ *                  (the segment to the next node down / right lies inside the map and every cell of it == 1);
+ *                  ny = ceil((S0 - offset_y) / step), nx likewise.
+ * mb_nav_rects_clear  mass/navigation_policy.py:315-341 (update_navigation_graph): for rectangles {row0,row1,col0,col1}
+ *                  (inclusive), clear[i] = every cell == 1: the test of every node and edge of an existing graph. */
+int mb_world_to_map(void *stream, const float *coords, int64_t n, int k, const float *bins_x, int nx,
+                    const float *bins_y, int ny, const float *bins_z, int nz, int64_t *out);
+int mb_map_to_world(void *stream, const float *coords, int64_t n, int k, const float *bins_x, int nx,
+                    const float *bins_y, int ny, const float *bins_z, int nz, float *out);
+int mb_navigable_area(void *stream, const uint8_t *blocked, int S0, int S1, int padding, float *navigable);
+int mb_nav_graph_lattice(void *stream, const float *navigable, int S0, int S1, int offset_y, int offset_x,
+                         int step_size, uint8_t *node_ok, uint8_t *edge_ok);
+int mb_nav_rects_clear(void *stream, const float *navigable, int S0, int S1, const int32_t *rects, int m,
+                       uint8_t *clear);
+
 /* ---- a12: predict_scene_differences (mass/utils/experimentation.py:261-287) ------------------------------
  * mb_pairwise_l2: out[i][j] = ||a[i] - b[j]||_2 from direct differences (torch.linalg.norm of the
  *   broadcast difference), a [n][d], b [m][d], out [n][m].

@@ -111,6 +111,11 @@ _SIGNATURES = {
     "mb_column_summary": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
     "mb_masks_to_ids": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _f32, _vp]),
     "mb_top_down": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mb_world_to_map": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
+    "mb_map_to_world": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
+    "mb_navigable_area": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    "mb_nav_graph_lattice": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "mb_nav_rects_clear": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _vp]),
     "mb_pairwise_l2": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp]),
     "mb_cosine_best_match": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp]),
     "mb_lsap_workspace_bytes": (_sz, [_i32, _i32]),

@@ -469,6 +469,53 @@ MB_API int mb_instance_pool(void *stream, const int32_t *boxes, int nboxes, cons
                              FF, centres_x, centres_y, centres_z, out);
 }
 
+// ---- next to the path: coordinate transforms + navigation graph ---------------------------------
+MB_API int mb_world_to_map(void *stream, const float *coords, int64_t n, int k, const float *bins_x, int nx,
+                           const float *bins_y, int ny, const float *bins_z, int nz, int64_t *out)
+{
+    MB_REQUIRE(n >= 0 && (k == 2 || k == 3), "mb_world_to_map: coordinates must be [n, 2] or [n, 3]");
+    if (n == 0) return MB_OK;
+    MB_REQUIRE(coords && out && bins_x && bins_y && (k == 2 || bins_z), "mb_world_to_map: null pointer");
+    MB_REQUIRE(nx >= 2 && ny >= 2 && (k == 2 || nz >= 2), "mb_world_to_map: edge tables need two entries");
+    return mbk_world_to_map((cudaStream_t)stream, coords, n, k, bins_x, nx, bins_y, ny, bins_z, nz, out);
+}
+
+MB_API int mb_map_to_world(void *stream, const float *coords, int64_t n, int k, const float *bins_x, int nx,
+                           const float *bins_y, int ny, const float *bins_z, int nz, float *out)
+{
+    MB_REQUIRE(n >= 0 && (k == 2 || k == 3), "mb_map_to_world: coordinates must be [n, 2] or [n, 3]");
+    if (n == 0) return MB_OK;
+    MB_REQUIRE(coords && out && bins_x && bins_y && (k == 2 || bins_z), "mb_map_to_world: null pointer");
+    MB_REQUIRE(nx >= 2 && ny >= 2 && (k == 2 || nz >= 2), "mb_map_to_world: edge tables need two entries");
+    return mbk_map_to_world((cudaStream_t)stream, coords, n, k, bins_x, nx, bins_y, ny, bins_z, nz, out);
+}
+
+MB_API int mb_navigable_area(void *stream, const uint8_t *blocked, int S0, int S1, int padding, float *navigable)
+{
+    MB_REQUIRE(blocked && navigable && S0 > 0 && S1 > 0 && padding >= 0, "mb_navigable_area: bad arguments");
+    return mbk_navigable_area((cudaStream_t)stream, blocked, S0, S1, padding, navigable);
+}
+
+MB_API int mb_nav_graph_lattice(void *stream, const float *navigable, int S0, int S1, int offset_y, int offset_x,
+                                int step_size, uint8_t *node_ok, uint8_t *edge_ok)
+{
+    MB_REQUIRE(navigable && node_ok && edge_ok, "mb_nav_graph_lattice: null pointer");
+    MB_REQUIRE(S0 > 0 && S1 > 0 && step_size > 0 && offset_y >= 0 && offset_x >= 0 && offset_y < step_size &&
+               offset_x < step_size, "mb_nav_graph_lattice: bad lattice");
+    const int ny = (S0 - offset_y + step_size - 1) / step_size, nx = (S1 - offset_x + step_size - 1) / step_size;
+    if (ny <= 0 || nx <= 0) return MB_OK;
+    return mbk_nav_edges((cudaStream_t)stream, navigable, S0, S1, offset_y, offset_x, step_size, ny, nx, node_ok, edge_ok);
+}
+
+MB_API int mb_nav_rects_clear(void *stream, const float *navigable, int S0, int S1, const int32_t *rects, int m,
+                              uint8_t *clear)
+{
+    MB_REQUIRE(m >= 0 && S0 > 0 && S1 > 0, "mb_nav_rects_clear: bad sizes");
+    if (m == 0) return MB_OK;
+    MB_REQUIRE(navigable && rects && clear, "mb_nav_rects_clear: null pointer");
+    return mbk_nav_rects((cudaStream_t)stream, navigable, S1, rects, m, clear);
+}
+
 // ---- a12: predict_scene_differences --------------------------------------------------------------------
 MB_API int mb_pairwise_l2(void *stream, const float *a, int n, const float *b, int m, int d, float *out)
 {

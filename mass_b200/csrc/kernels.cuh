@@ -94,3 +94,13 @@ int mbk_cosine_best_match(cudaStream_t stream, const float *a, int n, const floa
 size_t mbk_lsap_workspace_bytes(int n, int m);
 int mbk_lsap(cudaStream_t stream, const float *cost32, const double *cost64, int n, int m, int64_t *rows, int64_t *cols,
              int *status, void *workspace, size_t workspace_bytes);
+
+// navigation.cu: coordinate transforms and navigation-graph tests next to the path
+int mbk_world_to_map(cudaStream_t stream, const float *coords, int64_t n, int k, const float *bx, int nx, const float *by,
+                     int ny, const float *bz, int nz, int64_t *out);
+int mbk_map_to_world(cudaStream_t stream, const float *coords, int64_t n, int k, const float *bx, int nx, const float *by,
+                     int ny, const float *bz, int nz, float *out);
+int mbk_navigable_area(cudaStream_t stream, const uint8_t *blocked, int S0, int S1, int padding, float *out);
+int mbk_nav_edges(cudaStream_t stream, const float *navigable, int S0, int S1, int off_y, int off_x, int step, int ny,
+                  int nx, uint8_t *node_ok, uint8_t *edge_ok);
+int mbk_nav_rects(cudaStream_t stream, const float *navigable, int S1, const int32_t *rects, int m, uint8_t *clear);

@@ -152,6 +152,15 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
             want = min(want, int(self.workspace_limit))
         ws = (self._ws or _lib.shared_workspace(device)).get(want, device)
         self._last_ws, self._last_ws_use = ws, _lib.note_workspace_use(ws)
+        if fold is not None and hasattr(fold, "slot_table"):
+            # sparse partial (mass_b200/nn/sharded.py: SparsePartial): rows found / created per touched voxel
+            _lib.check(L.mb_layer_fold_sparse(
+                _lib.stream_ptr(device), _lib.ptr(self.rays), _lib.ptr(prep["depth"]), _lib.ptr(prep["features"]),
+                _lib.ptr(prep["class_ids"]), _lib.ptr(prep["pose"]), T, H, W, fh, fw, F, _lib.ptr(self.bins_x), nx,
+                _lib.ptr(self.bins_y), ny, _lib.ptr(self.bins_z), nz, _lib.ptr(fold.slot_table), fold.buffer_ptr,
+                int(fold.capacity), float(self.interpolation_weight), float(self.min_ray_depth),
+                float(self.max_ray_depth), _lib.ptr(ws), want))
+            return self
         if fold is not None:
             partial_b, partial_a = fold
             _lib.check(L.mb_layer_fold(
@@ -209,6 +218,9 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
                                                      ctypes.byref(bits)))
         if bits.value & 2:
             raise RuntimeError("Class values must be in [0, %d)" % self.feature_size)
+        if bits.value & 4:
+            raise RuntimeError("libmassb200: the sparse partial is full (capacity too small for the voxels the "
+                               "folded frames touch); rows were dropped")
         if bits.value:
             raise RuntimeError("libmassb200: batched update reported error bits 0x%x" % bits.value)
         return self
@@ -416,9 +428,31 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         mz = (self.bins_z[:-1] + self.bins_z[1:]) / 2
         return mx, my, mz
 
+    def _transform(self, coords, to_world):
+        """Batched coordinate transform on the device (mb_map_to_world / mb_world_to_map): any leading shape, last
+        dimension 2 (xy) or 3 (xyz)."""
+        device = self.data.device
+        coords = torch.as_tensor(coords)
+        if to_world:
+            # clamp_to_map runs in the caller's dtype, then the reference casts to float32 (lines 471-472)
+            coords = self.clamp_to_map(coords.to(device)).to(torch.float32)
+        coords = coords.to(device=device, dtype=torch.float32).contiguous()
+        k = int(coords.shape[-1])
+        if k not in (2, 3):
+            raise ValueError("coordinates must end in a dimension of 2 (xy) or 3 (xyz), got %s" % (tuple(coords.shape),))
+        n = coords.numel() // k
+        out = torch.empty(coords.shape, dtype=torch.float32 if to_world else torch.int64, device=device)
+        fn = _lib.lib().mb_map_to_world if to_world else _lib.lib().mb_world_to_map
+        _lib.check(fn(_lib.stream_ptr(device), _lib.ptr(coords), n, k, _lib.ptr(self.bins_x), self.bins_x.numel(),
+                      _lib.ptr(self.bins_y), self.bins_y.numel(), _lib.ptr(self.bins_z), self.bins_z.numel(),
+                      _lib.ptr(out)))
+        return out
+
     def map_to_world(self, coords):
         """Map (x, y, z) cell coordinates (fractional allowed) -> world.
-        Reference: base_projection_layer.py:452-511."""
+        Reference: base_projection_layer.py:452-511.  One kernel for the whole batch when the layer is on the GPU."""
+        if self.data.is_cuda:
+            return self._transform(coords, to_world=True)
         coords = self.clamp_to_map(coords).to(torch.float32)
         base = coords.floor()
         cell = base.to(torch.int64)
@@ -434,7 +468,10 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         return torch.stack(out, dim=-1)
 
     def world_to_map(self, coords):
-        """World -> integer map (x, y, z) cells.  Reference: base_projection_layer.py:513-547."""
+        """World -> integer map (x, y, z) cells.  Reference: base_projection_layer.py:513-547.  One kernel for the
+        whole batch when the layer is on the GPU."""
+        if self.data.is_cuda:
+            return self._transform(coords, to_world=False)
         coords = self.clamp_to_world(coords)
         cells = [torch.bucketize(coords[..., 0].contiguous(), self.bins_x, right=True) - 1,
                  self.bins_y.numel() - torch.bucketize(coords[..., 1].contiguous(), self.bins_y, right=True) - 1]

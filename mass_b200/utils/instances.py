@@ -149,18 +149,27 @@ def find_instances(layer, semantic_category, confidence_threshold, contour_paddi
         num_classes = layer.data.shape[3]
         if not 0 <= c < num_classes:
             raise IndexError("semantic_category %d is outside [0, %d)" % (c, num_classes))
+        # contour boxes of EVERY class, once per state of the semantic map (one sweep for the presence images, OpenCV
+        # on the host per class): kept, so that a class served later costs one pooling launch and no contour pass
+        boxes_key = ("boxes", float(contour_threshold))
+        all_boxes = memo[1].get(boxes_key)
+        if all_boxes is None:
+            all_boxes = {k: contour_boxes(_presence_image(layer, k, 0, contour_threshold)) for k in range(num_classes)}
+            memo[1][boxes_key] = all_boxes
+        bulk_key = ("bulk",) + params + maps              # the shared pooling launch, once per (arguments, maps)
+        first = bulk_key not in memo[1]
+        memo[1][bulk_key] = True
         # classes whose boxes cover a large part of the map (the background class spans the whole room) are
-        # left out of the shared launch and served on demand: one CTA walks a box
-        per_class, boxes5 = {}, []
-        for k in range(num_classes):
-            bk = contour_boxes(_presence_image(layer, k, 0, contour_threshold))
-            if k == c or sum(b[2] * b[3] for b in bk) <= 4096:
-                per_class[k] = bk
-                boxes5.extend(b + (k,) for b in bk)
+        # left out of the shared launch and pooled on demand: one CTA walks a box
+        wanted = [k for k in range(num_classes)
+                  if k == c or (first and sum(b[2] * b[3] for b in all_boxes[k]) <= 4096)]
+        wanted = [k for k in wanted if (k,) + params + maps not in memo[1]]
+        boxes5 = [b + (k,) for k in wanted for b in all_boxes[k]]
         rows = _pool_rows(layer, boxes5, feature_map)
         keep = (rows[:, 0] > confidence_threshold).cpu().numpy() if boxes5 else np.zeros(0, bool)
         start = 0
-        for k, bk in per_class.items():
+        for k in wanted:
+            bk = all_boxes[k]
             sl = slice(start, start + len(bk))
             memo[1][(k,) + params + maps] = _instances_from_rows(bk, rows[sl], keep[sl], feature_map is not None)
             start += len(bk)

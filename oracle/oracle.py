@@ -351,3 +351,80 @@ def predict_scene_differences(sem0, sem1, res0, res1, objects_moved, object_ids_
         if object_to_move is not None:
             break
     return object_to_move, goals0, goals1, last
+
+
+# -- next to the path ------------------------------------
+def world_to_map(layer, coords):
+    """mass/nn/base_projection_layer.py:513-547 with clamp_to_world (:381-413): fp32 clamp to the span of the voxel
+    mid-points, searchsorted(side='right') - 1 on the layer's own edge tables, y index flipped.  coords [..., 2|3]."""
+    coords = _f32(coords)
+    k = coords.shape[-1]
+    out = np.empty(coords.shape, np.int64)
+    for axis, bins in enumerate((layer.bins_x, layer.bins_y, layer.bins_z)[:k]):
+        lo = (bins[0] + bins[1]) / np.float32(2)
+        hi = (bins[-1] + bins[-2]) / np.float32(2)
+        x = np.minimum(np.maximum(coords[..., axis], lo), hi)
+        idx = np.searchsorted(bins, x, side="right") - 1
+        out[..., axis] = (bins.size - 2 - idx) if axis == 1 else idx
+    return out
+
+
+def map_to_world(layer, coords):
+    """mass/nn/base_projection_layer.py:452-511 with clamp_to_map (:415-450), every fp32 operation rounded on its own:
+    left + (right - left) * (coords - floor(coords)) between neighbouring voxel mid-points."""
+    coords = _f32(coords)
+    k = coords.shape[-1]
+    out = np.empty(coords.shape, np.float32)
+    mids = layer.cell_centres()
+    sizes = (layer.map_width, layer.map_height, layer.map_depth)
+    for axis in range(k):
+        x = np.minimum(np.maximum(coords[..., axis], np.float32(0)), np.float32(sizes[axis] - 1))
+        fl = np.floor(x)
+        i = fl.astype(np.int64)
+        left = mids[axis][i]
+        right = mids[axis][np.minimum(np.maximum(i + 1, 0), sizes[axis] - 1)]
+        out[..., axis] = (left + ((right - left).astype(np.float32) * (x - fl).astype(np.float32)).astype(np.float32)).astype(np.float32)
+    return out
+
+
+def navigable_area(layer, padding=3, depth_slice=None, obstacle_threshold=0.0):
+    """mass/navigation_policy.py:205-221: cells with no occupied voxel in the depth slice, obstacles grown by
+    `padding` cells (max_pool2d pads with -inf: the image border does not count as an obstacle)."""
+    occ = np.abs(layer.data.astype(np.float64)).sum(axis=3).astype(np.float32) > np.float32(obstacle_threshold)
+    if depth_slice is not None:
+        occ = occ[:, :, depth_slice]
+    blocked = occ.any(axis=2)
+    S0, S1 = blocked.shape
+    grown = np.zeros_like(blocked)
+    for dy in range(-padding, padding + 1):
+        for dx in range(-padding, padding + 1):
+            ys, yd = slice(max(dy, 0), S0 + min(dy, 0)), slice(max(-dy, 0), S0 + min(-dy, 0))
+            xs, xd = slice(max(dx, 0), S1 + min(dx, 0)), slice(max(-dx, 0), S1 + min(-dx, 0))
+            grown[yd, xd] |= blocked[ys, xs]
+    return (~grown).astype(np.float32)
+
+
+def navigation_graph_edges(layer, navigable, step_size=5):
+    """mass/navigation_policy.py:253-285: the edge list of reset_navigation_graph, in its insertion order, as
+    ((x0, y0), (x1, y1)) tuples."""
+    origin = np.array([[layer.origin_x, layer.origin_y]], np.float32)
+    ox, oy = (int(v) % step_size for v in world_to_map(layer, origin)[0])
+    S0, S1 = navigable.shape
+    edges = []
+    for i in range(oy, S0, step_size):
+        for j in range(ox, S1, step_size):
+            for di, dj in ((step_size, 0), (0, step_size)):
+                y, x = i + di, j + dj
+                if 0 <= y < S0 and 0 <= x < S1 and (navigable[min(i, y):max(i, y) + 1, min(j, x):max(j, x) + 1] == 1).all():
+                    edges.append(((j, i), (x, y)))
+    return edges
+
+
+def update_navigation_graph(nodes, edges, navigable):
+    """mass/navigation_policy.py:315-341 on plain lists: the nodes and edges that survive the refresh."""
+    keep_nodes = [(j, i) for (j, i) in nodes if navigable[i, j] != 0]
+    alive = set(keep_nodes)
+    keep_edges = [((j, i), (x, y)) for (j, i), (x, y) in edges
+                  if (j, i) in alive and (x, y) in alive and
+                  not (navigable[min(i, y):max(i, y) + 1, min(j, x):max(j, x) + 1] == 0).any()]
+    return keep_nodes, keep_edges

@@ -1,5 +1,8 @@
 """torchrun target (one rank per GPU, NCCL): frames of one scene sharded across the ranks with
-update_batch_sharded, checked on every rank against the CPU oracle's sequential fusion.
+update_batch_sharded, checked on every rank against the CPU oracle's sequential fusion -- once through the portable
+all_gather exchange and once through the peer-memory exchange (rows read from the other ranks' allocations inside
+the apply kernel).  With MASSB200_PEER_TEST_ONE_GPU=1 all ranks share cuda:0 and gloo is the control plane (NCCL does
+not put two ranks on one device): the single-GPU test of the peer path.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/dist_sharded_check.py"""
 import os
 import sys
@@ -14,9 +17,15 @@ sys.path.insert(0, ROOT)
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    one_gpu = os.environ.get("MASSB200_PEER_TEST_ONE_GPU") == "1"
+    if one_gpu:
+        local = 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if one_gpu:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=dev)
     from mass_b200.nn.base_projection_layer import BaseProjectionLayer
     from mass_b200.nn import sharded
     from mass_b200.utils import synthetic
@@ -34,22 +43,42 @@ def main():
         ref.update(f)
     bounds = np.linspace(0, T, world + 1).astype(int)
     mine = frames[bounds[rank]:bounds[rank + 1]]
+
+    def verdict(layer, what):
+        torch.cuda.synchronize()
+        got = layer.data.cpu().numpy()
+        occ = np.array_equal((got != 0).any(-1), (ref.data != 0).any(-1))
+        err = np.abs(got.astype(np.float64) - ref.data)
+        ok = bool((err <= 1e-5 * np.abs(ref.data)).all())
+        flag = torch.tensor([int(ok and occ)], device="cpu" if one_gpu else dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("%s on %d ranks: %s (occupancy %s, max rel err %.2e)" % (
+                what, world, "OK" if int(flag.item()) else "MISMATCH", occ,
+                float((err / np.maximum(np.abs(ref.data), 1e-30)).max())), flush=True)
+        return int(flag.item())
+
+    good = 1
+    if not one_gpu:
+        layer = BaseProjectionLayer(exact=False, **kw).to(dev)
+        layer.data.copy_(torch.from_numpy(start))
+        sharded.update_batch_sharded(layer, mine)
+        good &= verdict(layer, "all_gather exchange")
+    # peer-memory exchange, twice through the same buffers (the second call checks that they come back empty)
     layer = BaseProjectionLayer(exact=False, **kw).to(dev)
-    layer.data.copy_(torch.from_numpy(start))
-    sharded.update_batch_sharded(layer, mine)
-    torch.cuda.synchronize()
-    got = layer.data.cpu().numpy()
-    occ = np.array_equal((got != 0).any(-1), (ref.data != 0).any(-1))
-    err = np.abs(got.astype(np.float64) - ref.data)
-    ok = bool((err <= 1e-5 * np.abs(ref.data)).all())
-    flag = torch.tensor([int(ok and occ)], device=dev)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    if rank == 0:
-        print("sharded fusion on %d ranks: %s (occupancy %s, max rel err %.2e)" % (
-            world, "OK" if int(flag.item()) else "MISMATCH", occ,
-            float((err / np.maximum(np.abs(ref.data), 1e-30)).max())))
+    ex = sharded.PeerExchange(layer, capacity=60000)
+    for rep in range(2):
+        layer.data.copy_(torch.from_numpy(start))
+        half = len(mine) // 2
+        if half:                                       # a rank folds its chunk in two pieces (ring by ring)
+            ex.partial.fold(layer, mine[:half])
+        sharded.update_batch_sharded(layer, mine[half:], exchange=ex)
+        layer.check()
+        good &= verdict(layer, "peer exchange (pass %d)" % rep)
+    ex.close()
+    dist.barrier()
     dist.destroy_process_group()
-    sys.exit(0 if int(flag.item()) else 1)
+    sys.exit(0 if good else 1)
 
 
 if __name__ == "__main__":

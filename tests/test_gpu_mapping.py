@@ -664,14 +664,15 @@ def test_fold_and_ordered_apply_equal_sequential(dev, oracle):
         ref.update({k: v[t] for k, v in frames.items()})
     layer = make_layer(kw, dev, exact=False)
     layer.data.copy_(torch.from_numpy(start))
-    partial = sharded.PartialMap(layer)
+    partial = sharded.SparsePartial(layer, capacity=20000)
     parts = []
     for lo, hi in ((0, 4), (4, 5), (5, 9)):
         parts.append(sharded.fold_frames(layer, {k: v[lo:hi] for k, v in frames.items()}, partial))
     assert torch.equal(layer.data.cpu(), torch.from_numpy(start))          # folding does not touch the map
-    assert float(partial.a.min()) == 2.0 and float(partial.b.abs().max()) == 0.0   # scratch is clean again
+    assert partial.count() == 0 and int(partial.slot_table.max()) == -1    # the partial is empty again
     for idx, a, b in parts:
         assert idx.dtype == torch.int64 and a.shape == idx.shape and tuple(b.shape) == (idx.numel(), F)
+        assert idx.unique().numel() == idx.numel()
         sharded.apply_partial(layer, idx, a, b)
     got = layer.data.cpu().numpy()
     assert np.array_equal((got != 0).any(-1), (ref.data != 0).any(-1))
@@ -681,6 +682,39 @@ def test_fold_and_ordered_apply_equal_sequential(dev, oracle):
     for idx, a, b in reversed(parts):
         sharded.apply_partial(wrong, idx, a, b)
     assert not np.allclose(wrong.data.cpu().numpy(), ref.data, rtol=1e-3, atol=0)
+    # several chunks composed onto ONE partial (a rank folding its frames ring by ring), applied from the buffer with
+    # the row count read on the device: the same map
+    third = make_layer(kw, dev, exact=False)
+    third.data.copy_(torch.from_numpy(start))
+    for lo, hi in ((0, 4), (4, 5), (5, 9)):
+        partial.fold(third, {k: v[lo:hi] for k, v in frames.items()})
+    third.check()
+    assert torch.equal(third.data.cpu(), torch.from_numpy(start))
+    state = third.map_state()
+    sharded.apply_partial_buffer(third, partial.buffer_ptr, partial.capacity)
+    assert third.map_state() != state
+    got3 = third.data.cpu().numpy()
+    assert np.array_equal((got3 != 0).any(-1), (ref.data != 0).any(-1))
+    assert_close_rel(got3, ref.data)
+    # a partial that is too small says so instead of dropping rows silently
+    tiny = sharded.SparsePartial(third, capacity=10)
+    tiny.fold(third, {k: v[0:2] for k, v in frames.items()})
+    with pytest.raises(RuntimeError, match="sparse partial is full"):
+        third.check()
+
+
+def test_peer_exchange_two_processes_one_gpu():
+    """The peer-memory path (CUDA IPC handles, rows read out of the other process's allocation by the apply kernel)
+    with two processes on THIS GPU and gloo as the control plane: what runs over NVLink between GPUs, minus the link."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MASSB200_PEER_TEST_ONE_GPU="1")
+    proc = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                           "--master-addr", "127.0.0.1", "--master-port", "29533",
+                           os.path.join(root, "tests", "dist_sharded_check.py")],
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
+    assert proc.returncode == 0, proc.stdout[-3000:]
+    assert "peer exchange" in proc.stdout
 
 
 def test_sharded_nccl_two_gpus():
