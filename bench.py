@@ -442,15 +442,16 @@ def run_c2(args):
                                "d2h_bytes_per_step": 8}
         del sem, sgraph, sprep, ids_d
 
-    # ---- with several GPUs: the frame-sharded scene (BASELINE config 4) in short, so that the scaling record ------
-    # ---- holds a path WITH a data-path exchange, not only replicas -------------------------------------------------
+    # ---- the frame-sharded scene (BASELINE config 4) in short, at every N, so that the scaling record also holds ------
+    # ---- a path WITH a data-path exchange (strong scaling), not only replicas ---------------------------------------
     c4 = None
-    if world > 1 and not args.no_c4:
+    if not args.no_c4:
         try:
             import bench_configs
+            layer = prep = graph = None
             torch.cuda.empty_cache()
-            c4 = bench_configs.c4_sharded(R, frames_total=256 * world if args.c4_frames <= 0 else args.c4_frames,
-                                          brief=True)
+            # the same 1024-frame scene at every N (strong scaling); `--config c4` runs all 4096 frames
+            c4 = bench_configs.c4_sharded(R, frames_total=1024 if args.c4_frames <= 0 else args.c4_frames, brief=True)
         except Exception as exc:                                  # never lose the main line to the extra one
             c4 = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
