@@ -227,6 +227,13 @@ int mb_pairwise_l2(void *stream, const float *a, int n, const float *b, int m, i
  * cosine; a zero vector has similarity 0 to everything. */
 int mb_cosine_best_match(void *stream, const float *a, int n, const float *b, int m, int d, int64_t *best,
                          float *best_sim);
+/* The same result (float64-exact decision, first maximum on ties) for LARGE instance matrices -- thousands of rows, a
+ * real dense contraction -- on the tcgen05 tensor cores: A B^T in 3 x TF32 with fp32 accumulators in TMEM ranks the
+ * candidates, every column within 2e-3 of a row's largest approximate cosine is re-evaluated exactly.  Workspace from
+ * mb_cosine_best_match_tc_workspace_bytes.  (No reference counterpart: SURVEY.md F3.) */
+size_t mb_cosine_best_match_tc_workspace_bytes(int n, int m);
+int mb_cosine_best_match_tc(void *stream, const float *a, int n, const float *b, int m, int d, int64_t *best,
+                            float *best_sim, void *workspace, size_t workspace_bytes);
 size_t mb_lsap_workspace_bytes(int n, int m);
 int mb_lsap(void *stream, const float *cost32, const double *cost64, int n, int m, int64_t *rows, int64_t *cols,
             int32_t *status, void *workspace, size_t workspace_bytes);

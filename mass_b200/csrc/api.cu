@@ -534,6 +534,21 @@ MB_API int mb_cosine_best_match(void *stream, const float *a, int n, const float
     return mbk_cosine_best_match((cudaStream_t)stream, a, n, b, m, d, best, best_sim);
 }
 
+MB_API size_t mb_cosine_best_match_tc_workspace_bytes(int n, int m)
+{
+    if (n <= 0) return 256;
+    return mbk_cosine_tc_workspace_bytes(n, m > 0 ? m : 1);
+}
+
+MB_API int mb_cosine_best_match_tc(void *stream, const float *a, int n, const float *b, int m, int d, int64_t *best,
+                                   float *best_sim, void *workspace, size_t workspace_bytes)
+{
+    MB_REQUIRE(n >= 0 && m >= 0 && d > 0, "mb_cosine_best_match_tc: bad sizes");
+    if (n == 0) return MB_OK;
+    MB_REQUIRE(a && best && best_sim && (m == 0 || b), "mb_cosine_best_match_tc: null pointer");
+    return mbk_cosine_best_match_tc((cudaStream_t)stream, a, n, b, m, d, best, best_sim, workspace, workspace_bytes);
+}
+
 MB_API size_t mb_lsap_workspace_bytes(int n, int m)
 {
     if (n <= 0 || m <= 0) return 256;

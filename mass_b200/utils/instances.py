@@ -196,9 +196,11 @@ def pairwise_l2(a, b):
     return out
 
 
-def cosine_best_match(a, b):
+def cosine_best_match(a, b, tensor_cores=None):
     """(best [n] int64, similarity [n] float32): for every row of a the row of b with the largest cosine
-    similarity, first maximum on ties.  An additional op: the reference matches by L2 distance + assignment
+    similarity, first maximum on ties.  Large matrices (>= 1024 rows on both sides; `tensor_cores` forces either
+    path) go through the tcgen05 kernel: 3 x TF32 ranks the candidates, float64 decides, so both paths return the same
+    indices.  An additional op: the reference matches by L2 distance + assignment
     (predict_scene_differences), which is what `pairwise_l2` + `linear_sum_assignment` reproduce."""
     device = _lib.require_cuda(a.device)
     a = a.to(torch.float32).contiguous()
@@ -207,6 +209,16 @@ def cosine_best_match(a, b):
         raise ValueError("cosine_best_match needs [n, d] and [m, d], got %s and %s" % (tuple(a.shape), tuple(b.shape)))
     best = torch.empty(a.shape[0], dtype=torch.int64, device=device)
     sim = torch.empty(a.shape[0], dtype=torch.float32, device=device)
+    if tensor_cores is None:
+        # a real dense contraction only from a few thousand instances on; below that the job is latency-sized
+        tensor_cores = a.shape[0] >= 1024 and b.shape[0] >= 1024 and a.shape[1] >= 32
+    if tensor_cores and a.shape[0] > 0:
+        L = _lib.lib()
+        nbytes = int(L.mb_cosine_best_match_tc_workspace_bytes(a.shape[0], b.shape[0]))
+        ws = _ws.get(nbytes, device)
+        _lib.check(L.mb_cosine_best_match_tc(_lib.stream_ptr(device), _lib.ptr(a), a.shape[0], _lib.ptr(b), b.shape[0],
+                                             a.shape[1], _lib.ptr(best), _lib.ptr(sim), _lib.ptr(ws), nbytes))
+        return best, sim
     _lib.check(_lib.lib().mb_cosine_best_match(_lib.stream_ptr(device), _lib.ptr(a), a.shape[0], _lib.ptr(b),
                                                b.shape[0], a.shape[1], _lib.ptr(best), _lib.ptr(sim)))
     return best, sim

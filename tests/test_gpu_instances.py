@@ -255,3 +255,31 @@ def test_cosine_best_match(dev):
     assert 7 not in best.cpu().numpy().tolist() or 3 not in ref.argmax(axis=1).tolist()
     e_best, e_sim = instances.cosine_best_match(torch.zeros(3, 8, device=dev), torch.zeros(0, 8, device=dev))
     assert e_best.tolist() == [-1, -1, -1]
+
+
+@pytest.mark.parametrize("n,m,d", [(1500, 2300, 256), (300, 1300, 70), (128, 128, 32)])
+def test_cosine_best_match_tensor_cores(dev, n, m, d):
+    """The tcgen05 path (3 x TF32 ranks, float64 decides) returns the SIMT kernel's indices -- first maximum on ties,
+    duplicates and zero rows included -- and both equal float64 numpy."""
+    from mass_b200.utils import instances
+    rng = np.random.default_rng(41)
+    a = rng.standard_normal((n, d)).astype(np.float32)
+    b = rng.standard_normal((m, d)).astype(np.float32)
+    k = min(n, m) // 2
+    b[:k] = a[rng.permutation(n)[:k]] * rng.uniform(0.5, 2.0, (k, 1)).astype(np.float32) \
+        + 0.02 * rng.standard_normal((k, d)).astype(np.float32)            # near-matches: close calls between candidates
+    b[m - 1] = b[5]                                                          # exact duplicates: the lower index must win
+    b[m // 2] = b[9]
+    b[17] = 0.0                                                              # zero rows never win a positive similarity
+    a[3] = 0.0                                                               # a zero query: similarity 0 everywhere, index 0
+    ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    best_tc, sim_tc = instances.cosine_best_match(ta, tb, tensor_cores=True)
+    best_sm, sim_sm = instances.cosine_best_match(ta, tb, tensor_cores=False)
+    torch.cuda.synchronize()
+    assert torch.equal(best_tc, best_sm)
+    np.testing.assert_allclose(sim_tc.cpu().numpy(), sim_sm.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    den = np.linalg.norm(a64, axis=1)[:, None] * np.linalg.norm(b64, axis=1)[None, :]
+    ref = np.where(den > 0, (a64 @ b64.T) / np.where(den > 0, den, 1.0), 0.0)
+    assert best_tc.cpu().numpy().tolist() == ref.argmax(axis=1).tolist()
+    assert int(best_tc[3]) == 0 and float(sim_tc[3]) == 0.0
