@@ -120,7 +120,7 @@ def c4_sharded(R, frames_total=C4_FRAMES, brief=False, check=False, ring=C4_RING
         c0.record()
         if ex is not None:
             rows = ex.partial.count_view.clone()                 # (device copy; read after the timed span)
-            ex.combine(layer)
+            ex.combine(layer, pull=os.environ.get("MASSB200_C4_DIRECT") != "1")
         c1.record()
         torch.cuda.synchronize()
         fold_ms = sum(a.elapsed_time(b) for a, b in marks)
@@ -160,8 +160,11 @@ def c4_sharded(R, frames_total=C4_FRAMES, brief=False, check=False, ring=C4_RING
            "value": frames_total / (total_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "scaling": "strong",
            "frames": frames_total, "ms": {"total_max_over_ranks": total_ms, "fold": fold_max, "combine": comb_max},
            "combine_share": comb_max / total_ms if total_ms > 0 else 0.0,
-           "exchange": ("peer memory over NVLink: each rank's sparse partial is read out of its owner's HBM by the apply "
-                        "kernel of every other rank (mb_affine_apply_partial), two stream-ordered NCCL barriers around it")
+           "exchange": (("peer memory over NVLink: each rank's sparse partial is read out of its owner's HBM by the apply "
+                         "kernel of every other rank (mb_affine_apply_partial)" if os.environ.get("MASSB200_C4_DIRECT") == "1" else
+                         "peer memory over NVLink: one kernel per rank pulls the sparse partials of all peers at once "
+                         "(mb_partial_pull, row counts read on the device), then they are applied in rank order")
+                        + ", two stream-ordered NCCL barriers around it")
            if world > 1 else "none (one GPU: sequential fusion into the map)",
            "partial_rows_per_rank": rows_all, "nvlink_bytes_read_per_rank": link_bytes,
            "nvlink_gbs_per_rank": (max(link_bytes) / (comb_max * 1e-3) / 1e9) if (world > 1 and comb_max > 0) else None,

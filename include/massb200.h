@@ -139,6 +139,11 @@ int mb_layer_fold_sparse(void *stream, const float *rays, const float *depth, co
                          int32_t *slot_table, void *partial_buffer, uint32_t capacity, float interpolation_weight,
                          float min_ray_depth, float max_ray_depth, void *workspace, size_t workspace_bytes);
 int mb_affine_apply_partial(void *stream, float *map, int F, const void *partial_buffer, uint32_t capacity);
+/* All peers' partials into local staging slots (each mb_partial_buffer_bytes large, same layout) in ONE kernel that
+ * reads from every peer at once -- rank `self` itself is skipped -- with the row counts read on the device.
+ * peer_buffers_host / staging_slots_host: HOST arrays of `world` (<= 16) device pointers, indexed by rank. */
+int mb_partial_pull(void *stream, const void *const *peer_buffers_host, void *const *staging_slots_host, int world,
+                    int self, uint32_t capacity, int F);
 
 /* Peer memory for partial buffers (CUDA IPC: another process of the box -- another GPU over NVLink -- maps the
  * allocation).  The one exception to "the library owns no memory": an IPC handle names a whole allocation. */

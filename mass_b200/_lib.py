@@ -96,6 +96,7 @@ _SIGNATURES = {
     "mb_layer_fold_sparse": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32,
                                     _vp, _i32, _vp, _i32, _vp, _vp, ctypes.c_uint32, _f32, _f32, _f32, _vp, _sz]),
     "mb_affine_apply_partial": (_i32, [_vp, _vp, _i32, _vp, ctypes.c_uint32]),
+    "mb_partial_pull": (_i32, [_vp, _vp, _vp, _i32, _i32, ctypes.c_uint32, _i32]),
     "mb_peer_alloc": (_i32, [_sz, _vp]),
     "mb_peer_free": (_i32, [_vp]),
     "mb_peer_export": (_i32, [_vp, _vp]),
@@ -131,8 +132,12 @@ def lib():
     """Loads (building first if needed) the shared library; raises if impossible."""
     global _lib
     if _lib is None:
-        build()                            # no-op unless a source changed since the library was built
-        L = ctypes.CDLL(SO_PATH)
+        override = os.environ.get("MASSB200_LIB")         # tuning aid: a variant build of the same sources
+        if override:
+            L = ctypes.CDLL(override)
+        else:
+            build()                        # no-op unless a source changed since the library was built
+            L = ctypes.CDLL(SO_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError here = header/library mismatch
             fn.restype, fn.argtypes = res, args

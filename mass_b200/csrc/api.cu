@@ -345,6 +345,13 @@ MB_API int mb_layer_fold_sparse(void *stream, const float *rays, const float *de
                         workspace, workspace_bytes, &sp);
 }
 
+MB_API int mb_partial_pull(void *stream, const void *const *peer_buffers_host, void *const *staging_slots_host, int world,
+                           int self, uint32_t capacity, int F)
+{
+    MB_REQUIRE(peer_buffers_host && staging_slots_host && F > 0, "mb_partial_pull: bad arguments");
+    return mbk_partial_pull((cudaStream_t)stream, peer_buffers_host, staging_slots_host, world, self, capacity, F);
+}
+
 MB_API int mb_affine_apply_partial(void *stream, float *map, int F, const void *partial_buffer, uint32_t capacity)
 {
     MB_REQUIRE(map && partial_buffer && F > 0, "mb_affine_apply_partial: bad arguments");

@@ -34,6 +34,7 @@
 // run to run.
 // Weights follow the reference's fp32 operation order; occupancy is bit-exact and values differ from
 // the reference CPU path by fp32 re-association only (<= 1e-5 relative).
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "kernels.cuh"
 #include "geometry.cuh"
@@ -126,10 +127,33 @@ __device__ __forceinline__ int find_cell(const uint32_t *__restrict__ ucell, uin
 // it (items are sorted by cell key, and a cell has one group per tile).
 //   item value = tile << 12 | first slot << 4 | (length - 1);  pixel record = {ratio0, ratio1, ratio2, pixel in tile}
 constexpr int TILE_W = 32, TILE_H = 8, TILE_PIX = TILE_W * TILE_H;
-constexpr int WHASH = 512;                       // hash slots per warp (>= 2 x pixels of a tile)
+#ifndef MB_WHASH
+#define MB_WHASH 512
+#endif
+#ifndef MB_TG_MINB
+#define MB_TG_MINB 4
+#endif
+#ifndef MB_VOX_MINB
+#define MB_VOX_MINB 5
+#endif
+#ifndef MB_TASK_ITEMS
+#define MB_TASK_ITEMS 128
+#endif
+#ifndef MB_ACC_U21
+#define MB_ACC_U21 8
+#endif
+#ifndef MB_SEG_MINB
+#define MB_SEG_MINB 1
+#endif
+#ifndef MB_VS_MINB
+#define MB_VS_MINB 4
+#endif
+constexpr int WHASH = MB_WHASH;                  // hash slots per warp (>= pixels of a tile)
+constexpr int WHASH_BITS = MB_WHASH == 256 ? 8 : MB_WHASH == 512 ? 9 : MB_WHASH == 1024 ? 10 : -1;
+static_assert(WHASH_BITS > 0, "MB_WHASH must be 256, 512 or 1024");
 constexpr int ITEM_MAX = 16;                     // pixels per item
 constexpr uint32_t HASH_EMPTY = 0xffffffffu;
-constexpr int TASK_ITEMS = 128;                  // items per accumulate task; runs never cross a task
+constexpr int TASK_ITEMS = MB_TASK_ITEMS;        // most items of an accumulate run (one warp task)
 constexpr int TASK_WORDS = TASK_ITEMS / 32;      // items per lane when a warp loads a task
 constexpr uint32_t MAX_TILES = 1u << 20;         // tile ids are 20 bits of the item value
 
@@ -187,7 +211,7 @@ constexpr int VOX_PPT = 4;                       // pixels per thread of k_cell_
 
 // K1a: grid = (pixel blocks, frames): pixel -> {cell key (or >= 0xffffffe0: invalid), 3 in-voxel ratios}, in
 // image order.  Pure per-pixel math at full occupancy; the grouping kernel below re-reads it.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MB_VOX_MINB)
 k_cell_voxelise(const float *__restrict__ rays, const float *__restrict__ depth, const float *__restrict__ pose,
                 uint32_t npix, const float *__restrict__ bins_x, int nx, const float *__restrict__ bins_y, int ny,
                 const float *__restrict__ bins_z, int nz, CellGrid g, float min_d, float max_d,
@@ -247,7 +271,7 @@ struct __align__(16) WarpTile {
 
 // K1b: one warp per 32 x 8 tile groups the tile's pixels by cell (see above) and writes the grouped records
 // and the tile's items.
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, MB_TG_MINB)
 k_tile_group(const uint4 *__restrict__ pix, TileGeom tg, uint32_t ntiles, uint4 *__restrict__ rec,
              uint32_t *__restrict__ tkey, uint32_t *__restrict__ tval, uint32_t *__restrict__ tcount)
 {
@@ -287,7 +311,7 @@ k_tile_group(const uint4 *__restrict__ pix, TileGeom tg, uint32_t ntiles, uint4 
         const int leader = __ffs(m) - 1;
         uint32_t sl = 0;
         if (valid && lane == leader) {
-            uint32_t h = (key * 2654435761u) >> 23;                   // 9 bits
+            uint32_t h = (key * 2654435761u) >> (32 - WHASH_BITS);    // the top bits of the product
             for (;;) {
                 const uint32_t old = atomicCAS(&S.hkey[h], HASH_EMPTY, key);
                 if (old == HASH_EMPTY || old == key) break;
@@ -631,7 +655,7 @@ k_vox_list(const uint32_t *__restrict__ bitmap, uint32_t nwords, uint32_t *state
 
 // K5: per (cell, frame) segment and slot: W = sum w, S2 = sum w^2 over the pixels of the segment's items (item
 // order, pixel order inside the item).  One thread per segment; an item's records are contiguous.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MB_SEG_MINB)
 k_seg_sums(const uint32_t *__restrict__ ival, const uint4 *__restrict__ rec, const uint32_t *__restrict__ seg_start,
            float2 *__restrict__ segws, size_t cap, const uint32_t *__restrict__ counters)
 {
@@ -698,7 +722,7 @@ k_voxel_sources(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__
 // g(t) = r(t) * prod_{s>t} a(s) is the coefficient of every contribution of frame t to this voxel,
 // A = prod a multiplies the old row.  All list loads of a 64-segment block are issued before the first
 // is used: the kernel lives on memory-level parallelism.
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, MB_VS_MINB)
 k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vseg, const uint32_t *__restrict__ seg_frame,
                 const float2 *__restrict__ segws, size_t cap, CellGrid g, float alpha, int T,
                 float *__restrict__ gcoef, float *__restrict__ vA, uint32_t *__restrict__ counters)
@@ -959,11 +983,8 @@ struct AccSmem {
 };
 
 template <int VEC, int IT, bool ONEHOT, int U>
-__global__ void __launch_bounds__(ACC_THREADS, (VEC * IT <= 2 ? 4 : 1))
-k_cell_accumulate(const AccArgs A)
+__device__ __forceinline__ void accumulate_round(const AccArgs &A, AccSmem &SM)
 {
-    extern __shared__ __align__(16) unsigned char acc_smem_raw[];
-    AccSmem &SM = *reinterpret_cast<AccSmem *>(acc_smem_raw);
     auto &s_coef = SM.coef; auto &s_src = SM.src; auto &s_pre = SM.pre; auto &s_ival = SM.ival; auto &s_seg = SM.seg;
     auto &s_p2i = SM.p2i;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1115,6 +1136,14 @@ k_cell_accumulate(const AccArgs A)
     }
 }
 
+template <int VEC, int IT, bool ONEHOT, int U>
+__global__ void __launch_bounds__(ACC_THREADS, (VEC * IT <= 2 ? 4 : 1))
+k_cell_accumulate(const AccArgs A)
+{
+    extern __shared__ __align__(16) unsigned char acc_smem_raw[];
+    accumulate_round<VEC, IT, ONEHOT, U>(A, *reinterpret_cast<AccSmem *>(acc_smem_raw));
+}
+
 // K8: one warp per touched voxel: map = A * map + sum of the P rows of its cells' runs (round 0), or
 // map += sum (later rounds, when the runs did not fit one P buffer).  The old row and the first two P
 // rows of every source are requested before anything is added.
@@ -1134,15 +1163,14 @@ struct ApplyArgs {
 };
 
 template <int VEC, int IT>
-__global__ void __launch_bounds__(256)
-k_voxel_apply(const ApplyArgs A)
+__device__ __forceinline__ void apply_round(const ApplyArgs &A, int chblock)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t nvox = A.counters[MB_CNT_VOX], nruns = A.counters[MB_CNT_RUNS];
     if (A.run_base >= nruns && A.run_base > 0) return;
     const uint32_t run_end = A.run_base + A.run_cap;
     const int F = A.F;
-    const int ch0 = (int)blockIdx.y * (32 * VEC * IT) + lane * VEC;
+    const int ch0 = chblock * (32 * VEC * IT) + lane * VEC;
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t j = wid; j < nvox; j += nw) {
         const uint32_t v = A.vlist[j];
@@ -1263,13 +1291,45 @@ k_voxel_apply(const ApplyArgs A)
                 row_store<VEC>(grow + ch, old[it]);
             }
         }
-        if (A.affine_a != nullptr && A.run_base == 0 && blockIdx.y == 0 && lane == 0) {
+        if (A.affine_a != nullptr && A.run_base == 0 && chblock == 0 && lane == 0) {
             // fold output: 2.0 marks a voxel no chunk has touched yet (a product of a's never exceeds 1)
             const float prev = A.affine_a[v];
             A.affine_a[v] = (prev == 2.0f ? 1.0f : prev) * a;
         }
-        if (A.vslot != nullptr && A.run_base == 0 && blockIdx.y == 0 && lane == 0)
+        if (A.vslot != nullptr && A.run_base == 0 && chblock == 0 && lane == 0)
             A.part_a[slot] = fresh ? a : A.part_a[slot] * a;
+    }
+}
+
+template <int VEC, int IT>
+__global__ void __launch_bounds__(256)
+k_voxel_apply(const ApplyArgs A)
+{
+    apply_round<VEC, IT>(A, (int)blockIdx.y);
+}
+
+// Rounds 1 .. rounds-1 of the feature pass in ONE cooperative launch.  The run buffer is sized far below the worst
+// case (every pixel its own cell), so the host plans several accumulate + apply rounds, but a real call fits the
+// first: instead of a pair of (empty) launches per planned round this kernel checks the run count on the device and,
+// in the rare case that runs are left, does the remaining rounds itself with grid-wide barriers between the phases.
+template <int VEC, int IT, bool ONEHOT, int U>
+__global__ void __launch_bounds__(ACC_THREADS, (VEC * IT <= 2 ? 4 : 1))
+k_overflow_rounds(AccArgs A, ApplyArgs Y, int rounds)
+{
+    extern __shared__ __align__(16) unsigned char acc_smem_raw[];
+    AccSmem &SM = *reinterpret_cast<AccSmem *>(acc_smem_raw);
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const uint32_t nruns = A.counters[MB_CNT_RUNS];
+    const int cblocks = (A.F + 32 * VEC * IT - 1) / (32 * VEC * IT);
+    for (int r = 1; r < rounds; ++r) {
+        const uint64_t base = (uint64_t)r * A.run_cap;
+        if (base >= nruns) break;                        // (the same decision in every thread of the grid)
+        A.run_base = Y.run_base = (uint32_t)base;
+        A.round = (uint32_t)r;
+        accumulate_round<VEC, IT, ONEHOT, U>(A, SM);
+        grid.sync();
+        for (int cb = 0; cb < cblocks; ++cb) apply_round<VEC, IT>(Y, cb);
+        grid.sync();
     }
 }
 
@@ -1390,6 +1450,49 @@ k_affine_apply_partial(float *__restrict__ map, int F, PartialView P, uint32_t c
                 row_store<VEC>(r1 + ch, m1);
             }
         }
+    }
+}
+
+// All peers' partials into local staging slots in ONE kernel: the CTAs are dealt round-robin to the world - 1 peers,
+// starting with the rank after `self`, so at every moment each rank reads from all its peers and each GPU's NVLink
+// egress serves its 7 readers evenly (applying partial g straight out of rank g's memory on every rank at once makes
+// rank g's egress the bottleneck of step g: measured 6.2 ms for 8 x 0.5 M rows against ~1 ms of link time).  A slot has
+// the layout of a partial buffer; the row count is read on the device.
+struct PullArgs {
+    const void *peer[16];           // partial buffers of all ranks (mapped peer memory), indexed by rank
+    void *slot[16];                 // local staging slot of every rank
+    int world, self;
+    uint32_t capacity;
+    int F;
+};
+
+__global__ void __launch_bounds__(256)
+k_partial_pull(const PullArgs A)
+{
+    const int npeers = A.world - 1;
+    if (npeers <= 0) return;
+    const int p = blockIdx.x % npeers, g = (A.self + 1 + p) % A.world;
+    const uint32_t cta = blockIdx.x / npeers, nctas = (gridDim.x - p + npeers - 1) / npeers;
+    size_t off[4];
+    partial_layout(A.capacity, A.F, off, nullptr);
+    const char *src = (const char *)A.peer[g];
+    char *dst = (char *)A.slot[g];
+    const uint32_t n = min(*(const volatile uint32_t *)src, A.capacity);
+    if (cta == 0 && threadIdx.x == 0) *(uint32_t *)dst = n;
+    const size_t bytes[3] = { (size_t)n * sizeof(int64_t), (size_t)n * sizeof(float), (size_t)n * A.F * sizeof(float) };
+#pragma unroll
+    for (int sec = 0; sec < 3; ++sec) {
+        const uint4 *s4 = (const uint4 *)(src + off[sec + 1]);
+        uint4 *d4 = (uint4 *)(dst + off[sec + 1]);
+        const size_t n16 = (bytes[sec] + 15) / 16;                     // (sections are padded to 256 bytes)
+        size_t i = (size_t)cta * 256 + threadIdx.x;
+        const size_t stride = (size_t)nctas * 256;
+        // four independent 16-byte loads in flight per thread: the link latency is a few microseconds
+        for (; i + 3 * stride < n16; i += 4 * stride) {
+            const uint4 v0 = s4[i], v1 = s4[i + stride], v2 = s4[i + 2 * stride], v3 = s4[i + 3 * stride];
+            d4[i] = v0; d4[i + stride] = v1; d4[i + 2 * stride] = v2; d4[i + 3 * stride] = v3;
+        }
+        for (; i < n16; i += stride) d4[i] = s4[i];
     }
 }
 
@@ -1517,7 +1620,7 @@ int dispatch_accumulate(cudaStream_t stream, const AccArgs &A, int vec, int it)
 #define MB_ACC(V, I, UU)                                                              \
     if (vec == V && it == I)                                                          \
         return oh ? launch_accumulate<V, I, true, UU>(stream, A) : launch_accumulate<V, I, false, UU>(stream, A)
-    MB_ACC(1, 1, 8); MB_ACC(1, 2, 4); MB_ACC(2, 1, 8); MB_ACC(2, 2, 4); MB_ACC(4, 1, 4); MB_ACC(4, 2, 2);
+    MB_ACC(1, 1, 8); MB_ACC(1, 2, 4); MB_ACC(2, 1, MB_ACC_U21); MB_ACC(2, 2, 4); MB_ACC(4, 1, 4); MB_ACC(4, 2, 2);
 #undef MB_ACC
     mb_set_error("internal: no accumulate kernel for vec %d it %d", vec, it);
     return MB_ERR_ARG;
@@ -1531,6 +1634,37 @@ int launch_apply(cudaStream_t stream, const ApplyArgs &A)
     k_voxel_apply<VEC, IT><<<grid, 256, 0, stream>>>(A);
     MB_LAUNCHED();
     return MB_OK;
+}
+
+template <int VEC, int IT, bool ONEHOT, int U>
+int launch_overflow(cudaStream_t stream, const AccArgs &A, const ApplyArgs &Y, int rounds)
+{
+    auto kern = k_overflow_rounds<VEC, IT, ONEHOT, U>;
+    int per_sm = 1;
+    MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccSmem)));
+    MB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ACC_THREADS, sizeof(AccSmem)));
+    if (per_sm < 1) per_sm = 1;
+    AccArgs a = A;
+    ApplyArgs y = Y;
+    int r = rounds;
+    void *args[] = { &a, &y, &r };
+    // cooperative: every CTA is resident (grid = SMs x occupancy), so the grid-wide barriers between the phases are safe
+    MB_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(MB_NUM_SMS * per_sm), dim3(ACC_THREADS), args,
+                                              sizeof(AccSmem), stream));
+    MB_LAUNCHED();
+    return MB_OK;
+}
+
+int dispatch_overflow(cudaStream_t stream, const AccArgs &A, const ApplyArgs &Y, int rounds, int vec, int it)
+{
+    const bool oh = A.class_ids != nullptr;
+#define MB_OVF(V, I, UU)                                                              \
+    if (vec == V && it == I)                                                          \
+        return oh ? launch_overflow<V, I, true, UU>(stream, A, Y, rounds) : launch_overflow<V, I, false, UU>(stream, A, Y, rounds)
+    MB_OVF(1, 1, 8); MB_OVF(1, 2, 4); MB_OVF(2, 1, MB_ACC_U21); MB_OVF(2, 2, 4); MB_OVF(4, 1, 4); MB_OVF(4, 2, 2);
+#undef MB_OVF
+    mb_set_error("internal: no overflow kernel for vec %d it %d", vec, it);
+    return MB_ERR_ARG;
 }
 
 int dispatch_apply(cudaStream_t stream, const ApplyArgs &A, int vec, int it)
@@ -1606,6 +1740,19 @@ int mbk_partial_clear(cudaStream_t stream, int32_t *slot_table, void *buffer, ui
     k_partial_clear<<<MB_NUM_SMS * 4, 256, 0, stream>>>(slot_table, partial_view(buffer, capacity, F), capacity);
     MB_LAUNCHED();
     MB_CHECK_CUDA(cudaMemsetAsync(buffer, 0, 256, stream));
+    return MB_OK;
+}
+
+int mbk_partial_pull(cudaStream_t stream, const void *const *peer_buffers_host, void *const *slots_host, int world,
+                     int self, uint32_t capacity, int F)
+{
+    MB_REQUIRE(world >= 1 && world <= 16 && self >= 0 && self < world, "mb_partial_pull: at most 16 ranks");
+    if (world == 1) return MB_OK;
+    PullArgs A;
+    for (int g = 0; g < 16; ++g) { A.peer[g] = g < world ? peer_buffers_host[g] : nullptr; A.slot[g] = g < world ? slots_host[g] : nullptr; }
+    A.world = world; A.self = self; A.capacity = capacity; A.F = F;
+    k_partial_pull<<<MB_NUM_SMS * 8, 256, 0, stream>>>(A);
+    MB_LAUNCHED();
     return MB_OK;
 }
 
@@ -1805,13 +1952,14 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
         MB_LAUNCHED();
         Y.vslot = b.vslot; Y.part_a = pv.a; Y.part_b = pv.b; Y.map = pv.b;
     }
-    for (int r = 0; r < rounds; ++r) {
-        A.run_base = Y.run_base = (uint32_t)r * run_cap;
-        A.round = (uint32_t)r;
-        if (r == 0 && (rc = stage_mark(stream, 4))) return rc;
-        if ((rc = dispatch_accumulate(stream, A, vec, it))) return rc;
-        if (r == 0 && (rc = stage_mark(stream, 5))) return rc;
-        if ((rc = dispatch_apply(stream, Y, vec, it))) return rc;
-    }
+    // round 0 holds every run of a real call; the rounds the worst case would need beyond it are one cooperative launch
+    // that looks at the run count on the device
+    A.run_base = Y.run_base = 0;
+    A.round = 0;
+    if ((rc = stage_mark(stream, 4))) return rc;
+    if ((rc = dispatch_accumulate(stream, A, vec, it))) return rc;
+    if ((rc = stage_mark(stream, 5))) return rc;
+    if ((rc = dispatch_apply(stream, Y, vec, it))) return rc;
+    if (rounds > 1 && (rc = dispatch_overflow(stream, A, Y, rounds, vec, it))) return rc;
     return stage_mark(stream, 6);
 }

@@ -71,6 +71,8 @@ size_t mbk_partial_buffer_layout(uint32_t capacity, int F, size_t *offsets);
 int mbk_partial_reset(cudaStream_t stream, int32_t *slot_table, int64_t voxels, void *buffer);
 int mbk_partial_clear(cudaStream_t stream, int32_t *slot_table, void *buffer, uint32_t capacity, int F);
 int mbk_affine_apply_partial(cudaStream_t stream, float *map, int F, const void *buffer, uint32_t capacity);
+int mbk_partial_pull(cudaStream_t stream, const void *const *peer_buffers_host, void *const *slots_host, int world,
+                     int self, uint32_t capacity, int F);
 
 int mbk_affine_apply_rows(cudaStream_t stream, float *map, int F, const int64_t *idx, const float *a, const float *b,
                           int64_t n);

@@ -116,7 +116,7 @@ struct TcArgs {
 };
 
 template <int PASS>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 3)
 k_cosine_tc(const TcArgs A)
 {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];

@@ -135,6 +135,7 @@ class PeerExchange:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.partial = SparsePartial(layer, capacity, peer=True)
         self.capacity = int(capacity)
+        self._slots = self._stage = None
         handles = [None] * self.world
         dist.all_gather_object(handles, (self.partial.handle(), self.capacity), group=group)
         L = _lib.lib()
@@ -151,11 +152,39 @@ class PeerExchange:
                 self.ptrs.append(p)
                 self._opened.append(p)
 
-    def combine(self, layer):
+    def _staging(self):
+        """world - 1 local slots the peers' partials are pulled into (allocated on first use)."""
+        if self._slots is None:
+            n = self.partial.nbytes
+            self._stage = torch.empty(max(self.world - 1, 1) * n, dtype=torch.uint8, device=self.partial.device)
+            base, k = self._stage.data_ptr(), 0
+            self._slots = []
+            for g in range(self.world):
+                if g == self.rank:
+                    self._slots.append(self.partial.buffer_ptr)          # my own partial is applied where it is
+                else:
+                    self._slots.append(ctypes.c_void_p(base + k * n))
+                    k += 1
+        return self._slots
+
+    def combine(self, layer, pull=True):
+        """Applies every rank's partial to layer.data in rank (= time) order.  pull=True (default): ONE kernel first
+        copies all peers' rows into local staging slots, reading from every peer at once, then the partials are
+        applied from local memory; pull=False: partial g is applied straight out of rank g's memory (every rank reads
+        the same owner at the same time: that owner's link is the bottleneck of its step)."""
         dev = self.partial.device
         _rank_barrier(self.group, dev)                      # every rank's fold is complete
-        for g in range(self.world):                         # rank order = time order
-            apply_partial_buffer(layer, self.ptrs[g], self.capacity)
+        if pull and self.world > 1:
+            slots = self._staging()
+            arr = ctypes.c_void_p * self.world
+            _lib.check(_lib.lib().mb_partial_pull(
+                _lib.stream_ptr(dev), arr(*[p.value for p in self.ptrs]), arr(*[p.value for p in slots]), self.world,
+                self.rank, self.capacity, self.partial.features))
+            for g in range(self.world):                     # rank order = time order
+                apply_partial_buffer(layer, slots[g], self.capacity)
+        else:
+            for g in range(self.world):
+                apply_partial_buffer(layer, self.ptrs[g], self.capacity)
         _rank_barrier(self.group, dev)                      # nobody still reads my rows
         self.partial.clear()
         return layer

@@ -72,9 +72,14 @@ def main():
         half = len(mine) // 2
         if half:                                       # a rank folds its chunk in two pieces (ring by ring)
             ex.partial.fold(layer, mine[:half])
-        sharded.update_batch_sharded(layer, mine[half:], exchange=ex)
+        if rep == 0:                                   # pull all peers' rows, then apply locally
+            sharded.update_batch_sharded(layer, mine[half:], exchange=ex)
+        else:                                          # apply straight out of the owners' memory
+            if mine[half:]:
+                ex.partial.fold(layer, mine[half:])
+            ex.combine(layer, pull=False)
         layer.check()
-        good &= verdict(layer, "peer exchange (pass %d)" % rep)
+        good &= verdict(layer, "peer exchange (%s)" % ("pulled" if rep == 0 else "read in place"))
     ex.close()
     dist.barrier()
     dist.destroy_process_group()
