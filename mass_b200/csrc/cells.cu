@@ -34,6 +34,7 @@
 // run to run.
 // Weights follow the reference's fp32 operation order; occupancy is bit-exact and values differ from
 // the reference CPU path by fp32 re-association only (<= 1e-5 relative).
+#include <cstdlib>
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "kernels.cuh"
@@ -128,7 +129,7 @@ __device__ __forceinline__ int find_cell(const uint32_t *__restrict__ ucell, uin
 //   item value = tile << 12 | first slot << 4 | (length - 1);  pixel record = {ratio0, ratio1, ratio2, pixel in tile}
 constexpr int TILE_W = 32, TILE_H = 8, TILE_PIX = TILE_W * TILE_H;
 #ifndef MB_WHASH
-#define MB_WHASH 512
+#define MB_WHASH 256
 #endif
 #ifndef MB_TG_MINB
 #define MB_TG_MINB 4
@@ -1960,6 +1961,13 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     if ((rc = dispatch_accumulate(stream, A, vec, it))) return rc;
     if ((rc = stage_mark(stream, 5))) return rc;
     if ((rc = dispatch_apply(stream, Y, vec, it))) return rc;
-    if (rounds > 1 && (rc = dispatch_overflow(stream, A, Y, rounds, vec, it))) return rc;
+    static const bool no_coop = getenv("MASSB200_NO_COOP") != nullptr;        // measurement aid: one launch pair per round
+    if (rounds > 1 && !no_coop && (rc = dispatch_overflow(stream, A, Y, rounds, vec, it))) return rc;
+    for (int r = 1; r < rounds && no_coop; ++r) {
+        A.run_base = Y.run_base = (uint32_t)r * run_cap;
+        A.round = (uint32_t)r;
+        if ((rc = dispatch_accumulate(stream, A, vec, it))) return rc;
+        if ((rc = dispatch_apply(stream, Y, vec, it))) return rc;
+    }
     return stage_mark(stream, 6);
 }
