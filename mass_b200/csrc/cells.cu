@@ -266,23 +266,43 @@ k_cell_voxelise(const float *__restrict__ rays, const float *__restrict__ depth,
 }
 
 struct __align__(16) WarpTile {
+    uint4 px[TILE_PIX];                          // the tile's pixels {key, 3 ratios}, image order (bulk-copied in)
     uint32_t hkey[WHASH];
     uint16_t cnt[WHASH], start[WHASH];
+    uint64_t bar;                                // counts the bytes of the tile's bulk copies
 };
 
+__device__ __forceinline__ uint32_t tile_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 // K1b: one warp per 32 x 8 tile groups the tile's pixels by cell (see above) and writes the grouped records
-// and the tile's items.
+// and the tile's items.  The tile (8 image rows of 512 contiguous bytes) comes in through the TMA engine's linear mode:
+// lane 0 issues one bulk copy per row and the warp waits on its own mbarrier, the hash table being cleared meanwhile;
+// keys and records are then read from shared memory.
 __global__ void __launch_bounds__(256, MB_TG_MINB)
 k_tile_group(const uint4 *__restrict__ pix, TileGeom tg, uint32_t ntiles, uint4 *__restrict__ rec,
              uint32_t *__restrict__ tkey, uint32_t *__restrict__ tval, uint32_t *__restrict__ tcount)
 {
-    __shared__ WarpTile s_w[8];
+    extern __shared__ __align__(16) unsigned char tile_smem_raw[];
+    WarpTile *s_w = reinterpret_cast<WarpTile *>(tile_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x * 8u + warp;
     if (tile >= ntiles) return;
     WarpTile &S = s_w[warp];
     const uint32_t frame = tile / (uint32_t)tg.tpf, tif = tile - frame * (uint32_t)tg.tpf;
     const int y0 = (int)(tif / (uint32_t)tg.tiles_x) * TILE_H, x0 = (int)(tif % (uint32_t)tg.tiles_x) * TILE_W;
+    const size_t fbase = (size_t)frame * tg.H * tg.W;
+    const int cols = min(TILE_W, tg.W - x0), rows = min(TILE_H, tg.H - y0);
+    const uint32_t bar = tile_smem_addr(&S.bar);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t row_bytes = (uint32_t)cols * 16u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (uint32_t)rows) : "memory");
+        for (int r = 0; r < rows; ++r)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tile_smem_addr(&S.px[r * TILE_W])), "l"(pix + fbase + (size_t)(y0 + r) * tg.W + x0), "r"(row_bytes),
+                           "r"(bar) : "memory");
+    }
     {
         // clear the table with 16-byte stores (WHASH keys = WHASH / 4 pieces, WHASH counters = WHASH / 8 pieces)
         uint4 *hk = reinterpret_cast<uint4 *>(S.hkey), *ct = reinterpret_cast<uint4 *>(S.cnt);
@@ -293,15 +313,19 @@ k_tile_group(const uint4 *__restrict__ pix, TileGeom tg, uint32_t ntiles, uint4 
         for (int i = lane; i < WHASH / 8; i += 32) ct[i] = z4;
     }
     const uint32_t ltmask = (1u << lane) - 1u;
-    const size_t fbase = (size_t)frame * tg.H * tg.W;
-    const int x = x0 + lane;
-    uint32_t pkey[TILE_H];                            // keys of the lane's 8 pixels: column x, rows y0 .. y0 + 7
+    __syncwarp();
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar) : "memory");
+    }
+    uint32_t pkey[TILE_H];                            // keys of the lane's 8 pixels: column x0 + lane, rows y0 .. y0 + 7
 #pragma unroll
     for (int r = 0; r < TILE_H; ++r) {
         pkey[r] = 0xffffffffu;
-        if (y0 + r < tg.H && x < tg.W) pkey[r] = __ldg(pix + fbase + (size_t)(y0 + r) * tg.W + x).x;
+        if (r < rows && lane < cols) pkey[r] = S.px[r * TILE_W + lane].x;
     }
-    __syncwarp();
     uint32_t sr[TILE_H];                              // slot | rank << 16 (slot WHASH: invalid pixel)
     // ---- one grouping round per image row ------------------------------------------------------------------------
 #pragma unroll
@@ -369,7 +393,7 @@ k_tile_group(const uint4 *__restrict__ pix, TileGeom tg, uint32_t ntiles, uint4 
         const uint32_t sl = sr[r] & 0xffffu;
         if (sl < WHASH) {
             const uint32_t pos = (uint32_t)S.start[sl] + (sr[r] >> 16);
-            const uint4 px = __ldg(pix + fbase + (size_t)(y0 + r) * tg.W + x);       // second read: L2
+            const uint4 px = S.px[r * TILE_W + lane];
             rec[tbase + pos] = make_uint4(px.y, px.z, px.w, (uint32_t)(r * TILE_W + lane));
         }
     }
@@ -1872,7 +1896,8 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     k_cell_voxelise<<<vgrid, 256, 0, stream>>>(rays, depth, pose, npix, bins_x, nx, bins_y, ny, bins_z, nz, g, min_d, max_d,
                                                b.pix, b.counters);
     MB_LAUNCHED();
-    k_tile_group<<<(ntiles + 7) / 8, 256, 0, stream>>>(b.pix, tg, ntiles, b.rec, tkey, tval, b.tcount);
+    MB_CHECK_CUDA(cudaFuncSetAttribute(k_tile_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(WarpTile))));
+    k_tile_group<<<(ntiles + 7) / 8, 256, 8 * sizeof(WarpTile), stream>>>(b.pix, tg, ntiles, b.rec, tkey, tval, b.tcount);
     MB_LAUNCHED();
     if ((rc = mb_exclusive_scan_small(stream, b.tcount, b.toff, ntiles, b.scan_state))) return rc;
     k_tile_compact<<<(ntiles + 7) / 8, 256, 0, stream>>>(tkey, tval, b.tcount, b.toff, ntiles, b.keys_a, b.pids_a,

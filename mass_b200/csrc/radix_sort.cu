@@ -234,13 +234,29 @@ k_radix_block_hist(const uint32_t *__restrict__ keys, uint32_t n, const uint32_t
     table[threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];      // digit-major
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+// Bulk asynchronous copies (the TMA engine's linear mode, SASS UBLKCP): one thread hands a whole contiguous tile to the
+// copy engine and the CTA waits on an mbarrier that counts the bytes; no per-thread load instructions at all.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
 
 // Shared memory of k_radix_block_scatter (dynamic): two input buffers of one tile each (keys, values),
 // filled by cp.async one tile ahead of the tile being ranked, and the sorted staging area.
@@ -249,6 +265,7 @@ struct ScatterSmem {
     uint32_t s_key[OS_TILE], s_val[OS_TILE];
     uint32_t wcnt[OS_THREADS / 32][256];
     uint32_t s_dstart[256], s_gpos[256];
+    uint64_t bar[2];                             // one per input buffer: counts the bytes of its bulk copies
 };
 
 __global__ void __launch_bounds__(OS_THREADS, 2)
@@ -267,26 +284,35 @@ k_radix_block_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__re
     }
     const uint32_t beg = min(n, blockIdx.x * per_block), end = min(n, beg + per_block);
     S.s_gpos[tid] = table[tid * gridDim.x + blockIdx.x];
+    if (tid == 0) {
+        mbar_init(&S.bar[0], 1);
+        mbar_init(&S.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
-    // a tile is fetched in 16-byte pieces (beg is a multiple of the tile; the array tails are padded by the
-    // allocation: pieces that start before `end` are always in bounds of a 16-byte aligned buffer)
+    // a tile (16 KB of keys + 16 KB of values, contiguous) is fetched by ONE thread as two bulk copies, a multiple of
+    // 16 bytes each (beg is a multiple of the tile; the array tails are padded by the allocation: a piece that starts
+    // before `end` is always in bounds of the 16-byte aligned buffer)
     auto fetch = [&](uint32_t tbase, int buf) {
-        for (int c = tid; c < OS_TILE / 4; c += OS_THREADS) {
-            const uint32_t idx = tbase + 4u * c;
-            if (idx < end) {
-                cp_async16(&S.in_key[buf][4 * c], keys_in + idx);
-                if (!vals_iota) cp_async16(&S.in_val[buf][4 * c], vals_in + idx);
-            }
+        if (tid == 0) {
+            const uint32_t cnt = min((uint32_t)OS_TILE, end - tbase);
+            const uint32_t bytes = (cnt * 4u + 15u) & ~15u;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier reads of the buffer are done
+            mbar_expect_tx(&S.bar[buf], vals_iota ? bytes : 2u * bytes);
+            bulk_g2s(&S.in_key[buf][0], keys_in + tbase, bytes, &S.bar[buf]);
+            if (!vals_iota) bulk_g2s(&S.in_val[buf][0], vals_in + tbase, bytes, &S.bar[buf]);
         }
-        cp_async_commit();
     };
     if (beg < end) fetch(beg, 0);
     int buf = 0;
+    uint32_t phase[2] = { 0u, 0u };
     for (uint32_t tbase = beg; tbase < end; tbase += OS_TILE, buf ^= 1) {
         for (int i = tid; i < WARPS * R; i += OS_THREADS) (&S.wcnt[0][0])[i] = 0;
-        cp_async_wait_all();
-        __syncthreads();                          // this tile's input is in shared memory; staging area is free
+        __syncthreads();                          // the staging area and the other input buffer are free
         if (tbase + OS_TILE < end) fetch(tbase + OS_TILE, buf ^ 1);      // next tile, while this one is ranked
+        mbar_wait(&S.bar[buf], phase[buf]);       // this tile's input has landed in shared memory
+        phase[buf] ^= 1u;
         const uint32_t tile_n = min((uint32_t)OS_TILE, end - tbase);
         const uint32_t wloc = warp * (32 * OS_ITEMS);
         uint32_t k[OS_ITEMS];
