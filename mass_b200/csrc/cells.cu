@@ -144,7 +144,7 @@ constexpr int TILE_W = 32, TILE_H = 8, TILE_PIX = TILE_W * TILE_H;
 #define MB_ACC_U21 8
 #endif
 #ifndef MB_SEG_MINB
-#define MB_SEG_MINB 1
+#define MB_SEG_MINB 5
 #endif
 #ifndef MB_VS_MINB
 #define MB_VS_MINB 4
