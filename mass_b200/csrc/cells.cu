@@ -685,13 +685,24 @@ k_seg_sums(const uint32_t *__restrict__ ival, const uint4 *__restrict__ rec, con
            float2 *__restrict__ segws, size_t cap, const uint32_t *__restrict__ counters)
 {
     const uint32_t nsegs = counters[MB_CNT_SEGS];
-    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nsegs; s += gridDim.x * blockDim.x) {
-        const uint32_t beg = seg_start[s], end = seg_start[s + 1];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsegs) return;
+    // The loads of a segment form a chain (segment bounds -> item -> records); the kernel is bound by that latency, not
+    // by its arithmetic.  So the bounds and the first item of the NEXT segment of this thread are requested before the
+    // current one is processed: only the record loads remain on the critical path.
+    uint32_t beg = __ldg(seg_start + s), end = __ldg(seg_start + s + 1);
+    uint32_t v0 = __ldg(ival + beg);
+    for (;;) {
+        const uint32_t sn = s + stride;
+        const bool more = sn < nsegs;
+        uint32_t nbeg = 0, nend = 0;
+        if (more) { nbeg = __ldg(seg_start + sn); nend = __ldg(seg_start + sn + 1); }
         float W[8], S2[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { W[k] = 0.f; S2[k] = 0.f; }
         for (uint32_t it = beg; it < end; ++it) {
-            const uint32_t v = ival[it];
+            const uint32_t v = it == beg ? v0 : __ldg(ival + it);
             const uint4 *pr = rec + (size_t)item_tile(v) * TILE_PIX + item_pos(v);
             const uint32_t len = item_len(v);
             for (uint32_t i = 0; i < len; i += 4) {
@@ -709,8 +720,12 @@ k_seg_sums(const uint32_t *__restrict__ ival, const uint4 *__restrict__ rec, con
                     }
             }
         }
+        uint32_t nv0 = 0;
+        if (more) nv0 = __ldg(ival + nbeg);             // (its address arrived while the records were being summed)
 #pragma unroll
         for (int k = 0; k < 8; ++k) segws[(size_t)k * cap + s] = make_float2(W[k], S2[k]);    // slot-major
+        if (!more) break;
+        s = sn; beg = nbeg; end = nend; v0 = nv0;
     }
 }
 
@@ -840,7 +855,7 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vs
             const int base = row << 5;
             const float W = tW[base + lane], S2 = tS[base + lane];
             float r = 0.f, a = 1.0f;
-            if (W > 0.f) { r = alpha / W; a = 1.0f - r * S2; }
+            if (W > 0.f) { r = __fdividef(alpha, W); a = 1.0f - r * S2; }      // (2 ulp: far inside the 1e-5 budget)
             nvt += __popc(__ballot_sync(FULL, W > 0.f));
             float inc = a;                             // inclusive product over lanes >= lane
 #pragma unroll
