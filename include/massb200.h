@@ -236,7 +236,7 @@ int mb_cosine_best_match(void *stream, const float *a, int n, const float *b, in
  * real dense contraction -- on the tcgen05 tensor cores: A B^T in 3 x TF32 with fp32 accumulators in TMEM ranks the
  * candidates, every column within 2e-3 of a row's largest approximate cosine is re-evaluated exactly.  Workspace from
  * mb_cosine_best_match_tc_workspace_bytes.  (No reference counterpart: SURVEY.md F3.) */
-size_t mb_cosine_best_match_tc_workspace_bytes(int n, int m);
+size_t mb_cosine_best_match_tc_workspace_bytes(int n, int m, int d);
 int mb_cosine_best_match_tc(void *stream, const float *a, int n, const float *b, int m, int d, int64_t *best,
                             float *best_sim, void *workspace, size_t workspace_bytes);
 size_t mb_lsap_workspace_bytes(int n, int m);

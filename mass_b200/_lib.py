@@ -119,7 +119,7 @@ _SIGNATURES = {
     "mb_nav_rects_clear": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _vp]),
     "mb_pairwise_l2": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp]),
     "mb_cosine_best_match": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp]),
-    "mb_cosine_best_match_tc_workspace_bytes": (_sz, [_i32, _i32]),
+    "mb_cosine_best_match_tc_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "mb_cosine_best_match_tc": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _sz]),
     "mb_lsap_workspace_bytes": (_sz, [_i32, _i32]),
     "mb_lsap": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz]),

@@ -541,10 +541,10 @@ MB_API int mb_cosine_best_match(void *stream, const float *a, int n, const float
     return mbk_cosine_best_match((cudaStream_t)stream, a, n, b, m, d, best, best_sim);
 }
 
-MB_API size_t mb_cosine_best_match_tc_workspace_bytes(int n, int m)
+MB_API size_t mb_cosine_best_match_tc_workspace_bytes(int n, int m, int d)
 {
-    if (n <= 0) return 256;
-    return mbk_cosine_tc_workspace_bytes(n, m > 0 ? m : 1);
+    if (n <= 0 || d <= 0) return 256;
+    return mbk_cosine_tc_workspace_bytes(n, m > 0 ? m : 1, d);
 }
 
 MB_API int mb_cosine_best_match_tc(void *stream, const float *a, int n, const float *b, int m, int d, int64_t *best,

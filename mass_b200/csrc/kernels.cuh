@@ -108,6 +108,6 @@ int mbk_nav_edges(cudaStream_t stream, const float *navigable, int S0, int S1, i
 int mbk_nav_rects(cudaStream_t stream, const float *navigable, int S1, const int32_t *rects, int m, uint8_t *clear);
 
 // tc_match.cu: cosine similarity + best match on tcgen05 tensor cores (large instance matrices)
-size_t mbk_cosine_tc_workspace_bytes(int n, int m);
+size_t mbk_cosine_tc_workspace_bytes(int n, int m, int d);
 int mbk_cosine_best_match_tc(cudaStream_t stream, const float *a, int n, const float *b, int m, int d, int64_t *best,
                              float *best_sim, void *workspace, size_t workspace_bytes);

@@ -214,7 +214,7 @@ def cosine_best_match(a, b, tensor_cores=None):
         tensor_cores = a.shape[0] >= 1024 and b.shape[0] >= 1024 and a.shape[1] >= 32
     if tensor_cores and a.shape[0] > 0:
         L = _lib.lib()
-        nbytes = int(L.mb_cosine_best_match_tc_workspace_bytes(a.shape[0], b.shape[0]))
+        nbytes = int(L.mb_cosine_best_match_tc_workspace_bytes(a.shape[0], b.shape[0], a.shape[1]))
         ws = _ws.get(nbytes, device)
         _lib.check(L.mb_cosine_best_match_tc(_lib.stream_ptr(device), _lib.ptr(a), a.shape[0], _lib.ptr(b), b.shape[0],
                                              a.shape[1], _lib.ptr(best), _lib.ptr(sim), _lib.ptr(ws), nbytes))
