@@ -35,6 +35,7 @@
 // Weights follow the reference's fp32 operation order; occupancy is bit-exact and values differ from
 // the reference CPU path by fp32 re-association only (<= 1e-5 relative).
 #include <cstdlib>
+#include <mutex>
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "kernels.cuh"
@@ -165,7 +166,20 @@ __device__ __forceinline__ uint32_t item_len(uint32_t v) { return (v & 15u) + 1u
 struct TileGeom {
     int H, W;                // camera
     int tiles_x, tpf;        // tiles per image row, tiles per frame
+    uint32_t tpf_magic, tx_magic;     // ceil(2^32 / d) for the two divisors (0: divide)
 };
+
+// x / d for x < 2^20 (tile ids) as one multiply-high: with m = ceil(2^32 / d) and e = m * d - 2^32 < d the product
+// x * m / 2^32 exceeds x / d by x * e / (d * 2^32) < 1 / d as long as x * e < 2^32, which d <= 4096 guarantees.
+__host__ __device__ inline uint32_t div_magic(uint32_t d)
+{
+    return d >= 2u && d <= 4096u ? (uint32_t)((((uint64_t)1 << 32) + d - 1) / d) : 0u;
+}
+
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t d, uint32_t magic)
+{
+    return magic ? __umulhi(x, magic) : x / d;
+}
 
 __host__ __device__ inline TileGeom make_tiles(int H, int W)
 {
@@ -173,6 +187,8 @@ __host__ __device__ inline TileGeom make_tiles(int H, int W)
     t.H = H; t.W = W;
     t.tiles_x = (W + TILE_W - 1) / TILE_W;
     t.tpf = t.tiles_x * ((H + TILE_H - 1) / TILE_H);
+    t.tpf_magic = div_magic((uint32_t)t.tpf);
+    t.tx_magic = div_magic((uint32_t)t.tiles_x);
     return t;
 }
 
@@ -288,8 +304,9 @@ k_tile_group(const uint4 *__restrict__ pix, TileGeom tg, uint32_t ntiles, uint4 
     const uint32_t tile = blockIdx.x * 8u + warp;
     if (tile >= ntiles) return;
     WarpTile &S = s_w[warp];
-    const uint32_t frame = tile / (uint32_t)tg.tpf, tif = tile - frame * (uint32_t)tg.tpf;
-    const int y0 = (int)(tif / (uint32_t)tg.tiles_x) * TILE_H, x0 = (int)(tif % (uint32_t)tg.tiles_x) * TILE_W;
+    const uint32_t frame = fast_div(tile, (uint32_t)tg.tpf, tg.tpf_magic), tif = tile - frame * (uint32_t)tg.tpf;
+    const uint32_t tyo = fast_div(tif, (uint32_t)tg.tiles_x, tg.tx_magic);
+    const int y0 = (int)tyo * TILE_H, x0 = (int)(tif - tyo * (uint32_t)tg.tiles_x) * TILE_W;
     const size_t fbase = (size_t)frame * tg.H * tg.W;
     const int cols = min(TILE_W, tg.W - x0), rows = min(TILE_H, tg.H - y0);
     const uint32_t bar = tile_smem_addr(&S.bar);
@@ -298,11 +315,12 @@ k_tile_group(const uint4 *__restrict__ pix, TileGeom tg, uint32_t ntiles, uint4 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t row_bytes = (uint32_t)cols * 16u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (uint32_t)rows) : "memory");
-        for (int r = 0; r < rows; ++r)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(tile_smem_addr(&S.px[r * TILE_W])), "l"(pix + fbase + (size_t)(y0 + r) * tg.W + x0), "r"(row_bytes),
-                           "r"(bar) : "memory");
     }
+    __syncwarp();
+    if (lane < rows)                                   // one row per lane: the eight copies are issued in one go
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(tile_smem_addr(&S.px[lane * TILE_W])), "l"(pix + fbase + (size_t)(y0 + lane) * tg.W + x0),
+                       "r"((uint32_t)cols * 16u), "r"(bar) : "memory");
     {
         // clear the table with 16-byte stores (WHASH keys = WHASH / 4 pieces, WHASH counters = WHASH / 8 pieces)
         uint4 *hk = reinterpret_cast<uint4 *>(S.hkey), *ct = reinterpret_cast<uint4 *>(S.cnt);
@@ -442,7 +460,7 @@ struct IndexOut {
 
 __global__ void __launch_bounds__(256)
 k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sval, const uint32_t *__restrict__ n_dev,
-             uint32_t tpf, CellGrid g, const IndexOut O)
+             TileGeom tg, CellGrid g, const IndexOut O)
 {
     __shared__ uint32_t s_tile, s_wsum[8][2], s_base[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -473,7 +491,8 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
         pv = __shfl_sync(FULL, val[r], 31);
         const bool valid = i < n;
         const bool chead = valid && (i == 0 || kprev != key[r]);
-        const bool shead = valid && (chead || item_tile(vprev) / tpf != item_tile(val[r]) / tpf);
+        const uint32_t tpf = (uint32_t)tg.tpf;
+        const bool shead = valid && (chead || fast_div(item_tile(vprev), tpf, tg.tpf_magic) != fast_div(item_tile(val[r]), tpf, tg.tpf_magic));
         cm[r] = __ballot_sync(FULL, chead);
         sm[r] = __ballot_sync(FULL, shead);
         cw += __popc(cm[r]); sw += __popc(sm[r]);
@@ -521,7 +540,7 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
             const uint32_t crank = cb + __popc(cm[r] & lt), srank = sb + __popc(sm[r] & lt);
             if ((sm[r] >> lane) & 1u) {
                 O.seg_start[srank] = i;
-                O.seg_frame[srank] = item_tile(val[r]) / tpf;
+                O.seg_frame[srank] = fast_div(item_tile(val[r]), (uint32_t)tg.tpf, tg.tpf_magic);
             }
             if ((cm[r] >> lane) & 1u) {
                 const uint32_t k = key[r];
@@ -1083,6 +1102,8 @@ __device__ __forceinline__ void accumulate_round(const AccArgs &A, AccSmem &SM)
             for (int it = 0; it < IT; ++it)
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) acc[k][it][j] = 0.f;
+        const char *fbase = (const char *)(A.features + ch0);          // this lane's first channel of row 0
+        const uint32_t row_bytes = (uint32_t)F * (uint32_t)sizeof(float);
 
         for (uint32_t b0 = 0; b0 < npixels; b0 += 32) {
             // ---- lanes = pixels: coefficients of the batch ------------------------------------------------
@@ -1102,8 +1123,8 @@ __device__ __forceinline__ void accumulate_round(const AccArgs &A, AccSmem &SM)
                     splat_weights(r, c);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) c[k] = c[k] * c[k] * gk[k];
-                    const uint32_t frame = tile / (uint32_t)A.tg.tpf, tif = tile - frame * (uint32_t)A.tg.tpf;
-                    const uint32_t tyo = tif / (uint32_t)A.tg.tiles_x, txo = tif - tyo * (uint32_t)A.tg.tiles_x;
+                    const uint32_t frame = fast_div(tile, (uint32_t)A.tg.tpf, A.tg.tpf_magic), tif = tile - frame * (uint32_t)A.tg.tpf;
+                    const uint32_t tyo = fast_div(tif, (uint32_t)A.tg.tiles_x, A.tg.tx_magic), txo = tif - tyo * (uint32_t)A.tg.tiles_x;
                     const uint32_t y = tyo * TILE_H + (r.w >> 5), x = txo * TILE_W + (r.w & 31u);
                     if (ONEHOT) {
                         const int64_t id = A.class_ids[(size_t)frame * np + y * A.fi.W + x];
@@ -1135,9 +1156,20 @@ __device__ __forceinline__ void accumulate_round(const AccArgs &A, AccSmem &SM)
             const int nb = (int)min(32u, npixels - b0);
             for (int jj = 0; jj < nb; jj += U) {
                 float f[U][IT][VEC];
+                uint32_t srcs[U];                                         // (jj is a multiple of U: 16-byte pieces)
+                if (U % 4 == 0) {
+#pragma unroll
+                    for (int u = 0; u < U; u += 4) {
+                        const uint4 q = *(const uint4 *)&s_src[warp][jj + u];
+                        srcs[u] = q.x; srcs[u + 1 < U ? u + 1 : u] = q.y; srcs[u + 2 < U ? u + 2 : u] = q.z; srcs[u + 3 < U ? u + 3 : u] = q.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) srcs[u] = s_src[warp][jj + u];
+                }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const uint32_t src = s_src[warp][jj + u];
+                    const uint32_t src = srcs[u];
 #pragma unroll
                     for (int it = 0; it < IT; ++it) {
                         const int ch = ch0 + it * 32 * VEC;
@@ -1145,7 +1177,8 @@ __device__ __forceinline__ void accumulate_round(const AccArgs &A, AccSmem &SM)
 #pragma unroll
                             for (int j = 0; j < VEC; ++j) f[u][it][j] = (uint32_t)(ch + j) == src ? 1.0f : 0.0f;
                         } else if (ch < F) {
-                            feat_load<VEC>(f[u][it], A.features + (size_t)src * F + ch);
+                            // one 32 x 32 -> 64-bit multiply-add per row address (row index x row bytes + lane base)
+                            feat_load<VEC>(f[u][it], (const float *)(fbase + (uint64_t)src * row_bytes + (uint32_t)(it * 32 * VEC * 4)));
                         } else {
 #pragma unroll
                             for (int j = 0; j < VEC; ++j) f[u][it][j] = 0.f;
@@ -1741,6 +1774,42 @@ int stage_mark(cudaStream_t stream, int i)
 
 int mbk_profile_enable(int enable) { g_profile = enable != 0; return MB_OK; }
 
+// ---- side branch of a batched update: the small, latency-bound launches between the index sweep and the voxel
+// scalar pass (accumulate runs, touched-voxel list, per-voxel source ranges: ~40 us of nearly empty GPU) and the
+// 4-byte-per-cell table memset do not depend on the segment sums, so they run on a library-owned stream next to
+// them: fork and join with events, which also makes them parallel branches when the caller captures the update in
+// a CUDA graph.  MASSB200_NO_FORK=1 keeps everything on the caller's stream (measurement aid).
+namespace {
+struct SideBranch {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, ctab_done = nullptr, indexed = nullptr, sources_done = nullptr;
+};
+constexpr int MAX_DEVICES = 64;
+SideBranch g_side[MAX_DEVICES];
+std::mutex g_side_mutex;
+
+// the calling device's side branch, or null (forking disabled / device index out of range)
+int side_branch(SideBranch **out)
+{
+    static const bool no_fork = getenv("MASSB200_NO_FORK") != nullptr;
+    *out = nullptr;
+    if (no_fork) return MB_OK;
+    int dev = 0;
+    MB_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES) return MB_OK;
+    SideBranch &sb = g_side[dev];
+    if (sb.stream == nullptr) {
+        cudaStream_t st;
+        MB_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        cudaEvent_t *ev[4] = { &sb.fork, &sb.ctab_done, &sb.indexed, &sb.sources_done };
+        for (auto e : ev) MB_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        sb.stream = st;
+    }
+    *out = &sb;
+    return MB_OK;
+}
+}  // namespace
+
 int mbk_profile_read(float *ms_host, int capacity)
 {
     if (!g_ev_recorded) return 0;
@@ -1904,6 +1973,17 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     // K1: voxelise + group inside tiles, compact the items; then sort the items by cell
     int rc;
     if ((rc = stage_mark(stream, 0))) return rc;
+    // the side branch's events are shared by all callers on this device: one enqueue at a time
+    std::lock_guard<std::mutex> side_lock(g_side_mutex);
+    SideBranch *side = nullptr;
+    if ((rc = side_branch(&side))) return rc;
+    if (side != nullptr && b.ctab) {
+        // the dense cell table is cleared next to the front end (only the index sweep needs it)
+        MB_CHECK_CUDA(cudaEventRecord(side->fork, stream));
+        MB_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        MB_CHECK_CUDA(cudaMemsetAsync(b.ctab, 0xff, (size_t)g.invalid * sizeof(int), side->stream));
+        MB_CHECK_CUDA(cudaEventRecord(side->ctab_done, side->stream));
+    }
     // every look-back word of the call and the touched-voxel bitmap: one memset up front
     MB_CHECK_CUDA(cudaMemsetAsync(b.idx_state, 0, b.state_bytes, stream));
     uint32_t *tkey = b.keys_b, *tval = b.pids_b;          // tile-local item lists live in the sort's second buffers
@@ -1929,7 +2009,10 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
 
     // K2: index sweep over the sorted items
     if ((rc = stage_mark(stream, 2))) return rc;
-    if (b.ctab) MB_CHECK_CUDA(cudaMemsetAsync(b.ctab, 0xff, (size_t)g.invalid * sizeof(int), stream));
+    if (b.ctab) {
+        if (side != nullptr) MB_CHECK_CUDA(cudaStreamWaitEvent(stream, side->ctab_done, 0));
+        else MB_CHECK_CUDA(cudaMemsetAsync(b.ctab, 0xff, (size_t)g.invalid * sizeof(int), stream));
+    }
     {
         const uint32_t itiles = (n + IDX_TILE - 1) / IDX_TILE;
         IndexOut O;
@@ -1937,20 +2020,32 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
         O.ucell = b.ucell; O.cstart = b.cstart; O.cseg = b.cseg;
         O.seg_start = b.seg_start; O.seg_frame = b.seg_frame; O.bitmap = b.bitmap; O.ctab = b.ctab;
         O.counters = b.counters; O.state = b.idx_state + 4; O.ticket = b.idx_state;
-        k_cell_index<<<itiles, 256, 0, stream>>>(ikey, ival, n_items, (uint32_t)tg.tpf, g, O);
+        k_cell_index<<<itiles, 256, 0, stream>>>(ikey, ival, n_items, tg, g, O);
         MB_LAUNCHED();
+    }
+    // K3, K4, K6a on the side branch (or in line): they need the index sweep only
+    cudaStream_t sstream = stream;
+    if (side != nullptr) {
+        MB_CHECK_CUDA(cudaEventRecord(side->indexed, stream));
+        MB_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->indexed, 0));
+        sstream = side->stream;
     }
     // K3: accumulate runs (cell-aligned pieces of <= TASK_ITEMS items)
     {
         const uint64_t lim = (uint64_t)rounds * run_cap;
-        k_cell_runs<<<MB_NUM_SMS * 4, 256, 0, stream>>>(b.cstart, b.counters, b.run_state + 4, b.run_state, b.crun, b.rstart,
-                                                        (uint32_t)(lim < 0xffffffffull ? lim : 0xffffffffull));
+        k_cell_runs<<<MB_NUM_SMS * 4, 256, 0, sstream>>>(b.cstart, b.counters, b.run_state + 4, b.run_state, b.crun, b.rstart,
+                                                         (uint32_t)(lim < 0xffffffffull ? lim : 0xffffffffull));
         MB_LAUNCHED();
     }
     // K4
-    k_vox_list<<<(vwords + VOX_TILE - 1) / VOX_TILE, 256, 0, stream>>>(b.bitmap, vwords, b.vox_state + 4, b.vox_state, b.vlist,
-                                                                       b.counters);
+    k_vox_list<<<(vwords + VOX_TILE - 1) / VOX_TILE, 256, 0, sstream>>>(b.bitmap, vwords, b.vox_state + 4, b.vox_state, b.vlist,
+                                                                        b.counters);
     MB_LAUNCHED();
+    // K6a
+    k_voxel_sources<<<MB_NUM_SMS * 8, 256, 0, sstream>>>(b.vlist, b.ucell, b.ctab, b.cseg, b.crun, g, b.vseg, b.vrun,
+                                                         b.counters);
+    MB_LAUNCHED();
+    if (side != nullptr) MB_CHECK_CUDA(cudaEventRecord(side->sources_done, side->stream));
     // K5, K6
     if ((rc = stage_mark(stream, 3))) return rc;
     {
@@ -1967,9 +2062,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
         int per_sm = 1;
         MB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_voxel_scalars, 256, smem));
         if (per_sm < 1) per_sm = 1;
-        k_voxel_sources<<<MB_NUM_SMS * 8, 256, 0, stream>>>(b.vlist, b.ucell, b.ctab, b.cseg, b.crun, g, b.vseg, b.vrun,
-                                                            b.counters);
-        MB_LAUNCHED();
+        if (side != nullptr) MB_CHECK_CUDA(cudaStreamWaitEvent(stream, side->sources_done, 0));
         k_voxel_scalars<<<MB_NUM_SMS * per_sm, 256, smem, stream>>>(b.vlist, b.vseg, b.seg_frame, b.segws, (size_t)n, g, alpha, T,
                                                                     b.gcoef, b.vA, b.counters);
         MB_LAUNCHED();

@@ -102,8 +102,25 @@ __device__ __forceinline__ float bins_scale(const float *__restrict__ bins, int 
 
 // Bucket of x for callers that only need VALID buckets: returns true iff bins[0] <= x < bins[n-1] (and x is
 // not NaN), i.e. iff torch.bucketize(x, bins, right=True) - 1 lies in [0, n-2]; then i is that value and
-// lo = bins[i], hi = bins[i+1].  One guess, at most one predicated step for near-uniform tables, and a
-// walk that only general tables ever enter.
+// lo = bins[i], hi = bins[i+1].  The guess from the table spacing is checked against the table itself (the only
+// authority on edge positions); on a near-uniform table it is right except within an ulp or two of an edge, so
+// everything else -- one step to a neighbour, the walk general tables need, points outside the table -- lives in
+// an out-of-line function that a warp only enters when one of its lanes needs it.
+struct BucketFix { int k; float lo, hi; int ok; };
+
+__device__ __noinline__ BucketFix bucket_walk(const float *__restrict__ bins, int n, float x, int k, float lo, float hi)
+{
+    BucketFix r;
+    r.ok = 0;
+    if (x >= __ldg(bins) && x < __ldg(bins + n - 1)) {          // (false for NaN)
+        while (x >= hi && k < n - 2) { ++k; lo = hi; hi = __ldg(bins + k + 1); }
+        while (x < lo && k > 0) { --k; hi = lo; lo = __ldg(bins + k); }
+        r.ok = (x >= lo && x < hi) ? 1 : 0;
+    }
+    r.k = k; r.lo = lo; r.hi = hi;
+    return r;
+}
+
 __device__ __forceinline__ bool bucket_valid(const float *__restrict__ bins, int n, float x, float b0, float scale,
                                              int &i, float &lo, float &hi)
 {
@@ -111,18 +128,10 @@ __device__ __forceinline__ bool bucket_valid(const float *__restrict__ bins, int
     int k = (int)fminf(fmaxf(gidx, 0.f), (float)(n - 2));        // NaN -> 0
     lo = __ldg(bins + k);
     hi = __ldg(bins + k + 1);
-    if (x >= hi) {
-        if (k < n - 2) { ++k; lo = hi; hi = __ldg(bins + k + 1); }
-    } else if (x < lo) {
-        if (k > 0) { --k; hi = lo; lo = __ldg(bins + k); }
-    }
     bool ok = x >= lo && x < hi;
-    if (!ok && x >= __ldg(bins) && x < __ldg(bins + n - 1)) {
-        // inside the table but more than one bucket from the guess: only tables that are far from uniform
-        // get here; walk to the bucket
-        while (x >= hi && k < n - 2) { ++k; lo = hi; hi = __ldg(bins + k + 1); }
-        while (x < lo && k > 0) { --k; hi = lo; lo = __ldg(bins + k); }
-        ok = x >= lo && x < hi;
+    if (!ok) {
+        const BucketFix f = bucket_walk(bins, n, x, k, lo, hi);
+        k = f.k; lo = f.lo; hi = f.hi; ok = f.ok != 0;
     }
     i = k;
     return ok;

@@ -258,6 +258,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
                      : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
 }
 
+// Lanes of the warp that hold the same 8-bit digit (out-of-range lanes never join a group).  match.any takes time
+// in proportion to the number of DISTINCT values in the warp: with the low digits of cell keys (close to 32 distinct
+// values per round) the ranking loop spent half its time waiting for it (ncu, profiles/r02z: 51 % of the scatter
+// kernel's samples on the instruction after the match; the top digit, a handful of values per round, ran 2.3x faster).
+// Eight ballots cost the same whatever the digits are.  -DMB_SORT_MATCH_ANY=1 restores the match.any form.
+#ifndef MB_SORT_MATCH_ANY
+#define MB_SORT_MATCH_ANY 0
+#endif
+__device__ __forceinline__ uint32_t match_digit(uint32_t d, bool valid, int lane)
+{
+#if MB_SORT_MATCH_ANY
+    return __match_any_sync(0xffffffffu, valid ? d : (256u + (uint32_t)lane));
+#else
+    uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t has = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? has : ~has;
+    }
+    return valid ? peers : (1u << lane);
+#endif
+}
+
 // Shared memory of k_radix_block_scatter (dynamic): two input buffers of one tile each (keys, values),
 // filled by cp.async one tile ahead of the tile being ranked, and the sorted staging area.
 struct ScatterSmem {
@@ -326,8 +350,7 @@ k_radix_block_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__re
         for (int r = 0; r < OS_ITEMS; ++r) {
             const bool valid = wloc + r * 32 + lane < tile_n;
             const uint32_t d = (k[r] >> shift) & (R - 1);
-            // out-of-range lanes get a private pseudo-digit so they never join a real group
-            const uint32_t m = __match_any_sync(0xffffffffu, valid ? d : (R + lane));
+            const uint32_t m = match_digit(d, valid, lane);
             const uint32_t rank = __popc(m & ((1u << lane) - 1u));
             const uint32_t prev = valid ? S.wcnt[warp][d] : 0u;
             __syncwarp();
