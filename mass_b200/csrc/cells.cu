@@ -284,7 +284,8 @@ k_cell_voxelise(const float *__restrict__ rays, const float *__restrict__ depth,
 struct __align__(16) WarpTile {
     uint4 px[TILE_PIX];                          // the tile's pixels {key, 3 ratios}, image order (bulk-copied in)
     uint32_t hkey[WHASH];
-    uint16_t cnt[WHASH], start[WHASH];
+    uint32_t cnt[WHASH];
+    uint16_t start[WHASH];
     uint64_t bar;                                // counts the bytes of the tile's bulk copies
 };
 
@@ -322,13 +323,13 @@ k_tile_group(const uint4 *__restrict__ pix, TileGeom tg, uint32_t ntiles, uint4 
                      ::"r"(tile_smem_addr(&S.px[lane * TILE_W])), "l"(pix + fbase + (size_t)(y0 + lane) * tg.W + x0),
                        "r"((uint32_t)cols * 16u), "r"(bar) : "memory");
     {
-        // clear the table with 16-byte stores (WHASH keys = WHASH / 4 pieces, WHASH counters = WHASH / 8 pieces)
+        // clear the table with 16-byte stores (WHASH keys and WHASH counters = WHASH / 4 pieces each)
         uint4 *hk = reinterpret_cast<uint4 *>(S.hkey), *ct = reinterpret_cast<uint4 *>(S.cnt);
         const uint4 e4 = make_uint4(HASH_EMPTY, HASH_EMPTY, HASH_EMPTY, HASH_EMPTY), z4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int i = lane; i < WHASH / 4; i += 32) hk[i] = e4;
 #pragma unroll
-        for (int i = lane; i < WHASH / 8; i += 32) ct[i] = z4;
+        for (int i = lane; i < WHASH / 4; i += 32) ct[i] = z4;
     }
     const uint32_t ltmask = (1u << lane) - 1u;
     __syncwarp();
@@ -362,13 +363,15 @@ k_tile_group(const uint4 *__restrict__ pix, TileGeom tg, uint32_t ntiles, uint4 
             }
             sl = h;
         }
+        // the leader adds its group to the slot's count and hands the old count (and the slot) to its peers: only
+        // atomics touch the counts in this loop, and a warp's shared-memory operations execute in order
+        uint32_t prev = 0;
+        if (valid && lane == leader) prev = atomicAdd(&S.cnt[sl], (uint32_t)__popc(m));
         sl = __shfl_sync(FULL, sl, leader);
-        const uint32_t prev = valid ? S.cnt[sl] : 0u;
-        __syncwarp();
-        if (valid && lane == leader) S.cnt[sl] = (uint16_t)(prev + __popc(m));
-        __syncwarp();
+        prev = __shfl_sync(FULL, prev, leader);
         sr[r] = valid ? (sl | ((prev + __popc(m & ltmask)) << 16)) : (uint32_t)WHASH;
     }
+    __syncwarp();                                     // the counts are read with plain loads from here on
     // ---- lay the groups out: lane owns slots lane, lane + 32, ... ---------------------------------------------
     uint32_t mine = 0;                                // pixels | items << 16 of this lane's slots
 #pragma unroll
@@ -454,7 +457,7 @@ struct IndexOut {
     uint32_t *bitmap;                             // touched voxels
     int *ctab;                                    // dense cell key -> unique index, or null
     uint32_t *counters;
-    uint32_t *state;                              // [tiles][3] look-back words, zeroed
+    uint32_t *state;                              // [tiles][2] look-back words (cells, segments), zeroed
     uint32_t *ticket;                             // zeroed
 };
 
@@ -500,7 +503,9 @@ k_cell_index(const uint32_t *__restrict__ skey, const uint32_t *__restrict__ sva
     if (lane == 0) { s_wsum[warp][0] = cw; s_wsum[warp][1] = sw; }
     __syncthreads();
     if (tid < 2) {
-        // tile total of counter `tid`, published; then the look-back for the tile's base rank
+        // tile total of counter `tid`, published; then the look-back for the tile's base rank (one thread per counter,
+        // four predecessors per step: a warp-wide look-back, 32 per step, measured 10-20 us SLOWER here -- the tiles
+        // start almost together, so the wider window mostly re-reads words that are not published yet)
         uint32_t total = 0;
         for (int w = 0; w < 8; ++w) total += s_wsum[w][tid];
         uint32_t *mine = O.state + (size_t)tile * 2 + tid;
@@ -1244,6 +1249,12 @@ __device__ __forceinline__ void apply_round(const ApplyArgs &A, int chblock)
     const uint32_t run_end = A.run_base + A.run_cap;
     const int F = A.F;
     const int ch0 = chblock * (32 * VEC * IT) + lane * VEC;
+    // P row of (run, slot) for this lane: one 32 x 32 -> 64-bit multiply-add ((run - run_base) * 8 + slot < 2^32: run_cap <= 2^28)
+    const char *pbase = (const char *)(A.P + ch0);
+    const uint32_t row_bytes = (uint32_t)F * (uint32_t)sizeof(float);
+    auto prow_of = [&](uint32_t run, int slot, int it) {
+        return (const float *)(pbase + (uint64_t)((run - A.run_base) * 8u + (uint32_t)slot) * row_bytes + (uint32_t)(it * 32 * VEC * 4));
+    };
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t j = wid; j < nvox; j += nw) {
         const uint32_t v = A.vlist[j];
@@ -1307,8 +1318,7 @@ __device__ __forceinline__ void apply_round(const ApplyArgs &A, int chblock)
                         const int ch = ch0 + it * 32 * VEC;
 #pragma unroll
                         for (int q = 0; q < VEC; ++q) x[s][r][it][q] = 0.f;
-                        if (slo[s] + r < shi[s] && ch < F)
-                            row_load<VEC>(x[s][r][it], A.P + ((size_t)(slo[s] + r - A.run_base) * 8 + (7 - s)) * F + ch);
+                        if (slo[s] + r < shi[s] && ch < F) row_load<VEC>(x[s][r][it], prow_of(slo[s] + r, 7 - s, it));
                     }
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
@@ -1319,13 +1329,12 @@ __device__ __forceinline__ void apply_round(const ApplyArgs &A, int chblock)
 #pragma unroll
                         for (int q = 0; q < VEC; ++q) acc[it][q] += x[s][r][it][q];
                 for (uint32_t e = slo[s] + 2; e < shi[s]; ++e) {
-                    const float *prow = A.P + ((size_t)(e - A.run_base) * 8 + (7 - s)) * F;
 #pragma unroll
                     for (int it = 0; it < IT; ++it) {
                         const int ch = ch0 + it * 32 * VEC;
                         if (ch < F) {
                             float y[VEC];
-                            row_load<VEC>(y, prow + ch);
+                            row_load<VEC>(y, prow_of(e, 7 - s, it));
 #pragma unroll
                             for (int q = 0; q < VEC; ++q) acc[it][q] += y[q];
                         }
@@ -1338,7 +1347,6 @@ __device__ __forceinline__ void apply_round(const ApplyArgs &A, int chblock)
                 if (slo[s] >= shi[s]) continue;
                 const uint32_t m = slot_mask(v0, v1, v2, s, A.g);
                 for (uint32_t e = slo[s]; e < shi[s]; ++e) {
-                    const float *prow = A.P + (size_t)(e - A.run_base) * 8 * F;
                     for (uint32_t mm = m; mm; mm &= mm - 1) {
                         const int k = __ffs(mm) - 1;
 #pragma unroll
@@ -1346,7 +1354,7 @@ __device__ __forceinline__ void apply_round(const ApplyArgs &A, int chblock)
                             const int ch = ch0 + it * 32 * VEC;
                             if (ch < F) {
                                 float y[VEC];
-                                row_load<VEC>(y, prow + (size_t)k * F + ch);
+                                row_load<VEC>(y, prow_of(e, k, it));
 #pragma unroll
                                 for (int q = 0; q < VEC; ++q) acc[it][q] += y[q];
                             }
@@ -1966,7 +1974,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     const size_t run_cap_sz = b.P_floats / ((size_t)8 * F);
     const size_t wruns = worst_runs(n, g);
     MB_REQUIRE(run_cap_sz >= (wruns < 512 ? wruns : 512), "batch workspace too small for the run buffer");
-    const uint32_t run_cap = (uint32_t)(run_cap_sz < 0x7fffffffull ? run_cap_sz : 0x7fffffffull);
+    const uint32_t run_cap = (uint32_t)(run_cap_sz < (1ull << 28) ? run_cap_sz : (1ull << 28));      // (run * 8 + slot stays 32-bit)
     const int rounds = (int)((wruns + run_cap - 1) / run_cap);
     MB_REQUIRE(rounds <= 4096, "batch workspace far too small for the run buffer");
 

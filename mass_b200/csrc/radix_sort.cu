@@ -5,8 +5,8 @@
 // /root/reference/mass/utils/projection.py:294-298, 319-323, 349-351) without float atomics.
 //
 // 8-bit digits, one contiguous block of the input per resident CTA (see below).  Inside a tile each warp
-// owns 512 consecutive elements and ranks them in 16 rounds of 32 with match.any, so the order
-// (tile, warp, round, lane) is the input order.
+// owns 256 consecutive elements and ranks them in 8 rounds of 32 (lanes with equal digits found by ballots),
+// so the order (tile, warp, round, lane) is the input order.
 #include "common.cuh"
 
 namespace {
@@ -169,21 +169,22 @@ k_scan_lookback(const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *state)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Radix sort, 8 bits per pass.  The input is cut into one contiguous block per resident CTA (148 SMs x 4);
+// Radix sort, 8 bits per pass.  The input is cut into one contiguous block per resident CTA (148 SMs x 2);
 // per pass:
 //   k_radix_block_hist     each CTA counts the digits of its block (runs of equal digits are merged before
 //                          they touch the shared-memory histogram) -> table [digit][block]
 //   exclusive scan of the table (digit-major): the global position of every (digit, block)
-//   k_radix_block_scatter  each CTA walks its block tile by tile (4096 pairs): ranks the tile (match.any per
-//                          warp round, per-warp digit counters), stages the pairs through shared memory in
-//                          sorted order and writes them out coalesced, carrying the running position of
-//                          every digit in shared memory.
+//   k_radix_block_scatter  each CTA walks its block tile by tile (4096 pairs): ranks the tile (equal digits of a
+//                          warp round by ballots, per-warp digit counters), stages the pairs through shared
+//                          memory in sorted order and writes them out coalesced; thread d carries the running
+//                          position of digit d.
 // No CTA ever waits for another one.  Stable: the global order inside a digit is (block, tile, warp, round,
 // lane) = the input order.
-constexpr int OS_ITEMS = 16;
-constexpr int OS_THREADS = 256;
+constexpr int OS_ITEMS = 8;
+constexpr int OS_THREADS = 512;
 constexpr int OS_TILE = OS_THREADS * OS_ITEMS;
 constexpr int OS_BLOCKS = MB_NUM_SMS * 2;
+constexpr int HIST_THREADS = 1024;
 
 // elements per CTA: the tiles split evenly over the CTAs, a multiple of the tile
 __host__ __device__ inline uint32_t block_share(uint32_t n, uint32_t blocks)
@@ -192,12 +193,12 @@ __host__ __device__ inline uint32_t block_share(uint32_t n, uint32_t blocks)
     return ((ntiles + blocks - 1) / blocks) * OS_TILE;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(HIST_THREADS)
 k_radix_block_hist(const uint32_t *__restrict__ keys, uint32_t n, const uint32_t *__restrict__ n_dev,
                    uint32_t per_block, int shift, uint32_t *__restrict__ table)
 {
     __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
+    if (threadIdx.x < 256) h[threadIdx.x] = 0;
     if (n_dev) {                                  // the real count lives on the device: same split, computed here
         n = min(n, *n_dev);
         per_block = block_share(n, gridDim.x);
@@ -205,7 +206,7 @@ k_radix_block_hist(const uint32_t *__restrict__ keys, uint32_t n, const uint32_t
     __syncthreads();
     const uint32_t beg = min(n, blockIdx.x * per_block), end = min(n, beg + per_block);
     // each thread takes 16 consecutive keys (per_block and beg are multiples of 4096)
-    for (uint32_t base = beg + threadIdx.x * 16u; base < end; base += 256u * 16u) {
+    for (uint32_t base = beg + threadIdx.x * 16u; base < end; base += HIST_THREADS * 16u) {
         uint32_t k[16];
         if (base + 16u <= end) {
             const uint4 *p = (const uint4 *)(keys + base);
@@ -231,7 +232,7 @@ k_radix_block_hist(const uint32_t *__restrict__ keys, uint32_t n, const uint32_t
         atomicAdd(&h[cur], run);
     }
     __syncthreads();
-    table[threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];      // digit-major
+    if (threadIdx.x < 256) table[threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];      // digit-major
 }
 
 // Bulk asynchronous copies (the TMA engine's linear mode, SASS UBLKCP): one thread hands a whole contiguous tile to the
@@ -282,16 +283,19 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d, bool valid, int lane
 #endif
 }
 
-// Shared memory of k_radix_block_scatter (dynamic): two input buffers of one tile each (keys, values),
-// filled by cp.async one tile ahead of the tile being ranked, and the sorted staging area.
+// Shared memory of k_radix_block_scatter (dynamic): the input buffer of ONE tile (keys, values), which the TMA
+// engine refills with the next tile while the current one -- already in registers -- is ranked, and the sorted
+// staging area.
 struct ScatterSmem {
-    uint32_t in_key[2][OS_TILE], in_val[2][OS_TILE];
+    uint32_t in_key[OS_TILE], in_val[OS_TILE];
     uint32_t s_key[OS_TILE], s_val[OS_TILE];
     uint32_t wcnt[OS_THREADS / 32][256];
-    uint32_t s_dstart[256], s_gpos[256];
-    uint64_t bar[2];                             // one per input buffer: counts the bytes of its bulk copies
+    uint32_t s_dstart[256], s_off[256], s_wsum[8];
+    uint64_t bar;                                // counts the bytes of the input buffer's bulk copies
 };
 
+// 16 warps of 8 rounds each per tile (two CTAs per SM: 32 warps): the ranking of a warp is a chain of dependent
+// shared-memory read-modify-writes, so it is the number of independent chains per SM that sets the pace.
 __global__ void __launch_bounds__(OS_THREADS, 2)
 k_radix_block_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                       uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n,
@@ -307,10 +311,10 @@ k_radix_block_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__re
         per_block = block_share(n, gridDim.x);
     }
     const uint32_t beg = min(n, blockIdx.x * per_block), end = min(n, beg + per_block);
-    S.s_gpos[tid] = table[tid * gridDim.x + blockIdx.x];
+    uint32_t gpos = tid < R ? table[tid * gridDim.x + blockIdx.x] : 0u;     // running position of digit `tid` in this block
+    for (int i = tid; i < WARPS * R; i += OS_THREADS) (&S.wcnt[0][0])[i] = 0;
     if (tid == 0) {
-        mbar_init(&S.bar[0], 1);
-        mbar_init(&S.bar[1], 1);
+        mbar_init(&S.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -318,58 +322,69 @@ k_radix_block_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__re
     // a tile (16 KB of keys + 16 KB of values, contiguous) is fetched by ONE thread as two bulk copies, a multiple of
     // 16 bytes each (beg is a multiple of the tile; the array tails are padded by the allocation: a piece that starts
     // before `end` is always in bounds of the 16-byte aligned buffer)
-    auto fetch = [&](uint32_t tbase, int buf) {
+    auto fetch = [&](uint32_t tbase) {
         if (tid == 0) {
             const uint32_t cnt = min((uint32_t)OS_TILE, end - tbase);
             const uint32_t bytes = (cnt * 4u + 15u) & ~15u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier reads of the buffer are done
-            mbar_expect_tx(&S.bar[buf], vals_iota ? bytes : 2u * bytes);
-            bulk_g2s(&S.in_key[buf][0], keys_in + tbase, bytes, &S.bar[buf]);
-            if (!vals_iota) bulk_g2s(&S.in_val[buf][0], vals_in + tbase, bytes, &S.bar[buf]);
+            mbar_expect_tx(&S.bar, vals_iota ? bytes : 2u * bytes);
+            bulk_g2s(&S.in_key[0], keys_in + tbase, bytes, &S.bar);
+            if (!vals_iota) bulk_g2s(&S.in_val[0], vals_in + tbase, bytes, &S.bar);
         }
     };
-    if (beg < end) fetch(beg, 0);
-    int buf = 0;
-    uint32_t phase[2] = { 0u, 0u };
-    for (uint32_t tbase = beg; tbase < end; tbase += OS_TILE, buf ^= 1) {
-        for (int i = tid; i < WARPS * R; i += OS_THREADS) (&S.wcnt[0][0])[i] = 0;
-        __syncthreads();                          // the staging area and the other input buffer are free
-        if (tbase + OS_TILE < end) fetch(tbase + OS_TILE, buf ^ 1);      // next tile, while this one is ranked
-        mbar_wait(&S.bar[buf], phase[buf]);       // this tile's input has landed in shared memory
-        phase[buf] ^= 1u;
+    if (beg < end) fetch(beg);
+    uint32_t phase = 0u;
+    for (uint32_t tbase = beg; tbase < end; tbase += OS_TILE) {
+        mbar_wait(&S.bar, phase);                 // this tile's input has landed in shared memory
+        phase ^= 1u;
         const uint32_t tile_n = min((uint32_t)OS_TILE, end - tbase);
         const uint32_t wloc = warp * (32 * OS_ITEMS);
-        uint32_t k[OS_ITEMS];
+        uint32_t k[OS_ITEMS], v[OS_ITEMS];
         uint32_t rk2[OS_ITEMS / 2];             // ranks inside (warp, digit), two 16-bit values per register
 #pragma unroll
         for (int r = 0; r < OS_ITEMS; ++r) {
             const uint32_t loc = wloc + r * 32 + lane;
-            k[r] = loc < tile_n ? S.in_key[buf][loc] : 0xffffffffu;
+            k[r] = loc < tile_n ? S.in_key[loc] : 0xffffffffu;
+            v[r] = vals_iota ? tbase + loc : S.in_val[loc];
         }
+        __syncthreads();                          // the input buffer is in registers; the staging area and wcnt are free
+        if (tbase + OS_TILE < end) fetch(tbase + OS_TILE);      // next tile, while this one is ranked
 #pragma unroll
         for (int r = 0; r < OS_ITEMS; ++r) {
             const bool valid = wloc + r * 32 + lane < tile_n;
             const uint32_t d = (k[r] >> shift) & (R - 1);
             const uint32_t m = match_digit(d, valid, lane);
             const uint32_t rank = __popc(m & ((1u << lane) - 1u));
-            const uint32_t prev = valid ? S.wcnt[warp][d] : 0u;
-            __syncwarp();
-            if (valid && rank == 0) S.wcnt[warp][d] = prev + __popc(m);
-            __syncwarp();
+            // the first lane of every group adds the group to the warp's digit counter and hands the old count to
+            // its peers.  Only atomics touch the counters in this loop and a warp's shared-memory operations
+            // execute in order, so the rounds need no barrier between them and their counter updates pipeline
+            // instead of forming a chain of read - barrier - write - barrier.
+            uint32_t prev = 0;
+            if (valid && rank == 0) prev = atomicAdd(&S.wcnt[warp][d], (uint32_t)__popc(m));
+            prev = __shfl_sync(0xffffffffu, prev, __ffs(m) - 1);
             if (r & 1) rk2[r >> 1] |= (prev + rank) << 16; else rk2[r >> 1] = prev + rank;
         }
         __syncthreads();
-        // thread d: digit d's count in this tile, exclusive offsets of the warps inside the digit
-        uint32_t count = 0;
+        // thread d < 256: digit d's count in this tile, exclusive offsets of the warps inside the digit
+        uint32_t count = 0, inc = 0;
+        if (tid < R) {
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            const uint32_t c = S.wcnt[w][tid];
-            S.wcnt[w][tid] = count;
-            count += c;
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t c = S.wcnt[w][tid];
+                S.wcnt[w][tid] = count;
+                count += c;
+            }
+            inc = warp_inclusive_scan(count, lane);
+            if (lane == 31) S.s_wsum[warp] = inc;
         }
-        uint32_t total;
-        const uint32_t dstart = block_exclusive_scan(count, &total);
-        S.s_dstart[tid] = dstart;
+        __syncthreads();
+        if (tid < R) {
+            uint32_t dstart = inc - count;
+            for (int w = 0; w < warp; ++w) dstart += S.s_wsum[w];
+            S.s_dstart[tid] = dstart;
+            S.s_off[tid] = gpos - dstart;         // global position of staged element i of digit d: s_off[d] + i
+            gpos += count;
+        }
         __syncthreads();
         // stage in sorted order
 #pragma unroll
@@ -380,19 +395,18 @@ k_radix_block_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__re
                 const uint32_t rank = (r & 1) ? (rk2[r >> 1] >> 16) : (rk2[r >> 1] & 0xffffu);
                 const uint32_t lp = S.s_dstart[d] + S.wcnt[warp][d] + rank;
                 S.s_key[lp] = k[r];
-                S.s_val[lp] = vals_iota ? tbase + loc : S.in_val[buf][loc];
+                S.s_val[lp] = v[r];
             }
         }
         __syncthreads();
+        for (int i = tid; i < WARPS * R; i += OS_THREADS) (&S.wcnt[0][0])[i] = 0;      // (for the next tile)
         for (uint32_t i = tid; i < tile_n; i += OS_THREADS) {
             const uint32_t key = S.s_key[i];
             const uint32_t d = (key >> shift) & (R - 1);
-            const uint32_t pos = S.s_gpos[d] + (i - S.s_dstart[d]);
+            const uint32_t pos = S.s_off[d] + i;
             keys_out[pos] = key;
             vals_out[pos] = S.s_val[i];
         }
-        __syncthreads();
-        S.s_gpos[tid] += count;                  // running position of digit `tid` inside this block
     }
 }
 
@@ -467,7 +481,7 @@ int mb_sort_pairs(cudaStream_t stream, uint32_t *keys_a, uint32_t *vals_a, uint3
     uint32_t *kin = keys_a, *vin = vals_a, *kout = keys_b, *vout = vals_b;
     bool iota = vals_a_is_iota;
     for (int p = 0; p < passes; ++p) {
-        k_radix_block_hist<<<blocks, 256, 0, stream>>>(kin, n, n_dev, per_block, 8 * p, table);
+        k_radix_block_hist<<<blocks, HIST_THREADS, 0, stream>>>(kin, n, n_dev, per_block, 8 * p, table);
         MB_LAUNCHED();
         int rc = mb_exclusive_scan_small(stream, table, table, table_n, state + (size_t)p * state_words);
         if (rc) return rc;
