@@ -19,6 +19,7 @@ STAMP_PATH = SO_PATH + ".srchash"
 
 MODE_EXACT = 0
 MODE_FAST = 1
+CNT_ERROR = 5        # index of the sticky error word among the batched pipeline's device counters (kernels.cuh)
 
 _lib = None
 

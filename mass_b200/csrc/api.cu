@@ -256,7 +256,7 @@ static int layer_update(void *stream_, const float *rays, const float *depth, co
                                       class_ids ? class_ids + (size_t)t * npix : nullptr, pose + (size_t)t * 12, n,
                                       H, W, fh, fw, F, bins_x, nx, bins_y, ny, bins_z, nz, map, affine_a,
                                       interpolation_weight, min_ray_depth, max_ray_depth, workspace, workspace_bytes,
-                                      sparse);
+                                      sparse, t > 0);      // (the error bits of a call's earlier chunks stay set)
             if (rc) return rc;
         }
         return MB_OK;

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(256, MB_VOX_MINB)
 k_cell_voxelise(const float *__restrict__ rays, const float *__restrict__ depth, const float *__restrict__ pose,
                 uint32_t npix, const float *__restrict__ bins_x, int nx, const float *__restrict__ bins_y, int ny,
                 const float *__restrict__ bins_z, int nz, CellGrid g, float min_d, float max_d,
-                uint4 *__restrict__ pix, uint32_t *__restrict__ counters)
+                uint4 *__restrict__ pix, uint32_t *__restrict__ counters, bool keep_error_bits)
 {
     __shared__ float P[12], spacing[6];
     const uint32_t t = blockIdx.y;
@@ -244,7 +244,8 @@ k_cell_voxelise(const float *__restrict__ rays, const float *__restrict__ depth,
         spacing[2 * a] = __ldg(bb);
         spacing[2 * a + 1] = bins_scale(bb, nb);
     }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < MB_NUM_COUNTERS) counters[threadIdx.x] = 0;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < MB_NUM_COUNTERS && !(keep_error_bits && threadIdx.x == MB_CNT_ERROR))
+        counters[threadIdx.x] = 0;
     __syncthreads();
     // VOX_PPT pixels per thread (a CTA covers 256 * VOX_PPT consecutive pixels of one frame): the loads of all of them
     // are issued before the first is used, and the per-CTA prologue above is paid once for all of them
@@ -1955,7 +1956,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
                      const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw, int F,
                      const float *bins_x, int nx, const float *bins_y, int ny, const float *bins_z, int nz,
                      float *map, float *affine_a, float alpha, float min_d, float max_d, void *workspace,
-                     size_t workspace_bytes, const MbSparseFold *sparse)
+                     size_t workspace_bytes, const MbSparseFold *sparse, bool keep_error_bits)
 {
     const uint32_t npix = (uint32_t)H * (uint32_t)W;
     const TileGeom tg = make_tiles(H, W);
@@ -1997,7 +1998,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     uint32_t *tkey = b.keys_b, *tval = b.pids_b;          // tile-local item lists live in the sort's second buffers
     dim3 vgrid((npix + 256 * VOX_PPT - 1) / (256 * VOX_PPT), (unsigned)T);
     k_cell_voxelise<<<vgrid, 256, 0, stream>>>(rays, depth, pose, npix, bins_x, nx, bins_y, ny, bins_z, nz, g, min_d, max_d,
-                                               b.pix, b.counters);
+                                               b.pix, b.counters, keep_error_bits);
     MB_LAUNCHED();
     MB_CHECK_CUDA(cudaFuncSetAttribute(k_tile_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(WarpTile))));
     k_tile_group<<<(ntiles + 7) / 8, 256, 8 * sizeof(WarpTile), stream>>>(b.pix, tg, ntiles, b.rec, tkey, tval, b.tcount);

@@ -66,7 +66,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
                      const int64_t *class_ids, const float *pose, int T, int H, int W, int fh, int fw, int F,
                      const float *bins_x, int nx, const float *bins_y, int ny, const float *bins_z, int nz,
                      float *map, float *affine_a, float alpha, float min_d, float max_d, void *workspace,
-                     size_t workspace_bytes, const MbSparseFold *sparse = nullptr);
+                     size_t workspace_bytes, const MbSparseFold *sparse = nullptr, bool keep_error_bits = false);
 size_t mbk_partial_buffer_layout(uint32_t capacity, int F, size_t *offsets);
 int mbk_partial_reset(cudaStream_t stream, int32_t *slot_table, int64_t voxels, void *buffer);
 int mbk_partial_clear(cudaStream_t stream, int32_t *slot_table, void *buffer, uint32_t capacity, int F);

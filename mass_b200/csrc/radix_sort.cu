@@ -263,15 +263,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // in proportion to the number of DISTINCT values in the warp: with the low digits of cell keys (close to 32 distinct
 // values per round) the ranking loop spent half its time waiting for it (ncu, profiles/r02z: 51 % of the scatter
 // kernel's samples on the instruction after the match; the top digit, a handful of values per round, ran 2.3x faster).
-// Eight ballots cost the same whatever the digits are.  -DMB_SORT_MATCH_ANY=1 restores the match.any form.
-#ifndef MB_SORT_MATCH_ANY
-#define MB_SORT_MATCH_ANY 0
-#endif
+// Eight ballots cost the same whatever the digits are, so they rank the low digits; the LAST pass of a sort -- the
+// top digit of a spatial key, which neighbouring elements share -- keeps match.any (34 us against 48 us with ballots).
+template <bool MATCH_ANY>
 __device__ __forceinline__ uint32_t match_digit(uint32_t d, bool valid, int lane)
 {
-#if MB_SORT_MATCH_ANY
-    return __match_any_sync(0xffffffffu, valid ? d : (256u + (uint32_t)lane));
-#else
+    if (MATCH_ANY) return __match_any_sync(0xffffffffu, valid ? d : (256u + (uint32_t)lane));
     uint32_t peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
@@ -280,7 +277,6 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d, bool valid, int lane
         peers &= bit ? has : ~has;
     }
     return valid ? peers : (1u << lane);
-#endif
 }
 
 // Shared memory of k_radix_block_scatter (dynamic): the input buffer of ONE tile (keys, values), which the TMA
@@ -296,6 +292,7 @@ struct ScatterSmem {
 
 // 16 warps of 8 rounds each per tile (two CTAs per SM: 32 warps): the ranking of a warp is a chain of dependent
 // shared-memory read-modify-writes, so it is the number of independent chains per SM that sets the pace.
+template <bool MATCH_ANY>
 __global__ void __launch_bounds__(OS_THREADS, 2)
 k_radix_block_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                       uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n,
@@ -353,7 +350,7 @@ k_radix_block_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__re
         for (int r = 0; r < OS_ITEMS; ++r) {
             const bool valid = wloc + r * 32 + lane < tile_n;
             const uint32_t d = (k[r] >> shift) & (R - 1);
-            const uint32_t m = match_digit(d, valid, lane);
+            const uint32_t m = match_digit<MATCH_ANY>(d, valid, lane);
             const uint32_t rank = __popc(m & ((1u << lane) - 1u));
             // the first lane of every group adds the group to the warp's digit counter and hands the old count to
             // its peers.  Only atomics touch the counters in this loop and a warp's shared-memory operations
@@ -467,7 +464,9 @@ int mb_sort_pairs(cudaStream_t stream, uint32_t *keys_a, uint32_t *vals_a, uint3
     // n is an upper bound when n_dev is given: the CTAs then split min(n, *n_dev) among themselves
     const int blocks = ntiles < (size_t)OS_BLOCKS ? (int)ntiles : OS_BLOCKS;
     const uint32_t per_block = block_share(n, (uint32_t)blocks);
-    MB_CHECK_CUDA(cudaFuncSetAttribute(k_radix_block_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MB_CHECK_CUDA(cudaFuncSetAttribute(k_radix_block_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ScatterSmem)));
+    MB_CHECK_CUDA(cudaFuncSetAttribute(k_radix_block_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(ScatterSmem)));
     MbArena arena(workspace, workspace_bytes);
     const uint32_t table_n = 256u * (uint32_t)blocks;
@@ -485,8 +484,12 @@ int mb_sort_pairs(cudaStream_t stream, uint32_t *keys_a, uint32_t *vals_a, uint3
         MB_LAUNCHED();
         int rc = mb_exclusive_scan_small(stream, table, table, table_n, state + (size_t)p * state_words);
         if (rc) return rc;
-        k_radix_block_scatter<<<blocks, OS_THREADS, sizeof(ScatterSmem), stream>>>(kin, vin, kout, vout, n, n_dev,
-                                                                                   per_block, 8 * p, table, iota ? 1 : 0);
+        if (p == passes - 1 && passes > 1)
+            k_radix_block_scatter<true><<<blocks, OS_THREADS, sizeof(ScatterSmem), stream>>>(kin, vin, kout, vout, n, n_dev,
+                                                                                             per_block, 8 * p, table, iota ? 1 : 0);
+        else
+            k_radix_block_scatter<false><<<blocks, OS_THREADS, sizeof(ScatterSmem), stream>>>(kin, vin, kout, vout, n, n_dev,
+                                                                                              per_block, 8 * p, table, iota ? 1 : 0);
         MB_LAUNCHED();
         iota = false;
         uint32_t *t;

@@ -45,11 +45,13 @@ class SemanticProjectionLayer(BaseProjectionLayer):
 
     def _validate(self, ids):
         """functional.one_hot raises on ids outside [0, feature_size) (semantic_projection_layer.py:203-214).  A host
-        image (what the agent passes: numpy from the detector) is checked here, on the host, for free.  A DEVICE
+        image (what the agent passes: numpy from the detector) is checked here, on the host.  A DEVICE
         image is not read back -- that would stall the stream on every frame; the kernel flags the bad id, adds
         nothing for that pixel, and `check()` raises the same error."""
-        if not ids.is_cuda and ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= self.feature_size):
-            raise RuntimeError("Class values must be in [0, %d)" % self.feature_size)
+        if not ids.is_cuda and ids.numel():
+            lo, hi = torch.aminmax(ids)
+            if int(lo) < 0 or int(hi) >= self.feature_size:
+                raise RuntimeError("Class values must be in [0, %d)" % self.feature_size)
 
     def update(self, observation: Dict[str, Any]):
         """observation["semantic"]: [H, W, 1] integer class ids
@@ -70,10 +72,17 @@ class SemanticProjectionLayer(BaseProjectionLayer):
         if ids.is_cuda or ids.dtype not in (torch.int32, torch.int16, torch.uint8, torch.int8):
             ids = ids.to(torch.int64)           # (narrow host ids cross PCIe as they are and widen on the device)
         ids = ids.reshape(-1, self.camera_height, self.camera_width)
-        self._validate(ids)
+        # A batch of host images in the batched mode is not scanned on the host (a min/max pass over 500 frames of
+        # int64 ids takes longer than copying them to the GPU): the kernels check every id they read anyway, the
+        # host pipeline collects their error bits and raises before update_batch returns -- after the valid pixels
+        # have been fused, where the reference raises before the offending frame.
+        on_device_check = (not ids.is_cuda) and (not self.exact) and self.data.is_cuda and ids.shape[0] > 1 \
+            and not torch.as_tensor(observations["depth"]).is_cuda
+        if not on_device_check:
+            self._validate(ids)
         return super().update_batch(dict(position=observations["position"], yaw=observations["yaw"],
                                          elevation=observations["elevation"], depth=observations["depth"],
-                                         class_ids=ids), fold=fold)
+                                         class_ids=ids), fold=fold, check_ids=on_device_check)
 
     def visualize(self, obs: Dict[str, Any], depth_slice: slice = slice(0, 32)):
         """Top-down arg-max class colours, white where empty, red boxes from the last find().

@@ -290,9 +290,11 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         self._updates += 1
         return self
 
-    def update_batch(self, observations, fold=None):
+    def update_batch(self, observations, fold=None, check_ids=False):
         """Fuse T observations in order (frames do not commute).  `observations` is a
-        list of observation dicts or one dict of stacked arrays with a leading T axis."""
+        list of observation dicts or one dict of stacked arrays with a leading T axis.
+        check_ids: frames handed over in HOST memory have their class ids checked by the kernels (the error bits of
+        every chunk are collected on the device) and the call raises before it returns."""
         if isinstance(observations, (list, tuple)):
             if len(observations) == 0:
                 return self                                        # no frames: the map is unchanged
@@ -308,12 +310,12 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         class_ids = None if features is not None else observations["class_ids"]
         if T > 1 and self.data.is_cuda and not _on_device(observations["depth"]) \
                 and not _on_device(features if features is not None else class_ids):
-            return self._fuse_from_host(pose, observations["depth"], features, class_ids, T, fold)
+            return self._fuse_from_host(pose, observations["depth"], features, class_ids, T, fold, check_ids=check_ids)
         return self._fuse(pose, observations["depth"], features, class_ids, T, fold=fold)
 
     host_chunk_bytes = 256 << 20     # staging per chunk when update_batch is handed frames in HOST memory
 
-    def _fuse_from_host(self, pose, depth, features, class_ids, T, fold=None):
+    def _fuse_from_host(self, pose, depth, features, class_ids, T, fold=None, check_ids=False):
         """T frames that live in host memory (numpy arrays or CPU tensors; pinned memory makes the copies
         asynchronous): the call is cut into chunks of ~host_chunk_bytes, chunk i+1 is copied to one of two device
         staging sets on a copy stream while chunk i is being fused, so the caller sees the PCIe rate of its inputs
@@ -338,7 +340,11 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
                 ids = ids.to(torch.int64)
             other, name = ids, "class_ids"
         per_frame = depth[0].numel() * depth.element_size() + other[0].numel() * other.element_size()
-        chunk = int(max(1, min(T, self.host_chunk_bytes // max(per_frame, 1))))
+        # ~host_chunk_bytes per chunk, but at least four chunks when the call is small enough to fit fewer: the
+        # first chunk's copy is the only one nothing overlaps
+        chunk_bytes = min(self.host_chunk_bytes, max(per_frame * T // 4, 32 << 20))
+        chunk = int(max(1, min(T, chunk_bytes // max(per_frame, 1))))
+        errors = torch.zeros((), dtype=torch.int32, device=device) if check_ids and name == "class_ids" else None
         st = _lib.host_staging(device)
         main = torch.cuda.current_stream(device)
         for slot in st.slots:
@@ -359,7 +365,12 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
             else:
                 self._fuse(pose[s:e], d_buf, None, o_buf if o_buf.dtype == torch.int64 else o_buf.to(torch.int64),
                            e - s, fold=fold)
+                if errors is not None and not self.exact:
+                    # the chunk's sticky error word (bit 1: a class id outside [0, F)), OR-ed on the device
+                    errors |= self._last_ws[:64].view(torch.int32)[_lib.CNT_ERROR]
             slot["free"].record(main)
+        if errors is not None and int(errors.item()) & 2:
+            raise RuntimeError("Class values must be in [0, %d)" % self.feature_size)
         return self
 
     # -- whole-map readers next to the path ------------------------------------------------

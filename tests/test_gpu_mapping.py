@@ -620,6 +620,24 @@ def test_device_class_ids_out_of_range_are_flagged(dev):
     with pytest.raises(RuntimeError, match="Class values"):
         layer.check()
     layer.update_batch(dict(obs, depth=torch.from_numpy(obs["depth"]).to(dev), semantic=torch.full((2, 16, 16, 1), 1, device=dev))).check()
+    # a bad id in the FIRST of several host chunks (one frame per chunk) still raises when the call ends, and a bad
+    # id in the first of several INTERNAL chunks (scratch buffer too small for all frames) survives the later ones
+    T = 4
+    obs4 = dict(position=np.zeros((T, 3), np.float32), yaw=np.zeros(T, np.float32), elevation=np.zeros(T, np.float32),
+                depth=np.full((T, 16, 16, 1), 0.5, np.float32), semantic=np.full((T, 16, 16, 1), 2, np.int64))
+    obs4["semantic"][0, 3, 3, 0] = 9
+    small = SemanticProjectionLayer(exact=False, **kw).to(dev)
+    small.host_chunk_bytes = 16 * 16 * 12
+    with pytest.raises(RuntimeError, match="Class values"):
+        small.update_batch(obs4)
+    from mass_b200 import _lib
+    split = SemanticProjectionLayer(exact=False, **kw).to(dev)
+    L = _lib.lib()
+    nx, ny, nz = split.bins_x.numel(), split.bins_y.numel(), split.bins_z.numel()
+    split.workspace_limit = L.mb_layer_update_min_workspace_bytes(16, 16, nx, ny, nz, 1, 5, _lib.MODE_FAST)
+    split.update_batch(dict(obs4, depth=torch.from_numpy(obs4["depth"]).to(dev), semantic=torch.from_numpy(obs4["semantic"]).to(dev)))
+    with pytest.raises(RuntimeError, match="Class values"):
+        split.check()
 
 
 def test_update_batch_from_host_memory_is_pipelined_and_equal(dev):
