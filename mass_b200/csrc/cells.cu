@@ -707,7 +707,7 @@ k_vox_list(const uint32_t *__restrict__ bitmap, uint32_t nwords, uint32_t *state
 // order, pixel order inside the item).  One thread per segment; an item's records are contiguous.
 __global__ void __launch_bounds__(256, MB_SEG_MINB)
 k_seg_sums(const uint32_t *__restrict__ ival, const uint4 *__restrict__ rec, const uint32_t *__restrict__ seg_start,
-           float2 *__restrict__ segws, size_t cap, const uint32_t *__restrict__ counters)
+           float2 *__restrict__ segws, uint32_t cap, const uint32_t *__restrict__ counters)
 {
     const uint32_t nsegs = counters[MB_CNT_SEGS];
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -728,7 +728,7 @@ k_seg_sums(const uint32_t *__restrict__ ival, const uint4 *__restrict__ rec, con
         for (int k = 0; k < 8; ++k) { W[k] = 0.f; S2[k] = 0.f; }
         for (uint32_t it = beg; it < end; ++it) {
             const uint32_t v = it == beg ? v0 : __ldg(ival + it);
-            const uint4 *pr = rec + (size_t)item_tile(v) * TILE_PIX + item_pos(v);
+            const uint4 *pr = rec + (item_tile(v) * (uint32_t)TILE_PIX + item_pos(v));      // (< 2^28: 32-bit index)
             const uint32_t len = item_len(v);
             for (uint32_t i = 0; i < len; i += 4) {
                 uint4 r[4];
@@ -748,7 +748,7 @@ k_seg_sums(const uint32_t *__restrict__ ival, const uint4 *__restrict__ rec, con
         uint32_t nv0 = 0;
         if (more) nv0 = __ldg(ival + nbeg);             // (its address arrived while the records were being summed)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) segws[(size_t)k * cap + s] = make_float2(W[k], S2[k]);    // slot-major
+        for (int k = 0; k < 8; ++k) segws[(uint32_t)k * cap + s] = make_float2(W[k], S2[k]);    // slot-major (8 * cap < 2^31)
         if (!more) break;
         s = sn; beg = nbeg; end = nend; v0 = nv0;
     }
@@ -789,7 +789,7 @@ k_voxel_sources(const uint32_t *__restrict__ vlist, const uint32_t *__restrict__
 // is used: the kernel lives on memory-level parallelism.
 __global__ void __launch_bounds__(256, MB_VS_MINB)
 k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vseg, const uint32_t *__restrict__ seg_frame,
-                const float2 *__restrict__ segws, size_t cap, CellGrid g, float alpha, int T,
+                const float2 *__restrict__ segws, uint32_t cap, CellGrid g, float alpha, int T,
                 float *__restrict__ gcoef, float *__restrict__ vA, uint32_t *__restrict__ counters)
 {
     extern __shared__ float s_tab[];                  // [warps][2][Tp]
@@ -837,7 +837,7 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vs
                     const uint32_t q = slo[s] + off + lane;
                     if (q < shi[s]) {
                         f[s] = __ldg(seg_frame + q);
-                        x[s] = __ldg(segws + (size_t)(7 - s) * cap + q);
+                        x[s] = __ldg(segws + ((uint32_t)(7 - s) * cap + q));
                     }
                 }
 #pragma unroll
@@ -860,7 +860,7 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vs
                     const uint32_t f = seg_frame[q];
                     float W = 0.f, S2 = 0.f;
                     for (uint32_t mm = m; mm; mm &= mm - 1) {
-                        const float2 x = segws[(size_t)(__ffs(mm) - 1) * cap + q];
+                        const float2 x = segws[(uint32_t)(__ffs(mm) - 1) * cap + q];
                         W += x.x;
                         S2 += x.y;
                     }
@@ -908,7 +908,7 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vs
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     if (slo[s] + off >= shi[s]) continue;
-                    if (f[s] != 0xffffffffu) gcoef[(size_t)(7 - s) * cap + (slo[s] + off + lane)] = tW[f[s]];
+                    if (f[s] != 0xffffffffu) gcoef[(uint32_t)(7 - s) * cap + (slo[s] + off + lane)] = tW[f[s]];
                 }
             }
         } else {
@@ -918,7 +918,7 @@ k_voxel_scalars(const uint32_t *__restrict__ vlist, const uint2 *__restrict__ vs
                 const uint32_t m = slot_mask(v0, v1, v2, s, g);
                 for (uint32_t q = slo[s] + lane; q < shi[s]; q += 32) {
                     const float gv = tW[seg_frame[q]];
-                    for (uint32_t mm = m; mm; mm &= mm - 1) gcoef[(size_t)(__ffs(mm) - 1) * cap + q] = gv;
+                    for (uint32_t mm = m; mm; mm &= mm - 1) gcoef[(uint32_t)(__ffs(mm) - 1) * cap + q] = gv;
                 }
             }
         }
@@ -943,7 +943,7 @@ struct AccArgs {
     const uint32_t *smask, *soff;
     const uint32_t *rstart;        // first item of every run (+ sentinel)
     const float *gcoef;         // [8 slots][cap] coefficient per (slot, segment)
-    size_t cap;
+    uint32_t cap;               // padded pixel count of the chunk (< 2^28, so 8 * cap indices stay 32-bit)
     uint32_t *counters;            // read; the two work-queue heads are written
     MbFeatIndex fi;             // np = pixels per frame
     uint32_t fhw;               // feature rows per frame
@@ -1121,11 +1121,11 @@ __device__ __forceinline__ void accumulate_round(const AccArgs &A, AccSmem &SM)
                     const int lo = s_p2i[warp][qp];
                     const uint32_t v = s_ival[warp][lo], off = qp - s_pre[warp][lo];
                     const uint32_t tile = item_tile(v);
-                    const uint4 r = __ldg(A.rec + (size_t)tile * TILE_PIX + item_pos(v) + off);
+                    const uint4 r = __ldg(A.rec + (tile * (uint32_t)TILE_PIX + item_pos(v) + off));
                     const uint32_t sg = s_seg[warp][lo];
                     float gk[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) gk[k] = __ldg(A.gcoef + (size_t)k * A.cap + sg);
+                    for (int k = 0; k < 8; ++k) gk[k] = __ldg(A.gcoef + ((uint32_t)k * A.cap + sg));
                     splat_weights(r, c);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) c[k] = c[k] * c[k] * gk[k];
@@ -1691,6 +1691,8 @@ int launch_accumulate(cudaStream_t stream, const AccArgs &A)
     MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccSmem)));
     MB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ACC_THREADS, sizeof(AccSmem)));
     if (per_sm < 1) per_sm = 1;
+    static const int cap_per_sm = getenv("MASSB200_ACC_PER_SM") ? atoi(getenv("MASSB200_ACC_PER_SM")) : 0;   // measurement aid
+    if (cap_per_sm > 0 && per_sm > cap_per_sm) per_sm = cap_per_sm;
     kern<<<MB_NUM_SMS * per_sm, ACC_THREADS, sizeof(AccSmem), stream>>>(A);      // persistent: the kernel walks (run, channel block) units
     MB_LAUNCHED();
     return MB_OK;
@@ -2062,7 +2064,9 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
         int per_sm = 1;
         MB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_seg_sums, 256, 0));
         if (per_sm < 1) per_sm = 1;
-        k_seg_sums<<<MB_NUM_SMS * per_sm, 256, 0, stream>>>(ival, b.rec, b.seg_start, b.segws, (size_t)n, b.counters);
+        static const int cap_per_sm = getenv("MASSB200_SCALAR_PER_SM") ? atoi(getenv("MASSB200_SCALAR_PER_SM")) : 0;   // measurement aid
+        if (cap_per_sm > 0 && per_sm > cap_per_sm) per_sm = cap_per_sm;
+        k_seg_sums<<<MB_NUM_SMS * per_sm, 256, 0, stream>>>(ival, b.rec, b.seg_start, b.segws, n, b.counters);
         MB_LAUNCHED();
     }
     {
@@ -2071,15 +2075,17 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
         int per_sm = 1;
         MB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_voxel_scalars, 256, smem));
         if (per_sm < 1) per_sm = 1;
+        static const int cap_per_sm = getenv("MASSB200_SCALAR_PER_SM") ? atoi(getenv("MASSB200_SCALAR_PER_SM")) : 0;   // measurement aid
+        if (cap_per_sm > 0 && per_sm > cap_per_sm) per_sm = cap_per_sm;
         if (side != nullptr) MB_CHECK_CUDA(cudaStreamWaitEvent(stream, side->sources_done, 0));
-        k_voxel_scalars<<<MB_NUM_SMS * per_sm, 256, smem, stream>>>(b.vlist, b.vseg, b.seg_frame, b.segws, (size_t)n, g, alpha, T,
+        k_voxel_scalars<<<MB_NUM_SMS * per_sm, 256, smem, stream>>>(b.vlist, b.vseg, b.seg_frame, b.segws, n, g, alpha, T,
                                                                     b.gcoef, b.vA, b.counters);
         MB_LAUNCHED();
     }
     // K7, K8 (one round unless the runs outgrow the P buffer)
     AccArgs A;
     A.ikey = ikey; A.ival = ival; A.tg = tg; A.rec = b.rec; A.smask = b.smask; A.soff = b.soff; A.rstart = b.rstart;
-    A.gcoef = b.gcoef; A.cap = (size_t)n; A.counters = b.counters;
+    A.gcoef = b.gcoef; A.cap = n; A.counters = b.counters;
     A.fi = MbFeatIndex{ npix, (uint32_t)W, (uint32_t)(H / fh), (uint32_t)(W / fw), (uint32_t)fw };
     A.fhw = (uint32_t)fh * (uint32_t)fw;
     A.features = features; A.class_ids = class_ids; A.F = F; A.P = b.P; A.run_cap = run_cap;

@@ -91,8 +91,27 @@ def main():
         torch.cuda.synchronize()
         return ev0.elapsed_time(ev1) / reps
 
+    def pipelined(nbatches=20):
+        """steady state: half batches alternate between the two streams, each stream's calls back to back"""
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0, s1 = streams
+        ev0.record(torch.cuda.current_stream())
+        s0.wait_event(ev0), s1.wait_event(ev0)
+        for i in range(nbatches):
+            with torch.cuda.stream(streams[i % 2]):
+                layers[i % 2].update_prepared(halves[i % 2])
+        d0, d1 = torch.cuda.Event(), torch.cuda.Event()
+        d0.record(s0), d1.record(s1)
+        torch.cuda.current_stream().wait_event(d0), torch.cuda.current_stream().wait_event(d1)
+        ev1.record(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / (nbatches / 2)
+
     for _ in range(2):
         run(False, 0)
+    pipelined()
+    print("two streams, 20 half batches alternating: %.3f ms per 500 frames" % pipelined())
     print("graph, 2 x 250 frames back to back:      %.3f ms per 500 frames" % graph_time(False))
     print("graph, 2 x 250 frames on two branches:   %.3f ms per 500 frames" % graph_time(True))
     print("one stream, 2 x 250 frames back to back: %.3f ms per 500 frames" % run(False, 0))
