@@ -56,9 +56,8 @@ def predict_scene_differences(semantic_projection_layer0, semantic_projection_la
             candidate_object, feature_map=resnet_projection_layer1, **kw)
         if len(conf0) == 0 or len(conf1) == 0:
             continue
-        goal0, goal1 = torch.stack(goal0, dim=0), torch.stack(goal1, dim=0)
         # the assignment of a class is a pure function of the four maps: the agent's loop (agent.py:424-450) asks
-        # again after every rearranged object, so it is kept until a map changes
+        # again after every rearranged object, so it is kept -- with the stacked goal tensors -- until a map changes
         state = tuple(None if m is None else (id(m), m.map_state()) for m in
                       (semantic_projection_layer0, semantic_projection_layer1, resnet_projection_layer0,
                        resnet_projection_layer1))
@@ -69,9 +68,10 @@ def predict_scene_differences(semantic_projection_layer0, semantic_projection_la
         key = (candidate_object, float(confidence_threshold), int(contour_padding), float(contour_threshold),
                float(distance_threshold))
         if key not in memo[1]:
+            goal0, goal1 = torch.stack(goal0, dim=0), torch.stack(goal1, dim=0)
             rows, cols, distance = match_instances(feature0, feature1, goal0, goal1, size0, size1, object_pickable)
-            memo[1][key] = (rows, cols, (distance > distance_threshold).cpu().numpy())
-        rows, cols, far = memo[1][key]
+            memo[1][key] = (rows, cols, (distance > distance_threshold).cpu().numpy(), goal0, goal1)
+        rows, cols, far, goal0, goal1 = memo[1][key]
         for instance0, instance1 in zip(rows, cols):
             if (object_pickable and far[instance0, instance1]) or object_openable:
                 object_to_move = candidate_object
