@@ -244,7 +244,8 @@ int mb_lsap(void *stream, const float *cost32, const double *cost64, int n, int 
             int32_t *status, void *workspace, size_t workspace_bytes);
 
 /* Synchronises `stream` and returns the sticky error bits the batched kernels left in the workspace of
- * the last MB_MODE_FAST call: 0 = fine; bit 0 = more accumulate runs than the planned rounds hold (an
+ * the last MB_MODE_FAST call (the bits of ALL internal chunks of that call: a later chunk does not clear what an
+ * earlier one set): 0 = fine; bit 0 = more accumulate runs than the planned rounds hold (an
  * internal invariant: never expected, the map is then not trustworthy); bit 1 = a class id outside
  * [0, F) in `class_ids` (torch.nn.functional.one_hot raises on it in the reference,
  * mass/nn/applications/semantic_projection_layer.py:203-214; the kernel adds nothing for that pixel). */
