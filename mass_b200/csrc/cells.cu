@@ -122,7 +122,7 @@ __device__ __forceinline__ int find_cell(const uint32_t *__restrict__ ucell, uin
 // (cell, frame) segment averages ~4 pixels), so what leaves the tile is an ITEM list -- (cell key, tile, first
 // slot, length <= 16) -- a few times shorter than the pixel list; the pixel records are written in grouped
 // order, so an item's pixels are contiguous.  Grouping: per round, match.any finds the lanes that share a
-// key; the first of them looks the key up in (or adds it to) the warp's 512-slot hash table; a pixel's rank
+// key; the first of them looks the key up in (or adds it to) the warp's 256-slot hash table; a pixel's rank
 // inside its group is the group's count so far plus its rank among the round's matching lanes, i.e. the
 // pixels of a group are in (row, column) order.  Which slot a key gets depends on the probing races of one
 // round's leaders, so the ORDER OF GROUPS inside a tile may differ run to run; nothing downstream depends on

@@ -762,3 +762,24 @@ def test_batched_large_map_without_dense_cell_table(dev, oracle):
     got = layer.data.cpu().numpy()
     assert np.array_equal((got != 0).any(-1), (ref != 0).any(-1))
     assert_close_rel(got, ref)
+
+
+def test_batched_frames_with_more_than_4096_tiles(dev, oracle):
+    """Tile ids are turned into (frame, tile row, tile column) by a multiply-high that is exact for divisors up to 4096
+    and by a plain division beyond: a 1040 x 1024 camera has 130 x 32 = 4160 tiles per frame, two such frames must still
+    land where the oracle puts them (fast mode; low-resolution features keep the host arrays small)."""
+    H, W, T, F = 1040, 1024, 2, 3
+    kw = dict(camera_height=H, camera_width=W, vertical_fov=90.0, map_height=72, map_width=80, map_depth=30,
+              feature_size=F, grid_resolution=0.1, interpolation_weight=0.5, origin_z=0.4)
+    rng = np.random.default_rng(4160)
+    frames = _random_frames(rng, T, H, W, H // 8, W // 8, F, depth_lo=0.4, depth_hi=3.5)
+    # smooth depth (a slanted wall) so that neighbouring pixels share cells, as in a real frame
+    yy, xx = np.mgrid[0:H, 0:W]
+    for t in range(T):
+        frames["depth"][t, :, :, 0] = (1.0 + 0.8 * xx / W + 0.5 * yy / H + 0.3 * t).astype(np.float32)
+    ref = _oracle_run(oracle, kw, frames, T)
+    layer = make_layer(kw, dev, exact=False)
+    layer.update_batch(frames).check()
+    got = layer.data.cpu().numpy()
+    assert np.array_equal((got != 0).any(-1), (ref != 0).any(-1))
+    assert_close_rel(got, ref)
