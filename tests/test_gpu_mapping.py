@@ -343,12 +343,14 @@ def test_batched_many_pixels_per_cell(dev, oracle):
         assert_close_rel(got, ref)
 
 
-def test_batched_small_workspace_rounds_and_chunks(dev, oracle):
+@pytest.mark.parametrize("F", [10, 1])
+def test_batched_small_workspace_rounds_and_chunks(dev, oracle, F):
     """Random depths put nearly every pixel in its own cell (the worst case for the run buffer).  With
     the smallest one-chunk workspace the feature pass takes many rounds; with less the call is split into
-    chunks of fewer frames; with less than one frame's worth it fails loudly."""
+    chunks of fewer frames; with less than one frame's worth it fails loudly.  (F = 1: the single-channel
+    accumulate kernel and its own overflow rounds.)"""
     from mass_b200 import _lib
-    H, W, T, F = 40, 56, 6, 10
+    H, W, T = 40, 56, 6
     kw = dict(camera_height=H, camera_width=W, vertical_fov=90.0, map_height=60, map_width=64, map_depth=24,
               feature_size=F, grid_resolution=0.1, interpolation_weight=0.5, origin_z=0.3)
     rng = np.random.default_rng(77)
