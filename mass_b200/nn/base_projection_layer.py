@@ -81,9 +81,28 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         """Zero the map and re-centre it.  Reference: base_projection_layer.py:183-235."""
         self.origin_x, self.origin_y, self.origin_z = origin_x, origin_y, origin_z
         self.data.zero_()
-        self.bins_x.copy_(_edges(origin_x, self.map_width, self.grid_resolution))
-        self.bins_y.copy_(_edges(origin_y, self.map_height, self.grid_resolution))
-        self.bins_z.copy_(_edges(origin_z, self.map_depth, self.grid_resolution))
+        edges = (_edges(origin_x, self.map_width, self.grid_resolution),
+                 _edges(origin_y, self.map_height, self.grid_resolution),
+                 _edges(origin_z, self.map_depth, self.grid_resolution))
+        bins = (self.bins_x, self.bins_y, self.bins_z)
+        if not self.bins_x.is_cuda:
+            for b, e in zip(bins, edges):
+                b.copy_(e)
+            return
+        # On the GPU the three tables go through pinned staging and asynchronous copies: a copy from pageable memory
+        # blocks the host until everything queued before it (the memset of a map of up to 13.5 GiB just above, the
+        # previous episode's kernels) has finished, five layers in a row at every episode start.
+        device = self.bins_x.device
+        st = getattr(self, "_edge_staging", None)
+        if st is None or st["device"] != device:
+            st = dict(device=device, pinned=[torch.empty(b.numel(), dtype=torch.float32).pin_memory() for b in bins],
+                      done=torch.cuda.Event())
+            self._edge_staging = st
+        st["done"].synchronize()                   # the previous reset's copies have left the staging buffers
+        for b, pinned, e in zip(bins, st["pinned"], edges):
+            pinned.copy_(e)
+            b.copy_(pinned, non_blocking=True)
+        st["done"].record(torch.cuda.current_stream(device))
 
     def get_feature_map(self):
         return self.data
