@@ -1971,8 +1971,10 @@ constexpr int MAX_DEVICES = 64;
 SideBranch g_side[MAX_DEVICES];
 std::mutex g_side_mutex;
 
-// the calling device's side branch, or null (forking disabled / device index out of range)
-int side_branch(SideBranch **out)
+// the calling device's side branch, or null (forking disabled / device index out of range / the branch would have to
+// be created while the caller's stream is being captured: stream and event creation stay out of captures, that call
+// runs in line)
+int side_branch(cudaStream_t caller, SideBranch **out)
 {
     static const bool no_fork = getenv("MASSB200_NO_FORK") != nullptr;
     *out = nullptr;
@@ -1982,6 +1984,9 @@ int side_branch(SideBranch **out)
     if (dev < 0 || dev >= MAX_DEVICES) return MB_OK;
     SideBranch &sb = g_side[dev];
     if (sb.stream == nullptr) {
+        cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+        MB_CHECK_CUDA(cudaStreamIsCapturing(caller, &capturing));
+        if (capturing != cudaStreamCaptureStatusNone) return MB_OK;
         cudaStream_t st;
         MB_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         cudaEvent_t *ev[4] = { &sb.fork, &sb.ctab_done, &sb.indexed, &sb.sources_done };
@@ -2159,7 +2164,7 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
     // the side branch's events are shared by all callers on this device: one enqueue at a time
     std::lock_guard<std::mutex> side_lock(g_side_mutex);
     SideBranch *side = nullptr;
-    if ((rc = side_branch(&side))) return rc;
+    if ((rc = side_branch(stream, &side))) return rc;
     if (side != nullptr && b.ctab) {
         // the dense cell table is cleared next to the front end (only the index sweep needs it)
         MB_CHECK_CUDA(cudaEventRecord(side->fork, stream));

@@ -77,6 +77,17 @@ class BaseProjectionLayer(nn.Module, ProjectionLayer):
         self.workspace_limit = None      # optional cap (bytes) on the device scratch buffer of update()
 
     # -- state ---------------------------------------------------------------------------------
+    _TRANSIENT = ("_frame_graphs", "_edge_staging", "_last_ws", "_last_ws_use", "_find_cache", "_match_cache")
+
+    def __getstate__(self):
+        """copy.deepcopy / pickle: captured CUDA graphs, events, pinned staging and memoised query results belong to
+        this object and its device; a copy starts without them (they are rebuilt on demand)."""
+        state = self.__dict__.copy()
+        for key in self._TRANSIENT:
+            state.pop(key, None)
+        state["_frame_graphs"] = {}
+        return state
+
     def reset(self, origin_y: float = 0.0, origin_x: float = 0.0, origin_z: float = 0.0):
         """Zero the map and re-centre it.  Reference: base_projection_layer.py:183-235."""
         self.origin_x, self.origin_y, self.origin_z = origin_x, origin_y, origin_z

@@ -100,3 +100,21 @@ def test_new_entry_points_fail_loudly_without_cuda():
                depth=np.ones((1, 4, 4, 1), np.float32), semantic=np.ones((1, 4, 4, 1), np.int64))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         sharded.fold_frames(L, obs)
+
+
+def test_layer_deepcopy_drops_transient_state():
+    """A copied layer carries the buffers and settings, not the device-bound caches (graphs, events, memoised queries)."""
+    import copy
+    import torch
+    from mass_b200.nn.applications.semantic_projection_layer import SemanticProjectionLayer
+    L = SemanticProjectionLayer(camera_height=8, camera_width=8, map_height=6, map_width=6, map_depth=4, feature_size=3,
+                                exact=False)
+    L._find_cache = ("state", {"k": object()})
+    L._edge_staging = dict(done=object())
+    L.data[1, 2, 3, 0] = 2.0
+    C = copy.deepcopy(L)
+    assert torch.equal(C.data, L.data) and C.data.data_ptr() != L.data.data_ptr()
+    assert torch.equal(C.bins_x, L.bins_x) and C.exact is False and C.feature_size == 3
+    assert not hasattr(C, "_find_cache") and not hasattr(C, "_edge_staging") and C._frame_graphs == {}
+    C.reset(origin_x=0.5)
+    assert float(C.data.abs().sum()) == 0.0 and float(L.data.abs().sum()) == 2.0
