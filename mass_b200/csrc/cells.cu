@@ -144,6 +144,9 @@ constexpr int TILE_W = 32, TILE_H = 8, TILE_PIX = TILE_W * TILE_H;
 #ifndef MB_ACC_U21
 #define MB_ACC_U21 8
 #endif
+#ifndef MB_SEG_LONG_ITEMS
+#define MB_SEG_LONG_ITEMS 4
+#endif
 #ifndef MB_SEG_MINB
 #define MB_SEG_MINB 5
 #endif
@@ -154,6 +157,7 @@ constexpr int WHASH = MB_WHASH;                  // hash slots per warp (>= pixe
 constexpr int WHASH_BITS = MB_WHASH == 256 ? 8 : MB_WHASH == 512 ? 9 : MB_WHASH == 1024 ? 10 : -1;
 static_assert(WHASH_BITS > 0, "MB_WHASH must be 256, 512 or 1024");
 constexpr int ITEM_MAX = 16;                     // pixels per item
+constexpr int SEG_LONG_ITEMS = MB_SEG_LONG_ITEMS; // segments of more items than this are summed by a warp, not a thread
 constexpr uint32_t HASH_EMPTY = 0xffffffffu;
 constexpr int TASK_ITEMS = MB_TASK_ITEMS;        // most items of an accumulate run (one warp task)
 constexpr int TASK_WORDS = TASK_ITEMS / 32;      // items per lane when a warp loads a task
@@ -707,7 +711,7 @@ k_vox_list(const uint32_t *__restrict__ bitmap, uint32_t nwords, uint32_t *state
 // order, pixel order inside the item).  One thread per segment; an item's records are contiguous.
 __global__ void __launch_bounds__(256, MB_SEG_MINB)
 k_seg_sums(const uint32_t *__restrict__ ival, const uint4 *__restrict__ rec, const uint32_t *__restrict__ seg_start,
-           float2 *__restrict__ segws, uint32_t cap, const uint32_t *__restrict__ counters)
+           float2 *__restrict__ segws, uint32_t cap, uint32_t *__restrict__ counters, uint32_t *__restrict__ long_segs)
 {
     const uint32_t nsegs = counters[MB_CNT_SEGS];
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -723,6 +727,14 @@ k_seg_sums(const uint32_t *__restrict__ ival, const uint4 *__restrict__ rec, con
         const bool more = sn < nsegs;
         uint32_t nbeg = 0, nend = 0;
         if (more) { nbeg = __ldg(seg_start + sn); nend = __ldg(seg_start + sn + 1); }
+        // A segment of many items (a cell that fills a large part of a frame: a surface a few centimetres from the
+        // camera puts thousands of pixels into one cell) would keep this one thread busy for milliseconds while the rest
+        // of the grid has long finished: such segments go on a list and are summed by whole warps (k_seg_sums_long).
+        // (this thread then writes zeros for it, which the warp kernel, next in the stream, overwrites)
+        if (end - beg > (uint32_t)SEG_LONG_ITEMS) {
+            long_segs[atomicAdd(&counters[MB_CNT_LONGSEGS], 1u)] = s;
+            end = beg;
+        }
         float W[8], S2[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { W[k] = 0.f; S2[k] = 0.f; }
@@ -751,6 +763,49 @@ k_seg_sums(const uint32_t *__restrict__ ival, const uint4 *__restrict__ rec, con
         for (int k = 0; k < 8; ++k) segws[(uint32_t)k * cap + s] = make_float2(W[k], S2[k]);    // slot-major (8 * cap < 2^31)
         if (!more) break;
         s = sn; beg = nbeg; end = nend; v0 = nv0;
+    }
+}
+
+// K5b: the segments k_seg_sums put aside, one WARP each: lanes take the segment's items in turn (<= 16 pixels per
+// item), then the 16 sums are reduced over the warp by a fixed butterfly.  The order of the additions differs from the
+// one-thread order (it is still fixed, so results stay reproducible).
+__global__ void __launch_bounds__(256)
+k_seg_sums_long(const uint32_t *__restrict__ ival, const uint4 *__restrict__ rec, const uint32_t *__restrict__ seg_start,
+                float2 *__restrict__ segws, uint32_t cap, const uint32_t *__restrict__ counters,
+                const uint32_t *__restrict__ long_segs)
+{
+    const uint32_t nlong = counters[MB_CNT_LONGSEGS];
+    const int lane = threadIdx.x & 31;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j = wid; j < nlong; j += nw) {
+        const uint32_t s = long_segs[j];
+        const uint32_t beg = __ldg(seg_start + s), end = __ldg(seg_start + s + 1);
+        float W[8], S2[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { W[k] = 0.f; S2[k] = 0.f; }
+        for (uint32_t it = beg + lane; it < end; it += 32) {
+            const uint32_t v = __ldg(ival + it);
+            const uint4 *pr = rec + (item_tile(v) * (uint32_t)TILE_PIX + item_pos(v));
+            const uint32_t len = item_len(v);
+            for (uint32_t i = 0; i < len; ++i) {
+                const uint4 r = __ldg(pr + i);
+                float w[8];
+                splat_weights(r, w);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { W[k] += w[k]; S2[k] = fmaf(w[k], w[k], S2[k]); }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                W[k] += __shfl_xor_sync(FULL, W[k], d);
+                S2[k] += __shfl_xor_sync(FULL, S2[k], d);
+            }
+        // every lane holds the totals; lane k writes slot k
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (lane == k) segws[(uint32_t)k * cap + s] = make_float2(W[k], S2[k]);
     }
 }
 
@@ -1739,6 +1794,7 @@ struct CellBuffers {
     float *vA;
     uint2 *vseg, *vrun;
     uint32_t *vslot;            // sparse-partial row of every touched voxel (fold into a partial)
+    uint32_t *long_segs;        // segments put aside by k_seg_sums (more than SEG_LONG_ITEMS items each)
     int *ctab;                  // dense cell key -> unique cell index (or null: binary search)
     char *scan_ws, *sort_ws;
     size_t scan_bytes, sort_bytes;
@@ -1787,6 +1843,7 @@ size_t carve_cells(CellBuffers &b, void *ws, size_t bytes, uint32_t n, const Cel
     b.vseg = a.take<uint2>((vcap + 1) * 8);
     b.vrun = a.take<uint2>((vcap + 1) * 8);
     b.vslot = a.take<uint32_t>(vcap + 1);
+    b.long_segs = a.take<uint32_t>((size_t)n / (SEG_LONG_ITEMS + 1) + 16);      // (items <= pixels <= n)
     {
         // dense lookup table over the extended grid when it is not out of proportion to the batch
         // (it is re-initialised by every call: 4 bytes per cell of the extended grid; a one-frame call on a large
@@ -2243,7 +2300,9 @@ int mbk_batch_update(cudaStream_t stream, const float *rays, const float *depth,
         if (per_sm < 1) per_sm = 1;
         static const int cap_per_sm = getenv("MASSB200_SCALAR_PER_SM") ? atoi(getenv("MASSB200_SCALAR_PER_SM")) : 0;   // measurement aid
         if (cap_per_sm > 0 && per_sm > cap_per_sm) per_sm = cap_per_sm;
-        k_seg_sums<<<MB_NUM_SMS * per_sm, 256, 0, stream>>>(ival, b.rec, b.seg_start, b.segws, n, b.counters);
+        k_seg_sums<<<MB_NUM_SMS * per_sm, 256, 0, stream>>>(ival, b.rec, b.seg_start, b.segws, n, b.counters, b.long_segs);
+        MB_LAUNCHED();
+        k_seg_sums_long<<<MB_NUM_SMS * 8, 256, 0, stream>>>(ival, b.rec, b.seg_start, b.segws, n, b.counters, b.long_segs);
         MB_LAUNCHED();
     }
     {

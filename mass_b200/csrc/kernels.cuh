@@ -12,6 +12,7 @@ constexpr int MB_CNT_ERROR = 5;      // sticky error bits (read by mb_layer_upda
 constexpr int MB_CNT_VOX = 6;        // batched path: touched voxels
 constexpr int MB_CNT_VOXFRAMES = 7;  // batched path: (touched voxel, frame) pairs = sum over the chunk's frames of U_f
 constexpr int MB_CNT_TASKQ = 8;      // batched path: work-queue heads: +0/+1 accumulate (used in turn by its launches), +2 voxel scalars
+constexpr int MB_CNT_LONGSEGS = 11; // batched path: segments of more than SEG_LONG_ITEMS items, summed by whole warps
 constexpr int MB_NUM_COUNTERS = 16;
 constexpr int MB_MAX_CHUNK_FRAMES = 1024;   // frames fused per batched chunk (per-voxel frame table in shared memory)
 
