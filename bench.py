@@ -49,9 +49,10 @@ C2_FRAMES = 500
 # NOT measured by this script: dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu pass named
 # below (same command, same workload, the build named there).  bench.py only repeats them so that the JSON line
 # carries the traffic next to the algorithmic bytes; every other figure of the line is measured live.
-TRAFFIC_SOURCE = "profiles/r03z_step_traffic.txt (ncu pass of the final round-2 build; NOT measured in this run)"
+TRAFFIC_SOURCE = ("profiles/r03z_step_traffic.txt (ncu pass of the round-2 build just before k_seg_sums_long was added: "
+                  "22 of the final 23 launches, the 23rd moves no data on this workload; NOT measured in this run)")
 ACCUMULATE_DRAM_BYTES_PER_LAUNCH = 6842.1e6 + 171.4e6     # the k_cell_accumulate launch of one step
-STEP_DRAM_BYTES = 9042.6e6 + 1459.6e6                       # all 22 launches of one step
+STEP_DRAM_BYTES = 9042.6e6 + 1459.6e6                       # all 22 launches of one step of that build
 
 
 def algorithmic_bytes_per_frame(h, w, fh, fw, F, touched_row_floats, feature_bytes=4.0):
